@@ -1,0 +1,66 @@
+// Shared helpers for the libeitb200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/eitb200.h"
+
+#define EITB_NUM_SMS 148
+
+#define EITB_CHECK_LAUNCH()                                    \
+    do {                                                       \
+        if (cudaGetLastError() != cudaSuccess) return EITB_ERR_LAUNCH; \
+    } while (0)
+
+static inline int eitb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// grid for a grid-stride kernel: enough CTAs to fill the chip, capped by the work
+static inline int eitb_grid(long long work_items, int threads, int ctas_per_sm) {
+    long long need = (work_items + threads - 1) / threads;
+    long long cap = (long long)EITB_NUM_SMS * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_uint2(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_int4(int4* p, int4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_uint2(uint2* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// u8/255 rounded once to the output type, the way torch does x.to(dtype) / 255
+// (division evaluated in fp32, then rounded to the storage type).
+template <typename T> __device__ __forceinline__ T unit_from_u8(int u);
+template <> __device__ __forceinline__ float unit_from_u8<float>(int u) { return __fdiv_rn((float)u, 255.0f); }
+template <> __device__ __forceinline__ __half unit_from_u8<__half>(int u) { return __float2half_rn(__fdiv_rn((float)u, 255.0f)); }
+template <> __device__ __forceinline__ __nv_bfloat16 unit_from_u8<__nv_bfloat16>(int u) { return __float2bfloat16_rn(__fdiv_rn((float)u, 255.0f)); }

@@ -1,0 +1,226 @@
+// K6: mask decode (coef x proto contraction, crop, x4 bilinear upsample, threshold) fused with
+// the label-image overlay.
+//
+// Restates ultralytics process_mask(upsample=True) (call site
+// ai_tools.py:153) and the reference's create_segmentations_masks +
+// overlay_segmentation_masks (utils.py:437-523, 395-434), whose saturating colour adds
+// reduce to a per-pixel OR of 3-bit colour codes (bone 7, muscle 1, lung 6, adipose 3).
+//
+// One CTA owns a 16x16 tile of prototype pixels (+1 halo, replicated at the image frame like
+// the clamped source index of F.interpolate) = 64x64 output pixels.  The prototype tile is
+// staged once in shared memory as fp32; instances whose crop box touches the tile are
+// processed 8 at a time: logits for the 18x18 halo tile (fp32 FMA, crop applied), then every
+// thread interpolates its own 16 output pixels (fixed weights .125/.375/.625/.875) and ORs the
+// class code into registers.  Per-instance fp32 masks never exist in HBM: traffic is the
+// prototype read + one u8 code per pixel.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PT = 16;          // prototype pixels per tile side
+constexpr int HT = PT + 2;      // with halo
+constexpr int HP = HT * HT;     // 324
+constexpr int G = 8;            // instances per chunk
+constexpr int kThreads = 256;
+constexpr int kMaxDet = 1024;
+
+template <typename T> __device__ __forceinline__ float ld_f32(const T* p);
+template <> __device__ __forceinline__ float ld_f32<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_f32<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float ld_f32<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+
+__device__ __forceinline__ int class_code(float cls) {
+    // class id -> colour code (utils.py:468-473, 498-507); other ids are skipped
+    const int c = (int)cls;
+    return c == 0 ? EITB_CODE_BONE : c == 1 ? EITB_CODE_MUSCLE : c == 2 ? EITB_CODE_LUNG : c == 3 ? EITB_CODE_ADIPOSE : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n_det, int max_det,
+                   const T* __restrict__ protos, int nm, int mh, int mw, int H, int W, int tiles_x,
+                   int tiles_per_img, int variant, uint8_t* __restrict__ code, int32_t* __restrict__ inst_area,
+                   uint8_t* __restrict__ inst_bits) {
+    extern __shared__ __align__(16) float smem[];
+    float* P = smem;                         // [nm][HP]
+    float* Ls = P + nm * HP;                 // [G][HP]
+    float* sc = Ls + G * HP;                 // [G][nm]
+    float* sbox = sc + G * nm;               // [G][4]  crop box in prototype pixels
+    int* sinfo = reinterpret_cast<int*>(sbox + G * 4);   // [G][2]  code, instance index
+    int* act = sinfo + G * 2;                // [max_det]
+    __shared__ int s_nact;
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / tiles_per_img;
+    const int tile = blockIdx.x - b * tiles_per_img;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int D = 6 + nm;
+    const float* dimg = dets + (long long)b * max_det * D;
+    const int n = min(n_det[b], max_det);
+    const float rx = (float)((double)mw / (double)W), ry = (float)((double)mh / (double)H);
+    if (tid == 0) s_nact = 0;
+
+    // ---- stage the prototype tile (halo replicated at the frame)
+    {
+        const T* pimg = protos + (long long)b * nm * mh * mw;
+        for (int idx = tid; idx < nm * HP; idx += kThreads) {
+            const int k = idx / HP, h = idx - k * HP;
+            const int hy = h / HT, hx = h - hy * HT;
+            const int py = min(max(ty * PT - 1 + hy, 0), mh - 1);
+            const int px = min(max(tx * PT - 1 + hx, 0), mw - 1);
+            P[idx] = ld_f32(pimg + ((long long)k * mh + py) * mw + px);
+        }
+    }
+    __syncthreads();
+
+    // ---- instances whose crop box reaches this tile's halo
+    {
+        const float cx_lo = (float)max(tx * PT - 1, 0), cx_hi = (float)min(tx * PT + PT, mw - 1);
+        const float cy_lo = (float)max(ty * PT - 1, 0), cy_hi = (float)min(ty * PT + PT, mh - 1);
+        for (int i = tid; i < n; i += kThreads) {
+            const float* d = dimg + (long long)i * D;
+            const float x1 = d[0] * rx, y1 = d[1] * ry, x2 = d[2] * rx, y2 = d[3] * ry;
+            if (x2 > cx_lo && x1 <= cx_hi && y2 > cy_lo && y1 <= cy_hi && class_code(d[5]) != 0)
+                act[atomicAdd(&s_nact, 1)] = i;
+        }
+    }
+    __syncthreads();
+    const int nact = s_nact;
+
+    // this thread's 16 output pixels: row r of the tile, columns 16*cg .. 16*cg+15
+    const int r = tid >> 2, cg = tid & 3;
+    const int jy = r & 3;
+    const int hy0 = (r >> 2) + (jy >= 2);
+    const float ly = jy == 0 ? 0.625f : jy == 1 ? 0.875f : jy == 2 ? 0.125f : 0.375f;
+    const int oy = ty * (PT * 4) + r;
+    const int ox0 = tx * (PT * 4) + cg * 16;
+    const bool in_img = oy < H && ox0 < W;
+    uint32_t codes[4] = {0, 0, 0, 0};        // 16 x u8
+    const float thr = variant == 1 ? 0.5f : 0.0f;
+
+    for (int c0 = 0; c0 < nact; c0 += G) {
+        const int ng = min(G, nact - c0);
+        for (int i = tid; i < ng * nm; i += kThreads) {
+            const int g = i / nm, k = i - g * nm;
+            sc[g * nm + k] = dimg[(long long)act[c0 + g] * D + 6 + k];
+        }
+        if (tid < ng) {
+            const float* d = dimg + (long long)act[c0 + tid] * D;
+            sbox[tid * 4 + 0] = d[0] * rx; sbox[tid * 4 + 1] = d[1] * ry;
+            sbox[tid * 4 + 2] = d[2] * rx; sbox[tid * 4 + 3] = d[3] * ry;
+            sinfo[tid * 2] = class_code(d[5]);
+            sinfo[tid * 2 + 1] = act[c0 + tid];
+        }
+        __syncthreads();
+        // logits of the halo tile for the chunk, cropped to each instance's box
+        for (int h = tid; h < HP; h += kThreads) {
+            float acc[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g] = 0.f;
+            for (int k = 0; k < nm; ++k) {
+                const float p = P[k * HP + h];
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[g] = fmaf(sc[g * nm + k], p, acc[g]);
+            }
+            const int hy = h / HT, hx = h - hy * HT;
+            const float fy = (float)min(max(ty * PT - 1 + hy, 0), mh - 1);
+            const float fx = (float)min(max(tx * PT - 1 + hx, 0), mw - 1);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (g < ng) {
+                    const bool in = fx >= sbox[g * 4] && fx < sbox[g * 4 + 2] && fy >= sbox[g * 4 + 1] && fy < sbox[g * 4 + 3];
+                    float v = acc[g];
+                    if (variant == 1) v = 1.f / (1.f + expf(-v));
+                    Ls[g * HP + h] = in ? v : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+        // x4 bilinear (align_corners=False) + threshold + OR
+        for (int g = 0; g < ng; ++g) {
+            const float* L0 = Ls + g * HP + hy0 * HT + cg * 4;
+            const float* L1 = L0 + HT;
+            float V[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) V[i] = (1.f - ly) * L0[i] + ly * L1[i];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int mm = j >> 2, jj = j & 3;
+                const int x0 = mm + (jj >= 2);
+                const float lx = jj == 0 ? 0.625f : jj == 1 ? 0.875f : jj == 2 ? 0.125f : 0.375f;
+                const float v = (1.f - lx) * V[x0] + lx * V[x0 + 1];
+                bits |= (v > thr ? 1u : 0u) << j;
+            }
+            if (!in_img) bits = 0;
+            const uint32_t cc = (uint32_t)sinfo[g * 2];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if ((bits >> j) & 1u) codes[j >> 2] |= cc << (8 * (j & 3));
+            if (inst_bits && in_img) {
+                const long long o = (((long long)b * max_det + sinfo[g * 2 + 1]) * H + oy) * (W >> 3) + (ox0 >> 3);
+                *reinterpret_cast<uint16_t*>(inst_bits + o) = (uint16_t)bits;
+            }
+            if (inst_area) {
+                const int cnt = warp_sum(__popc(bits));
+                if ((tid & 31) == 0 && cnt) atomicAdd(inst_area + (long long)b * max_det + sinfo[g * 2 + 1], cnt);
+            }
+        }
+        __syncthreads();
+    }
+    if (in_img)
+        st_stream_int4(reinterpret_cast<int4*>(code + ((long long)b * H + oy) * W + ox0),
+                       make_int4((int)codes[0], (int)codes[1], (int)codes[2], (int)codes[3]));
+}
+
+size_t decode_smem(int nm, int max_det) {
+    return (size_t)(nm * HP + G * HP + G * nm + G * 4) * 4 + G * 2 * 4 + (size_t)max_det * 4;
+}
+
+template <typename T>
+int launch_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos, int B, int nm, int mh,
+                  int mw, int H, int W, int variant, uint8_t* code, int32_t* inst_area, uint8_t* inst_bits,
+                  cudaStream_t s) {
+    const int tiles_x = eitb_div_up(mw, PT), tiles_y = eitb_div_up(mh, PT);
+    const size_t smem = decode_smem(nm, max_det);
+    if (smem > 200 * 1024) return EITB_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(mask_decode_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return EITB_ERR_LAUNCH;
+    const long long grid = (long long)B * tiles_x * tiles_y;
+    if (grid > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
+    mask_decode_kernel<T><<<(unsigned)grid, kThreads, smem, s>>>(dets, n_det, max_det, (const T*)protos, nm, mh, mw, H, W,
+                                                                 tiles_x, tiles_x * tiles_y, variant, code, inst_area,
+                                                                 inst_bits);
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
+}
+
+}  // namespace
+
+extern "C" size_t eitb_mask_decode_workspace_bytes(int B, int max_det, int nm, int mh, int mw) {
+    (void)B; (void)max_det; (void)nm; (void)mh; (void)mw;
+    return 0;
+}
+
+extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos,
+                                int proto_dtype, int B, int nm, int mh, int mw, int H, int W, int variant,
+                                uint8_t* code, int32_t* inst_area, uint8_t* inst_bits, void* ws, size_t ws_bytes,
+                                eitb_stream_t stream) {
+    (void)ws; (void)ws_bytes;
+    if (!dets || !n_det || !protos || !code || B < 0 || nm <= 0 || mh <= 0 || mw <= 0 || max_det <= 0 ||
+        max_det > kMaxDet || (variant != 0 && variant != 1))
+        return EITB_ERR_BAD_ARG;
+    if (H != 4 * mh || W != 4 * mw || (mw % 4) != 0) return EITB_ERR_UNSUPPORTED;
+    if (B == 0) return EITB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (inst_area && cudaMemsetAsync(inst_area, 0, (size_t)B * max_det * sizeof(int32_t), s) != cudaSuccess)
+        return EITB_ERR_LAUNCH;
+    if (inst_bits && cudaMemsetAsync(inst_bits, 0, (size_t)B * max_det * H * (W / 8), s) != cudaSuccess)
+        return EITB_ERR_LAUNCH;
+    switch (proto_dtype) {
+        case EITB_F32: return launch_decode<float>(dets, n_det, max_det, protos, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
+        case EITB_F16: return launch_decode<__half>(dets, n_det, max_det, protos, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
+        case EITB_BF16: return launch_decode<__nv_bfloat16>(dets, n_det, max_det, protos, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
+        default: return EITB_ERR_BAD_ARG;
+    }
+}

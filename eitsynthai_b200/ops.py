@@ -1,0 +1,218 @@
+"""Device-tensor wrappers around the C-ABI (``cabi``): PyTorch supplies memory and streams,
+libeitb200 does the work.  Every function enqueues on the current CUDA stream of the
+tensor's device and returns device tensors; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import cabi
+
+_DT = {torch.float32: cabi.F32, torch.float16: cabi.F16, torch.bfloat16: cabi.BF16}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (libeitb200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------ K1
+def hu_window(px: torch.Tensor, lo: int = -160, hi: int = 240, rot180: bool = True,
+              body_mask: torch.Tensor | None = None, want_u8: bool = True,
+              nchw_dtype: torch.dtype | None = torch.float16):
+    """[B,H,W] int16 -> (u8 [B,H,W] or None, NCHW [B,3,H,W] or None).  classic_norm + mask + /255."""
+    _chk(px, torch.int16, "px")
+    B, H, W = px.shape
+    if body_mask is not None:
+        _chk(body_mask, torch.uint8, "body_mask")
+        assert body_mask.shape == px.shape
+    u8 = torch.empty((B, H, W), dtype=torch.uint8, device=px.device) if want_u8 else None
+    nchw = torch.empty((B, 3, H, W), dtype=nchw_dtype, device=px.device) if nchw_dtype is not None else None
+    with torch.cuda.device(px.device):
+        cabi.call("eitb_hu_window_nchw", px.data_ptr(), B, H, W, lo, hi, int(rot180), _ptr(body_mask),
+                  _ptr(u8), _ptr(nchw), _DT.get(nchw_dtype, cabi.F32), _stream(px))
+    return u8, nchw
+
+
+def u8_to_nchw(gray: torch.Tensor, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    _chk(gray, torch.uint8, "gray")
+    B, H, W = gray.shape
+    out = torch.empty((B, 3, H, W), dtype=dtype, device=gray.device)
+    with torch.cuda.device(gray.device):
+        cabi.call("eitb_u8_to_nchw", gray.data_ptr(), B, H, W, out.data_ptr(), _DT[dtype], _stream(gray))
+    return out
+
+
+# ------------------------------------------------------------------------------------ K2
+def body_mask(px: torch.Tensor, slope: int = 1, intercept: int = -1024, flipud: bool = True) -> torch.Tensor:
+    """[B,H,W] int16 -> [B,H,W] u8 {0,255}: get_axial_slice_body_mask(_nii)."""
+    _chk(px, torch.int16, "px")
+    B, H, W = px.shape
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=px.device)
+    lib = cabi.load()
+    nbytes = lib.eitb_body_mask_workspace_bytes(B, H, W)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=px.device)
+    with torch.cuda.device(px.device):
+        cabi.call("eitb_body_mask", px.data_ptr(), B, H, W, slope, intercept, int(flipud), out.data_ptr(),
+                  ws.data_ptr(), nbytes, _stream(px))
+    return out
+
+
+# ------------------------------------------------------------------------------------ K3
+def front_rows(px: torch.Tensor, order: torch.Tensor | None, n: int, row: int, flip_x: bool, flip_z: bool,
+               minmax: torch.Tensor | None = None):
+    """Coronal mid-rows [n,W] int16 + running (min,max) int32[2]."""
+    _chk(px, torch.int16, "px")
+    _, H, W = px.shape
+    if order is not None:
+        _chk(order, torch.int32, "order")
+    rows = torch.empty((n, W), dtype=torch.int16, device=px.device)
+    if minmax is None:
+        minmax = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=px.device)
+    with torch.cuda.device(px.device):
+        cabi.call("eitb_front_rows", px.data_ptr(), _ptr(order), n, H, W, row, int(flip_x), int(flip_z),
+                  rows.data_ptr(), minmax.data_ptr(), _stream(px))
+    return rows, minmax
+
+
+def minmax_u8(rows: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
+    _chk(rows, torch.int16, "rows")
+    _chk(minmax, torch.int32, "minmax")
+    out = torch.empty(rows.shape, dtype=torch.uint8, device=rows.device)
+    with torch.cuda.device(rows.device):
+        cabi.call("eitb_minmax_u8", rows.data_ptr(), rows.numel(), minmax.data_ptr(), out.data_ptr(), _stream(rows))
+    return out
+
+
+def letterbox_nchw(gray: torch.Tensor, nh: int, nw: int, top: int, left: int, outH: int, outW: int,
+                   dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    _chk(gray, torch.uint8, "gray")
+    B, H, W = gray.shape
+    out = torch.empty((B, 3, outH, outW), dtype=dtype, device=gray.device)
+    with torch.cuda.device(gray.device):
+        cabi.call("eitb_letterbox_nchw", gray.data_ptr(), B, H, W, nh, nw, top, left, outH, outW,
+                  out.data_ptr(), _DT[dtype], _stream(gray))
+    return out
+
+
+# ------------------------------------------------------------------------------------ K4
+def rib_select(xyxy: torch.Tensor, k: torch.Tensor, image_width: float = 512.0,
+               custom: torch.Tensor | None = None) -> torch.Tensor:
+    """[S,max_k,4] f32 boxes, [S] counts -> [S,4] int32 (y6, y7, mid+custom, ok)."""
+    _chk(xyxy, torch.float32, "xyxy")
+    _chk(k, torch.int32, "k")
+    S, max_k, _ = xyxy.shape
+    if custom is not None:
+        _chk(custom, torch.int32, "custom")
+    out = torch.empty((S, 4), dtype=torch.int32, device=xyxy.device)
+    with torch.cuda.device(xyxy.device):
+        cabi.call("eitb_rib_select", xyxy.data_ptr(), k.data_ptr(), S, max_k, float(image_width), _ptr(custom),
+                  out.data_ptr(), _stream(xyxy))
+    return out
+
+
+# ------------------------------------------------------------------------------------ K5
+def nms(head: torch.Tensor, nc: int, conf: float = 0.3, iou: float = 0.7, max_det: int = 300,
+        max_wh: float = 7680.0, want_idx: bool = True):
+    """[B,4+nc+nm,A] -> dets [B,max_det,6+nm] f32, keep_idx [B,max_det] i32, n [B] i32."""
+    if head.dtype not in _DT:
+        raise TypeError(f"head dtype {head.dtype} unsupported")
+    _chk(head, None, "head")
+    B, Cc, A = head.shape
+    nm = Cc - 4 - nc
+    dets = torch.zeros((B, max_det, 6 + nm), dtype=torch.float32, device=head.device)
+    idx = torch.full((B, max_det), -1, dtype=torch.int32, device=head.device) if want_idx else None
+    n = torch.zeros((B,), dtype=torch.int32, device=head.device)
+    with torch.cuda.device(head.device):
+        cabi.call("eitb_nms", head.data_ptr(), _DT[head.dtype], B, nc, nm, A, conf, iou, max_det, max_wh,
+                  dets.data_ptr(), _ptr(idx), n.data_ptr(), 0, 0, _stream(head))
+    return dets, idx, n
+
+
+# ------------------------------------------------------------------------------------ K6
+def mask_decode(dets: torch.Tensor, n_det: torch.Tensor, protos: torch.Tensor, variant: int = 0,
+                want_area: bool = False, want_bits: bool = False):
+    """dets/n from ``nms`` + protos [B,nm,mh,mw] -> overlay code image [B,4mh,4mw] u8
+    (+ per-instance areas [B,max_det] i32, + per-instance bit masks [B,max_det,H,W/8] u8)."""
+    _chk(dets, torch.float32, "dets")
+    _chk(n_det, torch.int32, "n_det")
+    _chk(protos, None, "protos")
+    B, nm, mh, mw = protos.shape
+    max_det = dets.shape[1]
+    assert dets.shape[2] == 6 + nm and dets.shape[0] == B
+    H, W = 4 * mh, 4 * mw
+    code = torch.empty((B, H, W), dtype=torch.uint8, device=dets.device)
+    area = torch.empty((B, max_det), dtype=torch.int32, device=dets.device) if want_area else None
+    bits = torch.empty((B, max_det, H, W // 8), dtype=torch.uint8, device=dets.device) if want_bits else None
+    with torch.cuda.device(dets.device):
+        cabi.call("eitb_mask_decode", dets.data_ptr(), n_det.data_ptr(), max_det, protos.data_ptr(),
+                  _DT[protos.dtype], B, nm, mh, mw, H, W, variant, code.data_ptr(), _ptr(area), _ptr(bits),
+                  0, 0, _stream(dets))
+    return code, area, bits
+
+
+# ------------------------------------------------------------------------------------ K7
+def label_cleanup(code: torch.Tensor, body: torch.Tensor | None) -> torch.Tensor:
+    """In-place clear_color_output (when ``body`` is given) + highlight_small_masks on code images."""
+    _chk(code, torch.uint8, "code")
+    B, H, W = code.shape
+    if body is not None:
+        _chk(body, torch.uint8, "body")
+    lib = cabi.load()
+    nbytes = lib.eitb_label_cleanup_workspace_bytes(B, H, W)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=code.device)
+    with torch.cuda.device(code.device):
+        cabi.call("eitb_label_cleanup", code.data_ptr(), _ptr(body), B, H, W, ws.data_ptr(), nbytes, _stream(code))
+    return code
+
+
+def codes_to_bgr(code: torch.Tensor) -> torch.Tensor:
+    _chk(code, torch.uint8, "code")
+    out = torch.empty(code.shape + (3,), dtype=torch.uint8, device=code.device)
+    with torch.cuda.device(code.device):
+        cabi.call("eitb_codes_to_bgr", code.data_ptr(), out.data_ptr(), code.numel(), _stream(code))
+    return out
+
+
+# ------------------------------------------------------------------------------------ K8
+def tri_label(nodes_xy: torch.Tensor, tri: torch.Tensor, poly_xy: torch.Tensor, poly_off: torch.Tensor,
+              poly_cls: torch.Tensor, outer_cls: int = 4) -> torch.Tensor:
+    _chk(nodes_xy, torch.float64, "nodes_xy")
+    _chk(tri, torch.int64, "tri")
+    _chk(poly_xy, torch.float64, "poly_xy")
+    _chk(poly_off, torch.int32, "poly_off")
+    _chk(poly_cls, torch.int32, "poly_cls")
+    T, P = tri.shape[0], poly_cls.shape[0]
+    out = torch.empty((T,), dtype=torch.int32, device=tri.device)
+    nbytes = cabi.load().eitb_tri_label_workspace_bytes(P)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=tri.device)
+    with torch.cuda.device(tri.device):
+        cabi.call("eitb_tri_label", nodes_xy.data_ptr(), nodes_xy.shape[0], tri.data_ptr(), T, poly_xy.data_ptr(),
+                  poly_off.data_ptr(), poly_cls.data_ptr(), P, outer_cls, out.data_ptr(), ws.data_ptr(), nbytes,
+                  _stream(tri))
+    return out
+
+
+def tri_label_raster(nodes_xy: torch.Tensor, tri: torch.Tensor, code: torch.Tensor, outer_cls: int = 4) -> torch.Tensor:
+    _chk(nodes_xy, torch.float64, "nodes_xy")
+    _chk(tri, torch.int64, "tri")
+    _chk(code, torch.uint8, "code")
+    H, W = code.shape
+    out = torch.empty((tri.shape[0],), dtype=torch.int32, device=tri.device)
+    with torch.cuda.device(tri.device):
+        cabi.call("eitb_tri_label_raster", nodes_xy.data_ptr(), nodes_xy.shape[0], tri.data_ptr(), tri.shape[0],
+                  code.data_ptr(), H, W, outer_cls, out.data_ptr(), _stream(tri))
+    return out

@@ -1,0 +1,187 @@
+/*
+ * eitb200.h -- C ABI of libeitb200.so: the B200 (sm_100a) kernels behind the kt_service
+ * imaging hot path of AndreyKatsupeev/EITSynthAI.
+ *
+ * The reference is pure Python and has no FFI; its seam for this path is the set of
+ * Python functions that kt_service/ai_tools/ai_tools.py imports from utils.py
+ * (ai_tools.py:12-15), the ultralytics post-process reached through model(...)
+ * (ai_tools.py:121-122,153) and the triangle labeller of
+ * mesh_tools/femm_generator.py:12-184.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all tensors are row-major, batch dimension first;
+ *   - unless an argument is documented as "host", every pointer is a DEVICE pointer
+ *     owned by the caller; the library never allocates, frees or keeps pointers;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing syncs;
+ *   - return value: EITB_OK (0) or a negative EITB_ERR_* code; no exceptions, no exit();
+ *   - scratch memory is passed in (`ws`, `ws_bytes`); sizes come from *_workspace_bytes().
+ */
+#ifndef EITB200_H
+#define EITB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EITB_OK 0
+#define EITB_ERR_BAD_ARG (-1)      /* null pointer, non-positive size, unsupported shape */
+#define EITB_ERR_WORKSPACE (-2)    /* ws_bytes smaller than *_workspace_bytes()           */
+#define EITB_ERR_LAUNCH (-3)       /* cudaGetLastError() != cudaSuccess after a launch    */
+#define EITB_ERR_UNSUPPORTED (-4)  /* valid request this build does not implement         */
+
+/* element types for "void*" image / tensor arguments */
+#define EITB_F32 0
+#define EITB_F16 1
+#define EITB_BF16 2
+
+/* label-image codes: code = B<<2 | G<<1 | R of the reference's BGR colours
+ * (utils.py:468-473): 0 black, 1 muscle (0,0,255), 3 adipose (0,255,255),
+ * 6 lung (255,255,0), 7 bone (255,255,255). */
+#define EITB_CODE_BLACK 0
+#define EITB_CODE_MUSCLE 1
+#define EITB_CODE_ADIPOSE 3
+#define EITB_CODE_LUNG 6
+#define EITB_CODE_BONE 7
+
+typedef void* eitb_stream_t;
+
+const char* eitb_strerror(int code);
+int eitb_version(void);
+
+/* ---- K1: HU window + normalise + rot180 + body-mask AND + NCHW ------------------------
+ * Replaces classic_norm (utils.py:272-313), cv2.bitwise_and(norm, norm, mask=body)
+ * (ai_tools.py:212-213,287-288,339-340,433-434) and, for the square 256/512 inputs the
+ * service feeds, the ultralytics preprocess (gray -> 3 equal channels, HWC->NCHW,
+ * /255).
+ *   px        [B,H,W] int16 stored pixel values
+ *   lo, hi    window bounds (reference: level 40, width 400 -> -160, 240)
+ *   rot180    1: rotate each slice by 180 degrees (utils.py:309)
+ *   body_mask [B,H,W] u8 or NULL; applied in OUTPUT orientation (nonzero keeps)
+ *   out_u8    [B,H,W] u8 or NULL      -- classic_norm (+mask) result
+ *   out_nchw  [B,3,H,W] of out_dtype or NULL -- u8/255 rounded once to out_dtype
+ * W must be a multiple of 8. */
+int eitb_hu_window_nchw(const int16_t* px, int B, int H, int W, int lo, int hi, int rot180,
+                        const uint8_t* body_mask, uint8_t* out_u8, void* out_nchw,
+                        int out_dtype, eitb_stream_t stream);
+
+/* u8 gray image(s) -> 3-channel NCHW /255 (the jpg_png route, ai_tools.py:365-400). */
+int eitb_u8_to_nchw(const uint8_t* gray, int B, int H, int W, void* out_nchw, int out_dtype,
+                    eitb_stream_t stream);
+
+/* ---- K2: body mask ----------------------------------------------------------------------
+ * Replaces get_axial_slice_body_mask (utils.py:526-585) and, with flipud=0, slope=1,
+ * intercept=0, get_axial_slice_body_mask_nii (utils.py:588-618): HU = slope*px+intercept
+ * wrapped to int16, -500 < HU < 1000, 5x5 opening, the external contour with the largest
+ * cv2.contourArea filled with 255 (ties: the contour starting last in raster order).
+ *   mask [B,H,W] u8 out, values {0,255} (all 0 when nothing survives the opening). */
+size_t eitb_body_mask_workspace_bytes(int B, int H, int W);
+int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope, int intercept, int flipud,
+                   uint8_t* mask, void* ws, size_t ws_bytes, eitb_stream_t stream);
+
+/* ---- K3: coronal mid-row gather + min/max, MINMAX normalise ------------------------------
+ * Replaces convert_to_3d + axial_to_sagittal + mid-plane (utils.py:73-163,
+ * ai_tools.py:98-99) without materialising the (H,W,N) volume: one row per slice.
+ *   px     [n_total,H,W] slices in file order
+ *   order  [n] int32 indices into px giving InstanceNumber order (NULL: identity)
+ *   row    source row (H/2, or H-1-H/2 when ImageOrientationPatient[4] == -1)
+ *   flip_x reverse each row; flip_z reverse the slice order (see host mirror for the rules)
+ *   rows   [n,W] int16 out
+ *   minmax [2] int32 in/out: atomically min/max-combined, caller initialises to
+ *          {INT32_MAX, INT32_MIN} (lets several shards or calls accumulate). */
+int eitb_front_rows(const int16_t* px, const int32_t* order, int n, int H, int W, int row,
+                    int flip_x, int flip_z, int16_t* rows, int32_t* minmax, eitb_stream_t stream);
+
+/* cv2.normalize(front, None, 0, 255, NORM_MINMAX, CV_8U) (ai_tools.py:101) with OpenCV's
+ * arithmetic: scale/shift in double, cast to float, one float FMA per pixel, round-half-even.
+ *   minmax [2] int32 device pointer (from eitb_front_rows / an all-reduce). */
+int eitb_minmax_u8(const int16_t* rows, int64_t count, const int32_t* minmax, uint8_t* out,
+                   eitb_stream_t stream);
+
+/* ---- a11: letterbox for non-square inputs (rib model on the (N,512) coronal image) -------
+ * Restates ultralytics LetterBox(auto=True)+preprocess (call site
+ * ai_tools.py:120-122): cv2.resize(INTER_LINEAR) fixed-point bilinear to (nh,nw), constant
+ * 114 border, 3 equal channels, /255.  Geometry is computed by the host mirror.
+ *   gray [B,H,W] u8 -> out [B,3,outH,outW]. */
+int eitb_letterbox_nchw(const uint8_t* gray, int B, int H, int W, int nh, int nw, int top,
+                        int left, int outH, int outW, void* out, int out_dtype,
+                        eitb_stream_t stream);
+
+/* ---- K4: rib arg-select -------------------------------------------------------------------
+ * Replaces search_number_axial_slice (utils.py:166-269) for S series at once.
+ *   xyxy   [S,max_k,4] float32 boxes in coronal-image pixels, k[S] valid counts
+ *   out    [S,4] int32: int(y1[5]), int(y1[6]), int(|y1[5]+y1[6]|/2)+custom, ok(1/0)
+ *          (ok=0 <=> fewer than 7 boxes right of image_width/2: the reference returns []). */
+int eitb_rib_select(const float* xyxy, const int32_t* k, int S, int max_k, float image_width,
+                    const int32_t* custom /* [S] or NULL */, int32_t* out, eitb_stream_t stream);
+
+/* ---- K5: confidence filter + class-aware NMS ------------------------------------------------
+ * Restates ultralytics non_max_suppression + torchvision.ops.nms (SURVEY Appendix A.3;
+ * call sites ai_tools.py:121-122,153: conf=0.3, iou=0.7, max_det=300, max_wh=7680).
+ *   head     [B,4+nc+nm,A] (xywh, class scores, mask coefficients) of head_dtype
+ *   dets     [B,max_det,6+nm] float32 out: x1,y1,x2,y2,conf,cls,coef.. in descending score
+ *   keep_idx [B,max_det] int32 out or NULL: anchor index of every kept detection
+ *   n_out    [B] int32 out */
+size_t eitb_nms_workspace_bytes(int B, int A);
+int eitb_nms(const void* head, int head_dtype, int B, int nc, int nm, int A, float conf,
+             float iou, int max_det, float max_wh, float* dets, int32_t* keep_idx,
+             int32_t* n_out, void* ws, size_t ws_bytes, eitb_stream_t stream);
+
+/* ---- K6: mask decode fused with the label-image overlay ---------------------------------------
+ * Restates ultralytics process_mask(upsample=True) -- coef x proto
+ * contraction, crop to box/4, bilinear x(H/mh) upsample, threshold -- fused with
+ * create_segmentations_masks + overlay_segmentation_masks (utils.py:437-523,395-434): per
+ * pixel OR of the colour codes of every instance covering it.
+ *   dets/n_det as written by eitb_nms; protos [B,nm,mh,mw] of proto_dtype
+ *   variant   0: logits, interpolate, > 0 (8.3.x)   1: sigmoid, interpolate, > 0.5 (8.0-8.2)
+ *   code      [B,H,W] u8 out: overlay codes
+ *   inst_area [B,max_det] int32 out or NULL: mask pixel count (the empty-mask filter)
+ *   inst_bits [B,max_det,H,W/8] u8 out or NULL: per-instance bit masks (LSB = lowest x)
+ * H == 4*mh, W == 4*mw. */
+size_t eitb_mask_decode_workspace_bytes(int B, int max_det, int nm, int mh, int mw);
+int eitb_mask_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos,
+                     int proto_dtype, int B, int nm, int mh, int mw, int H, int W, int variant,
+                     uint8_t* code, int32_t* inst_area, uint8_t* inst_bits, void* ws,
+                     size_t ws_bytes, eitb_stream_t stream);
+
+/* ---- K7: label-image clean-up -------------------------------------------------------------------
+ * Replaces clear_color_output (utils.py:691-755; skipped when body == NULL, utils.py:1005)
+ * followed by highlight_small_masks (utils.py:758-843), on code images, in place. */
+size_t eitb_label_cleanup_workspace_bytes(int B, int H, int W);
+int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int H, int W, void* ws,
+                       size_t ws_bytes, eitb_stream_t stream);
+
+/* code image -> the reference's BGR colour image, [n] -> [n,3]. */
+int eitb_codes_to_bgr(const uint8_t* code, uint8_t* bgr, int64_t n, eitb_stream_t stream);
+
+/* ---- K8: per-triangle tissue labelling ----------------------------------------------------------
+ * Replaces divide_triangles_into_groups / process_triangle / the CLASS vector of
+ * export_mesh_for_femm (mesh_tools/femm_generator.py:12-85,118-184,187-265) with the
+ * reference's polygon semantics in fp64: polygons in ascending area order, skipping class
+ * == outer_cls; centroid strictly inside -> class, stop; else intersection area / triangle
+ * area > 0.5 -> class, stop; else arg-max positive intersection; default outer_cls.
+ *   nodes_xy [n_nodes,2] f64; tri [T,3] int64 (0-based node indices)
+ *   poly_xy  [V,2] f64 closed rings back to back; poly_off [P+1] int32 vertex offsets;
+ *   poly_cls [P] int32; polygons already sorted by ascending area (host mirror does it)
+ *   cls_out  [T] int32
+ *   ws       eitb_tri_label_workspace_bytes(P) bytes (per-polygon bounding boxes, orientation)
+ * nodes_xy and poly_xy must be 16-byte aligned. */
+size_t eitb_tri_label_workspace_bytes(int P);
+int eitb_tri_label(const double* nodes_xy, int64_t n_nodes, const int64_t* tri, int64_t T,
+                   const double* poly_xy, const int32_t* poly_off, const int32_t* poly_cls, int P,
+                   int outer_cls, int32_t* cls_out, void* ws, size_t ws_bytes, eitb_stream_t stream);
+
+/* Raster mode named by the north star: class of the label-map pixel under the centroid
+ * (code -> class: 7->0, 1->1, 6->2, 3->3, else outer_cls).  Not the reference semantics;
+ * offered for comparison only. */
+int eitb_tri_label_raster(const double* nodes_xy, int64_t n_nodes, const int64_t* tri, int64_t T,
+                          const uint8_t* code, int H, int W, int outer_cls, int32_t* cls_out,
+                          eitb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EITB200_H */

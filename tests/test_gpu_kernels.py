@@ -1,0 +1,297 @@
+"""CUDA path (through the C-ABI) vs the CPU oracle and the golden vectors.  B200 only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from eitsynthai_b200 import synth
+from oracle import imaging as O
+from oracle import yolo_post as Y
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from eitsynthai_b200 import ops as _ops
+    return _ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# ----------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_hu_window_matches_reference_golden(ops, golden, dtype):
+    px = np.stack([synth.phantom_slice(0, -1024), synth.phantom_slice(3, 0)])
+    body = np.stack([golden["p0_body"], golden["p3hu_body"]])
+    u8, nchw = ops.hu_window(dev(px), body_mask=None, nchw_dtype=dtype)
+    assert np.array_equal(u8[0].cpu().numpy(), golden["p0_norm"])
+    assert np.array_equal(u8[1].cpu().numpy(), golden["p3hu_norm"])
+    u8m, nchwm = ops.hu_window(dev(px), body_mask=dev(body), nchw_dtype=dtype)
+    assert np.array_equal(u8m[0].cpu().numpy(), golden["p0_normbody"])
+    assert np.array_equal(u8m[1].cpu().numpy(), golden["p3hu_normbody"])
+    # ultralytics preprocess: u8 -> dtype -> /255, three equal channels
+    want = u8m.cpu().to(dtype) / 255
+    for c in range(3):
+        assert torch.equal(nchwm[:, c].cpu(), want)
+
+
+def test_hu_window_every_int16(ops, golden):
+    allv = np.arange(-32768, 32768, dtype=np.int16).reshape(1, 256, 256)
+    u8, _ = ops.hu_window(dev(allv), nchw_dtype=None)
+    assert np.array_equal(u8[0].cpu().numpy(), golden["norm_all_int16"])
+
+
+def test_hu_window_other_windows_and_no_rotation(ops):
+    rng = np.random.default_rng(3)
+    px = rng.integers(-2000, 3000, (3, 64, 128)).astype(np.int16)
+    for level, width, rot in ((40, 400, False), (-600, 1500, True), (300, 3000, True)):
+        u8, _ = ops.hu_window(dev(px), lo=level - width // 2, hi=level + width // 2, rot180=rot, nchw_dtype=None)
+        want = O.classic_norm(px, level, width)
+        if not rot:
+            want = want[..., ::-1, ::-1]
+        assert np.array_equal(u8.cpu().numpy(), want)
+
+
+def test_u8_to_nchw(ops):
+    g = np.arange(256, dtype=np.uint8).repeat(64).reshape(1, 128, 128)
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        out = ops.u8_to_nchw(dev(g), dt).cpu()
+        want = torch.from_numpy(g).to(dt) / 255
+        for c in range(3):
+            assert torch.equal(out[:, c], want)
+
+
+# ----------------------------------------------------------------------------------- K3 / K4
+@pytest.mark.parametrize("tag,pp,iop,po", [
+    ("hfs", "HFS", [1, 0, 0, 0, 1, 0], None), ("ffs", "FFS", [1, 0, 0, 0, 1, 0], None),
+    ("ffs_neg", "FFS", [-1, 0, 0, 0, -1, 0], ["L", "P"]), ("hfp", "HFP", [1, 0, 0, 0, -1, 0], ["L", "A"])])
+def test_front_rows_golden(ops, golden, tag, pp, iop, po):
+    from eitsynthai_b200.host import front_geometry
+    vol, inst = synth.phantom_series(40, seed=5, size=512)
+    order = np.argsort(inst, kind="stable").astype(np.int32)
+    row, fx, fz = front_geometry(512, pp, iop, po)
+    rows, mm = ops.front_rows(dev(vol), dev(order), 40, row, fx, fz)
+    assert np.array_equal(rows.cpu().numpy(), golden[f"front_{tag}_raw"])
+    assert mm.cpu().tolist() == [int(golden[f"front_{tag}_raw"].min()), int(golden[f"front_{tag}_raw"].max())]
+    u8 = ops.minmax_u8(rows, mm)
+    assert np.array_equal(u8.cpu().numpy(), golden[f"front_{tag}_u8"])
+
+
+def test_minmax_u8_adversarial(ops):
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        lo, hi = int(rng.integers(-3000, 0)), int(rng.integers(1, 3000))
+        a = rng.integers(lo, hi + 1, (37, 512)).astype(np.int16)
+        a[0, 0], a[0, 1] = lo, hi
+        mm = torch.tensor([lo, hi], dtype=torch.int32, device=DEV)
+        assert np.array_equal(ops.minmax_u8(dev(a), mm).cpu().numpy(), O.minmax_u8(a))
+    c = np.full((4, 512), 7, np.int16)
+    mm = torch.tensor([7, 7], dtype=torch.int32, device=DEV)
+    assert np.array_equal(ops.minmax_u8(dev(c), mm).cpu().numpy(), O.minmax_u8(c))
+
+
+def test_letterbox_matches_cv2(ops):
+    rng = np.random.default_rng(5)
+    for (h, w, imgsz) in ((320, 512, 640), (40, 512, 640), (512, 512, 512), (301, 512, 640), (700, 512, 640)):
+        g = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        nh, nw, top, bottom, left, right = Y.letterbox_geometry(h, w, imgsz)
+        want = Y.preprocess(g, imgsz, torch.float32)
+        out = ops.letterbox_nchw(dev(g[None]), nh, nw, top, left, nh + top + bottom, nw + left + right, torch.float32)
+        assert out.shape == want.shape
+        assert torch.equal(out.cpu(), want), (h, w, imgsz, (out.cpu() != want).sum())
+
+
+def test_rib_select_known_answer_and_random(ops, golden):
+    from oracle.gen_golden import DOCSTRING_BOXES
+    rng = np.random.default_rng(0)
+    cases = [DOCSTRING_BOXES, DOCSTRING_BOXES[:8], np.zeros((0, 4), np.float32)]
+    for _ in range(40):
+        k = int(rng.integers(0, 40))
+        b = rng.uniform(0, 512, (k, 4)).astype(np.float32)
+        if k > 3:
+            b[1, 1] = b[2, 1]                       # tie on y1 -> stable order matters
+        cases.append(b)
+    max_k = 64
+    xy = np.zeros((len(cases), max_k, 4), np.float32)
+    kk = np.zeros(len(cases), np.int32)
+    custom = rng.integers(-3, 4, len(cases)).astype(np.int32)
+    for i, b in enumerate(cases):
+        xy[i, :len(b)] = b
+        kk[i] = len(b)
+    out = ops.rib_select(dev(xy), dev(kk), 512.0, dev(custom)).cpu().numpy()
+    assert list(ops.rib_select(dev(xy[:1]), dev(kk[:1])).cpu().numpy()[0]) == [162, 201, 182, 1]
+    for i, b in enumerate(cases):
+        want = O.search_number_axial_slice(b, int(custom[i]))
+        if want == []:
+            assert out[i, 3] == 0
+        else:
+            assert list(out[i]) == want + [1]
+
+
+# ----------------------------------------------------------------------------------- K5
+def _nms_case(ops, head, nc, **kw):
+    B = head.shape[0]
+    dets, idx, n = ops.nms(dev(head), nc, **kw)
+    dets, idx, n = dets.cpu(), idx.cpu(), n.cpu()
+    for b in range(B):
+        want, widx = Y.nms(torch.from_numpy(head[b]).float(), nc, kw.get("conf", 0.3), kw.get("iou", 0.7),
+                           kw.get("max_det", 300))
+        assert int(n[b]) == want.shape[0], (b, int(n[b]), want.shape[0])
+        assert torch.equal(idx[b, :n[b]].long(), widx)
+        assert torch.equal(dets[b, :n[b]], want)
+
+
+@pytest.mark.parametrize("n_cand", [0, 1, 50, 300, 3000])
+def test_nms_random_heads_bit_exact(ops, n_cand):
+    head, _ = synth.random_heads(3, n_cand, seed=n_cand + 1)
+    _nms_case(ops, head, 4)
+
+
+def test_nms_teacher_and_rib_shapes(ops):
+    head, _ = synth.teacher_heads(seed=0)
+    _nms_case(ops, head[None], 4)
+    head256, _ = synth.teacher_heads(seed=2, size=256)
+    _nms_case(ops, head256[None], 4)
+    # rib model: nc=1, A=5460, dense overlapping boxes, score ties
+    rng = np.random.default_rng(9)
+    A = 5460
+    h = np.zeros((2, 37, A), np.float32)
+    h[:, 0] = rng.uniform(0, 640, (2, A)); h[:, 1] = rng.uniform(0, 416, (2, A))
+    h[:, 2:4] = rng.uniform(8, 40, (2, 2, A))
+    h[:, 4] = np.round(rng.uniform(0, 0.6, (2, A)), 2)        # many exactly equal scores
+    h[:, 5:] = rng.normal(0, 1, (2, 32, A))
+    _nms_case(ops, h, 1)
+    _nms_case(ops, h, 1, conf=0.05, iou=0.5, max_det=100)
+
+
+def test_nms_half_precision_heads(ops):
+    head, _ = synth.random_heads(2, 200, seed=4)
+    for dt in (torch.float16, torch.bfloat16):
+        hq = torch.from_numpy(head).to(dt)
+        dets, idx, n = ops.nms(hq.to(DEV), 4)
+        for b in range(2):
+            want, widx = Y.nms(hq[b].float(), 4)
+            assert int(n[b]) == want.shape[0]
+            assert torch.equal(idx[b, :n[b]].cpu().long(), widx)
+            assert torch.equal(dets[b, :n[b]].cpu(), want)
+
+
+# ----------------------------------------------------------------------------------- K6
+def _unpack_bits(bits, W):
+    b = np.unpackbits(bits, axis=-1, bitorder="little")
+    return b[..., :W]
+
+
+def _decode_case(ops, head, protos, variant, size, tol=1e-4):
+    """Per-instance masks, overlay codes and areas vs the CPU restatement."""
+    vname = "logit" if variant == 0 else "sigmoid"
+    dets, idx, n = ops.nms(dev(head[None]), 4)
+    code, area, bits = ops.mask_decode(dets, n, dev(protos[None]), variant, want_area=True, want_bits=True)
+    r = Y.postprocess(torch.from_numpy(head), torch.from_numpy(protos), 4, (size, size), (size, size),
+                      variant=vname, drop_empty=False)
+    nn = int(n[0])
+    assert nn == r["masks"].shape[0]
+    got = _unpack_bits(bits[0, :nn].cpu().numpy(), size)
+    want = r["masks"].numpy()
+    bad = int((got != want).sum())
+    assert bad <= tol * want.size, (bad, want.size)
+    assert np.array_equal(area[0, :nn].cpu().numpy(), got.reshape(nn, size * size).sum(1))
+    # overlay of the kernel's own masks == code image (exact); and close to the oracle's overlay
+    cls = r["cls"].numpy().astype(int)
+    assert np.array_equal(O.overlay_codes(O.class_union_masks(got, cls, size)), code[0].cpu().numpy())
+    wcode = O.overlay_codes(O.class_union_masks(want, cls, size))
+    assert (wcode != code[0].cpu().numpy()).mean() <= tol
+    for c in range(4):
+        a, b_ = wcode == O.CODE_OF_CLASS[c], code[0].cpu().numpy() == O.CODE_OF_CLASS[c]
+        if a.any():
+            assert (a & b_).sum() / (a | b_).sum() >= 0.999
+    return bad
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("seed,size", [(0, 512), (1, 512), (2, 256)])
+def test_mask_decode_teacher(ops, variant, seed, size):
+    head, protos = synth.teacher_heads(seed=seed, size=size)
+    _decode_case(ops, head, protos, variant, size)
+
+
+@pytest.mark.parametrize("n_cand", [0, 1, 50, 300])
+def test_mask_decode_random(ops, n_cand):
+    head, protos = synth.random_heads(1, n_cand, seed=7 + n_cand)
+    _decode_case(ops, head[0], protos[0], 0, 512)
+
+
+def test_mask_decode_batch_and_half_protos(ops):
+    head, protos = synth.random_heads(4, 40, seed=21)
+    dets, idx, n = ops.nms(dev(head), 4)
+    code32, _, _ = ops.mask_decode(dets, n, dev(protos))
+    for b in range(4):
+        c1, _, _ = ops.mask_decode(dets[b:b + 1].contiguous(), n[b:b + 1].contiguous(), dev(protos[b:b + 1]))
+        assert torch.equal(c1[0], code32[b])
+    ph = torch.from_numpy(protos).half()
+    code16, _, _ = ops.mask_decode(dets, n, ph.to(DEV))
+    code16ref, _, _ = ops.mask_decode(dets, n, ph.float().to(DEV))
+    assert torch.equal(code16, code16ref)          # fp16 protos are widened exactly
+
+
+def test_codes_to_bgr(ops):
+    code = np.random.default_rng(0).choice([0, 1, 3, 6, 7], (3, 64, 64)).astype(np.uint8)
+    assert np.array_equal(ops.codes_to_bgr(dev(code)).cpu().numpy(), O.code_to_bgr(code))
+
+
+# ----------------------------------------------------------------------------------- K8
+def _polys(tag):
+    from oracle import tri_label as TL
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "reference_polygons.json")) as f:
+        strs = json.load(f)[tag][2:]
+    outer = next((i for i, s in enumerate(strs) if isinstance(s, str) and s[:1] == "4"), None)
+    return TL.prepare_polygons(TL.parse_contours(strs, outer))
+
+
+@pytest.mark.parametrize("tag,pitch", [("seg0", 3.0), ("seg1", 2.5), ("seg2", 1.5), ("seg3", 1.08)])
+def test_tri_label_bit_exact(ops, tag, pitch):
+    from oracle import tri_label as TL
+    xy, off, cls, _ = _polys(tag)
+    bbox = (20, 40, 490, 470) if tag != "seg2" else (10, 20, 245, 235)
+    nodes, tri = synth.delaunay_mesh(bbox, pitch, seed=3)
+    want = TL.label_triangles(nodes, tri, xy, off, cls)
+    got = ops.tri_label(dev(nodes), dev(tri), dev(xy), dev(off), dev(cls)).cpu().numpy()
+    assert np.array_equal(got, want), (int((got != want).sum()), len(tri))
+    assert len(np.unique(want)) >= 4
+
+
+def test_tri_label_edge_cases(ops):
+    from oracle import tri_label as TL
+    xy, off, cls, _ = _polys("seg0")
+    nodes, tri = synth.delaunay_mesh((100, 100, 200, 200), 5.0, seed=1)
+    # no polygons at all -> outer class; empty triangle list; clockwise + degenerate triangles
+    got = ops.tri_label(dev(nodes), dev(tri), dev(np.zeros((0, 2))), dev(np.zeros(1, np.int32)),
+                        dev(np.zeros(0, np.int32))).cpu().numpy()
+    assert (got == 4).all()
+    assert ops.tri_label(dev(nodes), dev(tri[:0]), dev(xy), dev(off), dev(cls)).numel() == 0
+    tri2 = tri[:, ::-1].copy()
+    tri2[::7, 2] = tri2[::7, 1]                      # zero-area triangles
+    want = TL.label_triangles(nodes, tri2, xy, off, cls)
+    got = ops.tri_label(dev(nodes), dev(tri2), dev(xy), dev(off), dev(cls)).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_tri_label_raster(ops):
+    rng = np.random.default_rng(2)
+    code = rng.choice([0, 1, 3, 6, 7], (512, 512)).astype(np.uint8)
+    nodes, tri = synth.delaunay_mesh((-5, -5, 520, 520), 9.0, seed=4)
+    got = ops.tri_label_raster(dev(nodes), dev(tri), dev(code)).cpu().numpy()
+    c = nodes[tri].mean(1)
+    px, py = np.floor(c[:, 0] + 0.5).astype(int), np.floor(c[:, 1] + 0.5).astype(int)
+    ok = (px >= 0) & (px < 512) & (py >= 0) & (py < 512)
+    lut = np.full(8, 4); lut[7], lut[1], lut[6], lut[3] = 0, 1, 2, 3
+    want = np.where(ok, lut[code[py.clip(0, 511), px.clip(0, 511)]], 4)
+    assert np.array_equal(got, want)
