@@ -36,6 +36,7 @@ SIGNATURES = {
     "eitb_u8_to_nchw": (_i, [_p, _i, _i, _i, _p, _i, _p]),
     "eitb_body_mask_workspace_bytes": (_sz, [_i, _i, _i]),
     "eitb_body_mask": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "eitb_cc_label": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "eitb_front_rows": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "eitb_minmax_u8": (_i, [_p, _i64, _p, _p, _p]),
     "eitb_letterbox_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),

@@ -1,0 +1,191 @@
+// K2: body mask.
+//
+// Reference: get_axial_slice_body_mask (kt_service/ai_tools/utils.py:526-585) and its NIfTI twin
+// (:588-618): flipud (:551), HU = slope*px + intercept cast to int16 (:554-559), -500 < HU < 1000
+// (:565), 5x5 MORPH_OPEN (:569), external contours (:572), the one with the largest
+// cv2.contourArea (:577) filled with 255 (:581-582).
+//
+// Restated without contours (oracle/imaging.py largest_contour_fill_np, pinned to the reference
+// on the golden vectors):
+//   * pixels outside every external contour = 4-connected background reachable from the frame;
+//   * every 8-connected component of the rest is one filled external contour;
+//   * its contourArea is N4 + N3/2 over the 2x2 pixel blocks with 4 / exactly 3 filled pixels;
+//   * ties go to the component whose first pixel comes last in raster order.
+// Stages: threshold+erode -> dilate -> CC(background, 4, frame-linked) -> CC(filled, 8) ->
+// per-component 2*area accumulation -> arg-max -> write mask.
+#include "cc.cuh"
+
+namespace {
+
+using namespace eitb_cc;
+
+__device__ __forceinline__ bool hu_in_range(int px, int slope, int intercept) {
+    const int hu = (int)(short)(slope * px + intercept);          // .astype(int16) wraps (utils.py:559)
+    return hu > -500 && hu < 1000;
+}
+
+// erosion of the thresholded, vertically flipped slice with a 5x5 box; cv2's default border
+// for erosion never removes pixels (outside counts as set).
+__global__ void __launch_bounds__(256)
+thr_erode_kernel(const int16_t* __restrict__ px, int B, int H, int W, int slope, int intercept, int flipud,
+                 uint8_t* __restrict__ er) {
+    const long long n = (long long)B * H * W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / ((long long)H * W));
+        const int r = (int)(t - (long long)b * H * W);
+        const int y = r / W, x = r - y * W;
+        const int16_t* img = px + (long long)b * H * W;
+        bool all = true;
+        for (int dy = -2; dy <= 2 && all; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+            const int sy = flipud ? H - 1 - yy : yy;
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
+                all = all && hu_in_range(img[(long long)sy * W + xx], slope, intercept);
+            }
+        }
+        er[t] = all ? 1 : 0;
+    }
+}
+
+// dilation with a 5x5 box (outside counts as unset) -> opened mask (1/0)
+__global__ void __launch_bounds__(256)
+dilate_kernel(const uint8_t* __restrict__ er, int B, int H, int W, uint8_t* __restrict__ opened) {
+    const long long n = (long long)B * H * W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / ((long long)H * W));
+        const int r = (int)(t - (long long)b * H * W);
+        const int y = r / W, x = r - y * W;
+        const uint8_t* img = er + (long long)b * H * W;
+        bool any = false;
+        for (int dy = -2; dy <= 2 && !any; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
+                any = any || img[(long long)yy * W + xx];
+            }
+        }
+        opened[t] = any ? 1 : 0;
+    }
+}
+
+// 2*contourArea per component: +2 for every full 2x2 block, +1 for every block with 3 pixels.
+// Blocks are anchored at (y, x) = top-left pixel, y in [-1, H-1], x in [-1, W-1].
+__global__ void __launch_bounds__(256)
+area_kernel(const int32_t* __restrict__ lab, int B, int H, int W, int32_t* __restrict__ area2) {
+    const int bw = W + 1, bh = H + 1;
+    const long long per = (long long)bw * bh;
+    const long long n = (long long)B * per;
+    const long long nround = (n + 31) / 32 * 32;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += (long long)gridDim.x * blockDim.x) {
+        int root = -1, add = 0;
+        long long b = 0;
+        if (t < n) {
+            b = t / per;
+            const int r = (int)(t - b * per);
+            const int y = r / bw - 1, x = r - (r / bw) * bw - 1;
+            const int32_t* L = lab + b * H * W;
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int yy = y + (k >> 1), xx = x + (k & 1);
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                    const int l = L[yy * W + xx];
+                    if (l >= 0) { ++cnt; root = l; }
+                }
+            }
+            add = cnt == 4 ? 2 : cnt == 3 ? 1 : 0;
+            if (!add) root = -1;
+        }
+        // warp-aggregate by (image, root)
+        const long long key = root < 0 ? -1 : b * H * W + root;
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const int sum = __reduce_add_sync(grp, add);
+        if (root >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(area2 + key, sum);
+    }
+}
+
+// best[b] = max over roots of (area2 << 32 | root)
+__global__ void __launch_bounds__(256)
+best_kernel(const int32_t* __restrict__ lab, const int32_t* __restrict__ area2, long long n, int hw,
+            long long* __restrict__ best) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long b = t / hw;
+        const int i = (int)(t - b * hw);
+        if (lab[t] == i) atomicMax(best + b, ((long long)area2[t] << 32) | (long long)i);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+write_mask_kernel(const int32_t* __restrict__ lab, const long long* __restrict__ best, long long n, int hw,
+                  uint8_t* __restrict__ mask) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long b = t / hw;
+        const long long k = best[b];
+        const int l = lab[t];
+        mask[t] = (k >= 0 && l >= 0 && l == (int)(k & 0xffffffffLL)) ? 255 : 0;
+    }
+}
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t eitb_body_mask_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t n = (size_t)B * H * W;
+    // er u8, opened u8, labels A int32, labels B int32, area2 int32, best int64[B]
+    return align256(n) * 2 + align256(n * 4) * 3 + align256((size_t)B * 8);
+}
+
+extern "C" int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope, int intercept, int flipud,
+                              uint8_t* mask, void* ws, size_t ws_bytes, eitb_stream_t stream) {
+    if (!px || !mask || B < 0 || H <= 0 || W <= 0) return EITB_ERR_BAD_ARG;
+    if (B == 0) return EITB_OK;
+    if ((long long)H * W >= (1LL << 31)) return EITB_ERR_UNSUPPORTED;
+    if (!ws || ws_bytes < eitb_body_mask_workspace_bytes(B, H, W)) return EITB_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)B * H * W;
+    char* p = reinterpret_cast<char*>(ws);
+    uint8_t* er = reinterpret_cast<uint8_t*>(p); p += align256(n);
+    uint8_t* opened = reinterpret_cast<uint8_t*>(p); p += align256(n);
+    int32_t* labA = reinterpret_cast<int32_t*>(p); p += align256(n * 4);
+    int32_t* labB = reinterpret_cast<int32_t*>(p); p += align256(n * 4);
+    int32_t* area2 = reinterpret_cast<int32_t*>(p); p += align256(n * 4);
+    long long* best = reinterpret_cast<long long*>(p);
+    const int grid = eitb_grid((long long)n, 256, 8);
+
+    thr_erode_kernel<<<grid, 256, 0, s>>>(px, B, H, W, slope, intercept, flipud, er);
+    EITB_CHECK_LAUNCH();
+    dilate_kernel<<<grid, 256, 0, s>>>(er, B, H, W, opened);
+    EITB_CHECK_LAUNCH();
+    int rc = cc_label<PRED_U8_ZERO, 4>(opened, (size_t)H * W, 0, B, H, W, 1, labA, s);       // background, frame-linked
+    if (rc != EITB_OK) return rc;
+    rc = cc_label<PRED_LABEL_NOT_OUT, 8>(labA, (size_t)H * W * 4, 0, B, H, W, 0, labB, s);   // filled regions
+    if (rc != EITB_OK) return rc;
+    if (cudaMemsetAsync(area2, 0, n * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
+    if (cudaMemsetAsync(best, 0xff, (size_t)B * 8, s) != cudaSuccess) return EITB_ERR_LAUNCH;  // -1
+    area_kernel<<<eitb_grid((long long)B * (H + 1) * (W + 1), 256, 8), 256, 0, s>>>(labB, B, H, W, area2);
+    EITB_CHECK_LAUNCH();
+    best_kernel<<<grid, 256, 0, s>>>(labB, area2, (long long)n, H * W, best);
+    EITB_CHECK_LAUNCH();
+    write_mask_kernel<<<grid, 256, 0, s>>>(labB, best, (long long)n, H * W, mask);
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
+}
+
+extern "C" int eitb_cc_label(const uint8_t* mask, int B, int H, int W, int connectivity, int link_outside,
+                             int32_t* labels, eitb_stream_t stream) {
+    if (!mask || !labels || B < 0 || H <= 0 || W <= 0 || (connectivity != 4 && connectivity != 8)) return EITB_ERR_BAD_ARG;
+    if (B == 0) return EITB_OK;
+    if ((long long)H * W >= (1LL << 31)) return EITB_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    return connectivity == 4 ? cc_label<PRED_U8_NONZERO, 4>(mask, (size_t)H * W, 0, B, H, W, link_outside, labels, s)
+                             : cc_label<PRED_U8_NONZERO, 8>(mask, (size_t)H * W, 0, B, H, W, link_outside, labels, s);
+}

@@ -71,6 +71,16 @@ def body_mask(px: torch.Tensor, slope: int = 1, intercept: int = -1024, flipud: 
     return out
 
 
+def cc_label(mask: torch.Tensor, connectivity: int = 4, link_outside: bool = False) -> torch.Tensor:
+    """[B,H,W] u8 -> int32 labels (smallest pixel index of the component, -2 unset, -1 frame-connected)."""
+    _chk(mask, torch.uint8, "mask")
+    B, H, W = mask.shape
+    out = torch.empty((B, H, W), dtype=torch.int32, device=mask.device)
+    with torch.cuda.device(mask.device):
+        cabi.call("eitb_cc_label", mask.data_ptr(), B, H, W, connectivity, int(link_outside), out.data_ptr(), _stream(mask))
+    return out
+
+
 # ------------------------------------------------------------------------------------ K3
 def front_rows(px: torch.Tensor, order: torch.Tensor | None, n: int, row: int, flip_x: bool, flip_z: bool,
                minmax: torch.Tensor | None = None):

@@ -82,6 +82,14 @@ size_t eitb_body_mask_workspace_bytes(int B, int H, int W);
 int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope, int intercept, int flipud,
                    uint8_t* mask, void* ws, size_t ws_bytes, eitb_stream_t stream);
 
+/* Connected-component labelling, the building block of K2 and K7 (what scipy.ndimage.label /
+ * cv2.findContours supply to utils.py:572, 721, 792).  mask [B,H,W] u8 (nonzero = in the set);
+ * connectivity 4 or 8; labels [B,H,W] int32 out: the smallest pixel index (y*W+x) of the pixel's
+ * component, -2 for pixels outside the set, and -1 for components touching the image frame when
+ * link_outside != 0 (flood fill from the frame). */
+int eitb_cc_label(const uint8_t* mask, int B, int H, int W, int connectivity, int link_outside,
+                  int32_t* labels, eitb_stream_t stream);
+
 /* ---- K3: coronal mid-row gather + min/max, MINMAX normalise ------------------------------
  * Replaces convert_to_3d + axial_to_sagittal + mid-plane (utils.py:73-163,
  * ai_tools.py:98-99) without materialising the (H,W,N) volume: one row per slice.

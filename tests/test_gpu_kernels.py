@@ -295,3 +295,103 @@ def test_tri_label_raster(ops):
     lut = np.full(8, 4); lut[7], lut[1], lut[6], lut[3] = 0, 1, 2, 3
     want = np.where(ok, lut[code[py.clip(0, 511), px.clip(0, 511)]], 4)
     assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------------- CC / K2
+def _canon(lab):
+    """scipy labels (1..n in raster order of first pixel) -> smallest pixel index per component."""
+    from scipy import ndimage as ndi
+    out = np.full(lab.shape, -2, np.int64)
+    if lab.max() > 0:
+        idx = np.arange(lab.size).reshape(lab.shape)
+        mins = ndi.minimum(idx, lab, index=np.arange(1, lab.max() + 1))
+        out[lab > 0] = np.asarray(mins)[lab[lab > 0] - 1]
+    return out
+
+
+@pytest.mark.parametrize("conn", [4, 8])
+def test_cc_label_matches_scipy(ops, conn):
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(conn)
+    st = None if conn == 4 else np.ones((3, 3), int)
+    masks = []
+    for dens, shape in ((0.5, (512, 512)), (0.62, (512, 512)), (0.3, (512, 512)), (0.9, (512, 512))):
+        masks.append((rng.random(shape) < dens).astype(np.uint8))
+    spiral = np.zeros((512, 512), np.uint8)              # one long snake through every strip
+    spiral[::4, :] = 1
+    spiral[2::8, -1] = 1; spiral[1::8, -1] = 1; spiral[3::8, -1] = 1
+    spiral[6::8, 0] = 1; spiral[5::8, 0] = 1; spiral[7::8, 0] = 1
+    masks += [spiral, np.zeros((512, 512), np.uint8), np.ones((512, 512), np.uint8)]
+    m = np.stack(masks)
+    got = ops.cc_label(dev(m), conn).cpu().numpy()
+    for k in range(len(masks)):
+        lab, _ = ndi.label(masks[k], structure=st)
+        assert np.array_equal(got[k], _canon(lab)), k
+    # other shapes: 256x256 and a ragged one
+    for shape in ((256, 256), (100, 72), (3, 8)):
+        mk = (rng.random((2,) + shape) < 0.55).astype(np.uint8)
+        got = ops.cc_label(dev(mk), conn).cpu().numpy()
+        for k in range(2):
+            lab, _ = ndi.label(mk[k], structure=st)
+            assert np.array_equal(got[k], _canon(lab)), (shape, k)
+
+
+def test_cc_label_outside(ops):
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(5)
+    m = (rng.random((3, 512, 512)) < 0.58).astype(np.uint8)
+    got = ops.cc_label(dev(m), 4, link_outside=True).cpu().numpy()
+    for k in range(3):
+        lab, _ = ndi.label(np.pad(m[k], 1, constant_values=1))
+        outside = (lab == lab[0, 0])[1:-1, 1:-1]
+        assert np.array_equal(got[k] == -1, outside)
+        inner = _canon(ndi.label(m[k])[0])
+        sel = (m[k] > 0) & ~outside
+        assert np.array_equal(got[k][sel], inner[sel])
+        assert (got[k][m[k] == 0] == -2).all()
+
+
+def test_body_mask_golden(ops, golden):
+    px = np.stack([synth.phantom_slice(0, -1024), synth.phantom_slice(3, 0)])
+    b0 = ops.body_mask(dev(px[:1]), 1, -1024, True).cpu().numpy()[0]
+    b1 = ops.body_mask(dev(px[1:]), 1, 0, True).cpu().numpy()[0]
+    assert np.array_equal(b0, golden["p0_body"])
+    assert np.array_equal(b1, golden["p3hu_body"])
+    hu = synth.phantom_hu(3).astype(np.int16)
+    assert np.array_equal(ops.body_mask(dev(hu[None]), 1, 0, False).cpu().numpy()[0], golden["p3hu_body_nii"])
+
+
+def test_body_mask_adversarial_vs_oracle(ops):
+    """Several blobs with near-tied areas, holes, frame contact, nested islands, empty input."""
+    rng = np.random.default_rng(8)
+    cases = []
+    for k in range(12):
+        hu = np.full((512, 512), -1000, np.int32)
+        yy, xx = np.mgrid[0:512, 0:512]
+        for _ in range(int(rng.integers(1, 7))):
+            cy, cx = rng.integers(30, 480, 2)
+            ry, rx = rng.integers(8, 120, 2)
+            hu[((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1] = 50
+        for _ in range(int(rng.integers(0, 5))):                 # holes and islands
+            cy, cx = rng.integers(60, 450, 2)
+            r = int(rng.integers(5, 40))
+            hu[(yy - cy) ** 2 + (xx - cx) ** 2 < r * r] = -900
+            if rng.random() < 0.5:
+                hu[(yy - cy) ** 2 + (xx - cx) ** 2 < (r // 2) ** 2] = 30
+        hu += rng.integers(-30, 31, hu.shape)
+        if k % 4 == 0:
+            hu[rng.random(hu.shape) < 0.02] = 2000               # salt noise, removed by the opening
+        cases.append((hu + 1024).astype(np.int16))
+    two = np.full((512, 512), 24, np.int16)                      # two equal squares: tie -> the later one
+    two[100:150, 100:150] = 1100; two[300:350, 300:350] = 1100
+    cases += [two, np.full((512, 512), 0, np.int16), np.full((512, 512), 1100, np.int16)]
+    px = np.stack(cases)
+    got = ops.body_mask(dev(px), 1, -1024, True).cpu().numpy()
+    for k in range(len(cases)):
+        want = O.body_mask(px[k], -1024, 1)
+        assert np.array_equal(got[k], want), (k, int((got[k] != want).sum()))
+    small = rng.integers(0, 2000, (5, 256, 256)).astype(np.int16)
+    small[:, 60:200, 50:210] = 1050
+    got = ops.body_mask(dev(small), 1, -1024, True).cpu().numpy()
+    for k in range(5):
+        assert np.array_equal(got[k], O.body_mask(small[k], -1024, 1))
