@@ -141,7 +141,7 @@ cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __r
     }
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 cc_flatten_kernel(long long n_total, int hw, int32_t* __restrict__ labels) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (long long)gridDim.x * blockDim.x) {
         const long long b = t / hw;

@@ -1,0 +1,343 @@
+// K7: label-image clean-up on code images, in place.
+//
+// Reference: create_color_output's tail (kt_service/ai_tools/utils.py:1005-1007):
+//   clear_color_output (utils.py:691-755), only when a body mask with any non-zero pixel is given:
+//     1. black pixels inside the body become muscle (:704-709);
+//     2. 4-connected components (scipy.ndimage.label) of the pixels that are neither black nor
+//        muscle (:712-721); those with < 5 pixels, in label order (= raster order of their first
+//        pixel), take the most common non-background colour among the 8-neighbours of their
+//        pixels -- votes listed direction-major then pixel-major, Counter keeps the first seen on
+//        ties, own pixels vote, the image is updated as it goes -- or muscle when nobody votes
+//        (:724-752);
+//   highlight_small_masks (utils.py:758-843): for bone, muscle, adipose in that order, external
+//     contours (RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) of the exact-colour mask of the INPUT image with
+//     <= 5 points are filled (holes included) with the most common colour of the 1-pixel ring
+//     around the filled contour, read from the progressively updated output in raster order and
+//     ignoring the target colour and black; no vote -> the target colour itself (:807-839).
+//
+// Data-parallel parts (relabel, small-component detection by bounded flood, the frame flood that
+// tells external contours from nested ones, candidate border tracing) run one thread per pixel;
+// the order-dependent repaints run one warp per image over a bitmap of the few candidates.
+//
+// cv2's border following is restated from its published algorithm (Suzuki-Abe as implemented in
+// OpenCV's contour tracer: clockwise search from the west neighbour, then counter-clockwise
+// search from the previous pixel; a point is emitted where the chain direction changes).
+#include "cc.cuh"
+
+namespace {
+
+using namespace eitb_cc;
+
+__device__ __forceinline__ bool not_bg(uint8_t c) { return c != EITB_CODE_BLACK && c != EITB_CODE_MUSCLE; }
+__device__ __forceinline__ uint8_t ldv(const uint8_t* p) { return __ldcg(p); }     // L2-coherent read
+
+// ------------------------------------------------------------------ stage A: black in body -> muscle
+__global__ void __launch_bounds__(256)
+fill_body_kernel(uint8_t* __restrict__ code, const uint8_t* __restrict__ body, long long n, int hw, int* __restrict__ anybody) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const uint8_t m = body[t];
+        if (m) {
+            const int b = (int)(t / hw);
+            if (anybody[b] == 0) anybody[b] = 1;                  // benign race: everyone writes 1
+            if (m == 255 && code[t] == EITB_CODE_BLACK) code[t] = EITB_CODE_MUSCLE;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ stage B: components with < 5 px
+// Bounded flood over 4-neighbours; returns the component size (1..4) with its pixels sorted
+// ascending in px[], or 5 when the component has at least 5 pixels.
+__device__ __forceinline__ int small_component(const uint8_t* img, int H, int W, int p, int (&px)[5]) {
+    int n = 1;
+    px[0] = p;
+    for (int h = 0; h < n && n < 5; ++h) {
+        const int y = px[h] / W, x = px[h] - y * W;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int yy = y + (d == 0 ? -1 : d == 1 ? 1 : 0), xx = x + (d == 2 ? -1 : d == 3 ? 1 : 0);
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W || n >= 5) continue;
+            const int q = yy * W + xx;
+            if (!not_bg(ldv(img + q))) continue;
+            bool seen = false;
+            for (int k = 0; k < n; ++k) seen = seen || px[k] == q;
+            if (!seen) px[n++] = q;
+        }
+    }
+    if (n < 5)
+        for (int i = 1; i < n; ++i)                                // insertion sort, n <= 4
+            for (int j = i; j > 0 && px[j] < px[j - 1]; --j) { const int t = px[j]; px[j] = px[j - 1]; px[j - 1] = t; }
+    return n;
+}
+
+__global__ void __launch_bounds__(256)
+small_first_kernel(const uint8_t* __restrict__ code, const int* __restrict__ anybody, int B, int H, int W,
+                   unsigned* __restrict__ bitmap, int words_per_img) {
+    const long long n = (long long)B * H * W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / ((long long)H * W));
+        if (!anybody[b]) continue;
+        const int p = (int)(t - (long long)b * H * W);
+        const uint8_t* img = code + (long long)b * H * W;
+        if (!not_bg(img[p])) continue;
+        const int y = p / W, x = p - y * W;
+        if ((x > 0 && not_bg(img[p - 1])) || (y > 0 && not_bg(img[p - W]))) continue;   // cannot be a first pixel
+        int px[5];
+        if (small_component(img, H, W, p, px) < 5 && px[0] == p)
+            atomicOr(bitmap + (long long)b * words_per_img + (p >> 5), 1u << (p & 31));
+    }
+}
+
+// one warp per image, candidates in ascending raster order
+__global__ void __launch_bounds__(32)
+small_repaint_kernel(uint8_t* __restrict__ code, const int* __restrict__ anybody, int H, int W,
+                     const unsigned* __restrict__ bitmap, int words_per_img) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (!anybody[b]) return;
+    uint8_t* img = code + (long long)b * H * W;
+    const unsigned* bm = bitmap + (long long)b * words_per_img;
+    const int dY[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, dX[8] = {-1, 0, 1, -1, 1, -1, 0, 1};       // utils.py:734-736
+    for (int w0 = 0; w0 < words_per_img; w0 += 32) {
+        const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
+        unsigned nz = __ballot_sync(0xffffffffu, mine != 0);
+        while (nz) {
+            const int wl = __ffs(nz) - 1;
+            nz &= nz - 1;
+            unsigned word = __shfl_sync(0xffffffffu, mine, wl);
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                const int p = ((w0 + wl) << 5) + bit;
+                int px[5];
+                const int n = small_component(img, H, W, p, px);       // uniform across the warp
+                const int d = lane >> 2, k = lane & 3;
+                int v = 0;
+                if (k < n) {
+                    const int y = px[k] / W + dY[d], x = px[k] % W + dX[d];
+                    if (y >= 0 && y < H && x >= 0 && x < W) {
+                        const uint8_t c = ldv(img + y * W + x);
+                        if (not_bg(c)) v = c;
+                    }
+                }
+                // Counter.most_common(1): highest count, first seen wins ties
+                int best = EITB_CODE_MUSCLE, best_cnt = 0, best_first = 64;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const int val = ci == 0 ? EITB_CODE_ADIPOSE : ci == 1 ? EITB_CODE_LUNG : EITB_CODE_BONE;
+                    const unsigned m = __ballot_sync(0xffffffffu, v == val);
+                    const int cnt = __popc(m), first = m ? __ffs(m) - 1 : 64;
+                    if (cnt > best_cnt || (cnt == best_cnt && cnt > 0 && first < best_first)) { best = val; best_cnt = cnt; best_first = first; }
+                }
+                // any other non-background code (does not occur in overlay images) is left alone
+                __syncwarp();
+                if (d == 0 && k < n) __stcg(img + px[k], (uint8_t)best);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ stage C: highlight_small_masks
+__device__ __forceinline__ bool is_t(const uint8_t* img, int H, int W, int y, int x, int t) {
+    return y >= 0 && y < H && x >= 0 && x < W && img[y * W + x] == (uint8_t)t;
+}
+
+// cv2 outer-border following from the raster-first pixel (y0, x0) of a component of {img == t}.
+// Emits the CHAIN_APPROX_SIMPLE points; returns their number, or 6 as soon as there are more than 5.
+__device__ int trace_simple(const uint8_t* img, int H, int W, int y0, int x0, int t, int (&vx)[5], int (&vy)[5]) {
+    const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1}, DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    int s = 4;
+    do { s = (s - 1) & 7; } while (!is_t(img, H, W, y0 + DY[s], x0 + DX[s], t) && s != 4);
+    if (s == 4) { vx[0] = x0; vy[0] = y0; return 1; }                // isolated pixel
+    const int y1 = y0 + DY[s], x1 = x0 + DX[s];
+    int y3 = y0, x3 = x0, prev_s = s ^ 4, n = 0;
+    for (;;) {
+        int y4, x4;
+        for (;;) {
+            s = (s + 1) & 7;
+            y4 = y3 + DY[s]; x4 = x3 + DX[s];
+            if (is_t(img, H, W, y4, x4, t)) break;
+        }
+        if (s != prev_s) {
+            if (n == 5) return 6;
+            vx[n] = x3; vy[n] = y3; ++n;
+        }
+        prev_s = s;
+        if (y4 == y0 && x4 == x0 && y3 == y1 && x3 == x1) break;
+        y3 = y4; x3 = x4; s = (s + 4) & 7;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256)
+contour_cand_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ lab, int B, int H, int W, int t,
+                    unsigned* __restrict__ bitmap, int words_per_img) {
+    const long long n = (long long)B * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / ((long long)H * W));
+        const int p = (int)(i - (long long)b * H * W);
+        const uint8_t* img = src + (long long)b * H * W;
+        if (img[p] != (uint8_t)t) continue;
+        const int y = p / W, x = p - y * W;
+        // a component's first pixel has no set neighbour earlier in raster order ...
+        if (is_t(img, H, W, y, x - 1, t) || is_t(img, H, W, y - 1, x - 1, t) || is_t(img, H, W, y - 1, x, t) ||
+            is_t(img, H, W, y - 1, x + 1, t))
+            continue;
+        // ... and an external contour has the frame-connected background on its left
+        if (x > 0 && lab[(long long)b * H * W + p - 1] != CC_OUT) continue;
+        int vx[5], vy[5];
+        const int nv = trace_simple(img, H, W, y, x, t, vx, vy);
+        if (nv > 5) continue;
+        bool first = true;                                          // p must be the raster-first vertex
+        for (int k = 0; k < nv; ++k) first = first && (vy[k] > y || (vy[k] == y && vx[k] >= x));
+        if (first) atomicOr(bitmap + (long long)b * words_per_img + (p >> 5), 1u << (p & 31));
+    }
+}
+
+// inside-or-on-boundary test against a closed polygon with integer vertices (exact)
+__device__ __forceinline__ bool in_poly(int x, int y, const int (&vx)[5], const int (&vy)[5], int nv) {
+    bool in = false;
+    for (int i = 0; i < nv; ++i) {
+        const int ax = vx[i], ay = vy[i], bx = vx[i + 1 == nv ? 0 : i + 1], by = vy[i + 1 == nv ? 0 : i + 1];
+        if ((bx - ax) * (y - ay) - (by - ay) * (x - ax) == 0 && x >= min(ax, bx) && x <= max(ax, bx) &&
+            y >= min(ay, by) && y <= max(ay, by))
+            return true;
+        if ((ay > y) != (by > y)) {
+            const int num = (bx - ax) * (y - ay), den = by - ay, lhs = (x - ax) * den;
+            if (den > 0 ? lhs < num : lhs > num) in = !in;
+        }
+    }
+    return in;
+}
+
+// one warp per image, candidates in DESCENDING raster order (cv2 returns contours last-found first)
+__global__ void __launch_bounds__(32)
+contour_repaint_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ code, int H, int W, int t,
+                       const unsigned* __restrict__ bitmap, int words_per_img) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const uint8_t* simg = src + (long long)b * H * W;
+    uint8_t* out = code + (long long)b * H * W;
+    const unsigned* bm = bitmap + (long long)b * words_per_img;
+    const int nchunks = (words_per_img + 31) / 32;
+    for (int ch = nchunks - 1; ch >= 0; --ch) {
+        const int w0 = ch * 32;
+        const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
+        unsigned nz = __ballot_sync(0xffffffffu, mine != 0);
+        while (nz) {
+            const int wl = 31 - __clz(nz);
+            nz &= ~(1u << wl);
+            unsigned word = __shfl_sync(0xffffffffu, mine, wl);
+            while (word) {
+                const int bit = 31 - __clz(word);
+                word &= ~(1u << bit);
+                const int p = ((w0 + wl) << 5) + bit;
+                int vx[5], vy[5];
+                const int nv = trace_simple(simg, H, W, p / W, p % W, t, vx, vy);   // uniform across the warp
+                int x0 = vx[0], x1 = vx[0], y0 = vy[0], y1 = vy[0];
+                for (int k = 1; k < nv; ++k) { x0 = min(x0, vx[k]); x1 = max(x1, vx[k]); y0 = min(y0, vy[k]); y1 = max(y1, vy[k]); }
+                // ring votes over the bounding box grown by one pixel, raster order
+                const int rx0 = max(x0 - 1, 0), rx1 = min(x1 + 1, W - 1), ry0 = max(y0 - 1, 0), ry1 = min(y1 + 1, H - 1);
+                const int bw = rx1 - rx0 + 1;
+                const long long cells = (long long)bw * (ry1 - ry0 + 1);
+                int cnt[4] = {0, 0, 0, 0};
+                long long first[4] = {-1, -1, -1, -1};               // votes: muscle, adipose, lung, bone
+                for (long long c0 = 0; c0 < cells; c0 += 32) {
+                    const long long c = c0 + lane;
+                    int v = 0;
+                    if (c < cells) {
+                        const int y = ry0 + (int)(c / bw), x = rx0 + (int)(c % bw);
+                        if (!in_poly(x, y, vx, vy, nv)) {
+                            bool near = false;
+                            for (int dy = -1; dy <= 1; ++dy)
+                                for (int dx = -1; dx <= 1; ++dx)
+                                    if ((dy || dx) && x + dx >= x0 && x + dx <= x1 && y + dy >= y0 && y + dy <= y1)
+                                        near = near || in_poly(x + dx, y + dy, vx, vy, nv);
+                            if (near) {
+                                const int cc = ldv(out + y * W + x);
+                                if (cc != t && cc != EITB_CODE_BLACK) v = cc;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int val = ci == 0 ? EITB_CODE_MUSCLE : ci == 1 ? EITB_CODE_ADIPOSE : ci == 2 ? EITB_CODE_LUNG : EITB_CODE_BONE;
+                        const unsigned m = __ballot_sync(0xffffffffu, v == val);
+                        if (m) {
+                            cnt[ci] += __popc(m);
+                            if (first[ci] < 0) first[ci] = c0 + __ffs(m) - 1;
+                        }
+                    }
+                }
+                int fill = t, best_cnt = 0;
+                long long best_first = 0;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int val = ci == 0 ? EITB_CODE_MUSCLE : ci == 1 ? EITB_CODE_ADIPOSE : ci == 2 ? EITB_CODE_LUNG : EITB_CODE_BONE;
+                    if (cnt[ci] > best_cnt || (cnt[ci] == best_cnt && cnt[ci] > 0 && first[ci] < best_first)) {
+                        fill = val; best_cnt = cnt[ci]; best_first = first[ci];
+                    }
+                }
+                __syncwarp();
+                const int fw = x1 - x0 + 1;
+                const long long fcells = (long long)fw * (y1 - y0 + 1);
+                for (long long c = lane; c < fcells; c += 32) {
+                    const int y = y0 + (int)(c / fw), x = x0 + (int)(c % fw);
+                    if (x >= 0 && x < W && y >= 0 && y < H && in_poly(x, y, vx, vy, nv)) __stcg(out + y * W + x, (uint8_t)fill);
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t eitb_label_cleanup_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t n = (size_t)B * H * W;
+    const size_t words = ((size_t)H * W + 31) / 32;
+    // labels int32, snapshot u8, bitmap, per-image flags
+    return align256(n * 4) + align256(n) + align256((size_t)B * words * 4) + align256((size_t)B * 4);
+}
+
+extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int H, int W, void* ws, size_t ws_bytes,
+                                  eitb_stream_t stream) {
+    if (!code || B < 0 || H <= 0 || W <= 0) return EITB_ERR_BAD_ARG;
+    if (B == 0) return EITB_OK;
+    if ((long long)H * W >= (1LL << 30)) return EITB_ERR_UNSUPPORTED;
+    if (!ws || ws_bytes < eitb_label_cleanup_workspace_bytes(B, H, W)) return EITB_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)B * H * W;
+    const int words = (int)(((size_t)H * W + 31) / 32);
+    char* p = reinterpret_cast<char*>(ws);
+    int32_t* lab = reinterpret_cast<int32_t*>(p); p += align256(n * 4);
+    uint8_t* snap = reinterpret_cast<uint8_t*>(p); p += align256(n);
+    unsigned* bitmap = reinterpret_cast<unsigned*>(p); p += align256((size_t)B * words * 4);
+    int* anybody = reinterpret_cast<int*>(p);
+    const int grid = eitb_grid((long long)n, 256, 8);
+
+    if (body) {
+        if (cudaMemsetAsync(anybody, 0, (size_t)B * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
+        if (cudaMemsetAsync(bitmap, 0, (size_t)B * words * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
+        fill_body_kernel<<<grid, 256, 0, s>>>(code, body, (long long)n, H * W, anybody);
+        EITB_CHECK_LAUNCH();
+        small_first_kernel<<<grid, 256, 0, s>>>(code, anybody, B, H, W, bitmap, words);
+        EITB_CHECK_LAUNCH();
+        small_repaint_kernel<<<B, 32, 0, s>>>(code, anybody, H, W, bitmap, words);
+        EITB_CHECK_LAUNCH();
+    }
+    if (cudaMemcpyAsync(snap, code, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return EITB_ERR_LAUNCH;
+    const int targets[3] = {EITB_CODE_BONE, EITB_CODE_MUSCLE, EITB_CODE_ADIPOSE};            // dict order, utils.py:782-787
+    for (int k = 0; k < 3; ++k) {
+        const int t = targets[k];
+        const int rc = cc_label<PRED_CODE_NE, 4>(snap, (size_t)H * W, t, B, H, W, 1, lab, s);
+        if (rc != EITB_OK) return rc;
+        if (cudaMemsetAsync(bitmap, 0, (size_t)B * words * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
+        contour_cand_kernel<<<grid, 256, 0, s>>>(snap, lab, B, H, W, t, bitmap, words);
+        EITB_CHECK_LAUNCH();
+        contour_repaint_kernel<<<B, 32, 0, s>>>(snap, code, H, W, t, bitmap, words);
+        EITB_CHECK_LAUNCH();
+    }
+    return EITB_OK;
+}

@@ -395,3 +395,56 @@ def test_body_mask_adversarial_vs_oracle(ops):
     got = ops.body_mask(dev(small), 1, -1024, True).cpu().numpy()
     for k in range(5):
         assert np.array_equal(got[k], O.body_mask(small[k], -1024, 1))
+
+
+# ----------------------------------------------------------------------------------- K7
+@pytest.mark.parametrize("tag,seed,size,use_body", [("seg0", 0, 512, True), ("seg1", 1, 512, True),
+                                                    ("seg2", 2, 256, False), ("seg3", 3, 512, True)])
+def test_label_cleanup_reference_golden(ops, golden, tag, seed, size, use_body):
+    """Overlay image produced by the real reference -> our clean-up == the real reference's."""
+    code = O.bgr_to_code(golden[f"{tag}_overlay"])
+    body = None
+    if use_body:
+        ic = -1024 if seed % 2 == 0 else 0
+        body = O.body_mask(synth.phantom_slice(seed, ic, size=size), ic, 1)
+    got = ops.label_cleanup(dev(code[None]), None if body is None else dev(body[None]))[0].cpu().numpy()
+    assert np.array_equal(O.code_to_bgr(got), golden[f"{tag}_color"])
+
+
+def _noisy_codes(rng, S, it):
+    base = rng.choice([0, 1, 3, 6, 7], p=[.2, .35, .15, .15, .15], size=(S // 8, S // 8)).astype(np.uint8)
+    code = np.kron(base, np.ones((8, 8), np.uint8))
+    nz = rng.random((S, S)) < rng.choice([0.005, 0.03, 0.12])
+    code[nz] = rng.choice([0, 1, 3, 6, 7], size=int(nz.sum()))
+    if it % 3 == 0:                                    # rings with nested islands, big 4-point rectangles
+        code[5:20, 5:20] = 7; code[8:17, 8:17] = 6; code[11:13, 11:13] = 7
+        code[25:35, 22:36] = 1; code[27:33, 24:34] = 6; code[29, 28] = 1
+        code[40:44, 40:90] = 3; code[41, 60] = 0
+    return code
+
+
+def test_label_cleanup_adversarial_vs_oracle(ops):
+    rng = np.random.default_rng(12)
+    S = 128
+    codes = np.stack([_noisy_codes(rng, S, it) for it in range(48)])
+    yy, xx = np.mgrid[0:S, 0:S]
+    bodies = np.stack([np.where(((yy - 64) / rng.integers(30, 64)) ** 2 + ((xx - 64) / rng.integers(30, 64)) ** 2 < 1, 255, 0)
+                       for _ in range(48)]).astype(np.uint8)
+    bodies[5] = 0                                        # empty body mask: clear_color_output is skipped
+    got_nb = ops.label_cleanup(dev(codes.copy()), None).cpu().numpy()
+    got_b = ops.label_cleanup(dev(codes.copy()), dev(bodies)).cpu().numpy()
+    for k in range(len(codes)):
+        assert np.array_equal(got_nb[k], O.highlight_small_codes(codes[k])), ("nobody", k)
+        want = O.highlight_small_codes(O.clear_codes(bodies[k], codes[k]) if bodies[k].any() else codes[k])
+        assert np.array_equal(got_b[k], want), ("body", k, int((got_b[k] != want).sum()))
+
+
+def test_label_cleanup_full_size_pipeline(ops):
+    """512x512: decoded teacher masks + specks -> overlay -> clean-up, vs the oracle end to end."""
+    from oracle.gen_golden import segmentation_case
+    for seed, noise in ((5, 150), (6, 400)):
+        masks, cls = segmentation_case(seed, 512, noise)
+        code = O.overlay_codes(O.class_union_masks(masks, cls, 512))
+        body = O.body_mask(synth.phantom_slice(seed, -1024), -1024, 1)
+        got = ops.label_cleanup(dev(code[None].copy()), dev(body[None]))[0].cpu().numpy()
+        assert np.array_equal(got, O.create_color_codes(O.class_union_masks(masks, cls, 512), body))
