@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the kt_service imaging hot path (BASELINE.json metric: CT slices/s, series -> labels).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): synthetic 320-slice
+512x512 int16 series, dicom_sequences_auto in throughput mode -- coronal rib scan + slice pick for
+the series AND every slice through body mask -> HU window/NCHW -> YOLO11s-seg (PyTorch/cuDNN,
+random-init, class bias shifted) -> NMS -> mask decode/overlay -> label clean-up.  With N GPUs the
+batch is N such series, each cut into N contiguous z-ranges (weak scaling: 320 slices per GPU per
+step); the only exchange is the all-gather of coronal rows/min-max and of the selected indices.
+
+One "step" = one pass over the batch.  ``value`` counts slices/s with the int16 pixels already in
+HBM; ``e2e`` is the same pass through ``ImagingPipeline`` from pinned HOST memory with the
+host->device copy of the pixels and the device->host copy of the label maps inside the timed
+region.  Inputs (168 MB per GPU) exceed the 126 MB L2, so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SLICES = 320
+SIZE = 512
+METRIC = "ct_slices_per_sec_series_to_labels"
+UNIT = "slices/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunk", type=int, default=64, help="slices per CNN batch")
+    ap.add_argument("--slices", type=int, default=N_SLICES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config(world):
+    return {"workload": "configs[2]: synthetic 320-slice 512x512 int16 series, dicom_sequences_auto "
+                        "(rib-slice selection + every slice segmented and labelled)",
+            "series_per_step": world, "slices_per_series": N_SLICES, "slice": [SIZE, SIZE],
+            "sharding": "z-range per GPU, all-gather of coronal rows" if world > 1 else "single GPU",
+            "l2": "inputs (168 MB/GPU) larger than L2, no flush", "weights": "random-init YOLO11s-seg x3, class bias shifted"}
+
+
+# =============================================================================== clocks
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =============================================================================== CPU arm
+def cpu_path_rate(budget_s: float, threads: int, steps: int = 1, warmup: int = 0):
+    """Oracle port of the per-series path on the host cores.  Returns (slices/s, sample text, ms/step)."""
+    import numpy as np
+    import torch
+    from eitsynthai_b200 import synth
+    from eitsynthai_b200.yolo_seg import YOLO11sSeg
+    from oracle import cpu_path
+
+    torch.set_num_threads(threads)
+    try:
+        import cv2
+        cv2.setNumThreads(threads)
+    except Exception:
+        pass
+    torch.manual_seed(1)
+    model = YOLO11sSeg(4).eval()
+    # same class-bias idea as the GPU arm so NMS / mask decode see candidates
+    px0 = synth.phantom_slice(0)
+    with torch.no_grad():
+        from oracle import imaging as O, yolo_post as Y
+        x = Y.preprocess(O.apply_mask(O.classic_norm(px0), O.body_mask(px0, -1024, 1)), SIZE)
+        model.shift_class_bias(x)
+    t0 = time.perf_counter()
+    cpu_path.segment_slice_cpu(px0, model)                       # warm-up + cost probe
+    per_slice = time.perf_counter() - t0
+    n = max(1, min(32, int(budget_s / max(per_slice, 1e-3) / max(steps + warmup, 1))))
+    slices = [synth.phantom_slice(100 + i) for i in range(n)]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for px in slices:
+            cpu_path.segment_slice_cpu(px, model)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return n / dt, f"{n} phantom slices per step through the oracle port (norm, body mask, CNN fp32 on CPU, NMS, " \
+                   f"mask decode, label clean-up); rib scan excluded (1 CNN call per 320 slices)", dt * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rate, sample, ms = cpu_path_rate(120.0, threads, max(args.steps, 1), min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# =============================================================================== GPU arm
+class StageTimer:
+    """CUDA-event pairs around each stage on the launching stream."""
+
+    def __init__(self, torch):
+        self.torch, self.pairs, self.on = torch, {}, False
+
+    def __call__(self, name):
+        return _Span(self, name)
+
+    def totals(self):
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.pairs.items()}
+
+
+class _Span:
+    def __init__(self, t, name):
+        self.t, self.name = t, name
+
+    def __enter__(self):
+        if self.t.on:
+            self.a = self.t.torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.t.on:
+            b = self.t.torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.t.pairs.setdefault(self.name, []).append((self.a, b))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from eitsynthai_b200 import host, ops, sharded, synth
+    from eitsynthai_b200.pipeline import CONF, IOU, MAX_DET, ImagingPipeline, SeriesMeta
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+
+    pipe = ImagingPipeline(dev, torch.float16, seed=0)
+    S = world                                                     # series per step (weak scaling)
+    nslices = args.slices
+    z0, z1 = sharded.shard_range(nslices, world, rank)
+    nl = z1 - z0
+    # this rank's shard of every series, file order shuffled inside the shard
+    vols, insts = [], []
+    for s in range(S):
+        v, i = synth.phantom_series(nslices, seed=s, shuffle_seed=17 + s, z_range=(z0, z1))
+        vols.append(v); insts.append(i)
+    px_host = torch.from_numpy(np.stack(vols)).pin_memory()        # [S, nl, H, W]
+    labels_host = torch.empty((S, nl, SIZE, SIZE), dtype=torch.uint8).pin_memory()
+    px_dev = px_host.to(dev)
+    metas = [SeriesMeta(insts[s]) for s in range(S)]
+    orders = [torch.from_numpy(host.instance_order(m.instance_numbers)).to(dev) for m in metas]
+    row, fx, fz = host.front_geometry(SIZE)
+    timer = StageTimer(torch)
+    copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    launches = {"n": 0}
+
+    def rib_stage(px):
+        """coronal rows of the local shard -> exchange -> rib model on the owned series -> indices."""
+        with timer("K3_front_rows"):
+            rows = torch.empty((S, nl, SIZE), dtype=torch.int16, device=dev)
+            mm = torch.empty((S, 2), dtype=torch.int32, device=dev)
+            mm[:, 0] = 2 ** 31 - 1; mm[:, 1] = -2 ** 31
+            for s in range(S):
+                r, _ = ops.front_rows(px[s], orders[s], nl, row, fx, fz, mm[s])
+                rows[s] = r
+            launches["n"] += S
+        with timer("C1_exchange"):
+            rows_all, mm_all = sharded.gather_rows(rows, mm, nslices)
+        sel = torch.zeros((S, 4), dtype=torch.int32, device=dev)
+        mine = [s for s in range(S) if sharded.owner_of_series(s, world) == rank]
+        if mine:
+            with timer("K3_minmax_letterbox"):
+                front = torch.stack([ops.minmax_u8(rows_all[s], mm_all[s]) for s in mine])
+                x, (gain, pad_x, pad_y, w0, h0) = pipe._rib_input(front)
+                launches["n"] += len(mine) + 1
+            with timer("CNN_ribs"):
+                head, _ = pipe.ribs_model(x)
+                head = head.contiguous()
+            with timer("K5_nms_ribs"):
+                dets, _, k = ops.nms(head, 1, CONF, IOU, MAX_DET, want_idx=False)
+            with timer("K4_rib_select"):
+                boxes = ops.scale_boxes(dets, k, gain, pad_x, pad_y, w0, h0)
+                sel[mine] = ops.rib_select(boxes, k, 512.0)
+            launches["n"] += 3
+        with timer("C1_exchange"):
+            sel = sharded.share_selected(sel)
+        return sel
+
+    def slice_stage(px_chunk):
+        with timer("K2_body_mask"):
+            body = ops.body_mask(px_chunk, 1, -1024, True)
+        with timer("K1_hu_window_nchw"):
+            _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=torch.float16)
+        with timer("CNN_axial"):
+            head, protos = pipe.axial_model_512(x.contiguous(memory_format=torch.channels_last))
+            head, protos = head.contiguous(), protos.contiguous()
+        with timer("K5_nms"):
+            dets, _, n = ops.nms(head, 4, CONF, IOU, MAX_DET, want_idx=False)
+        with timer("K6_mask_decode"):
+            code, _, _ = ops.mask_decode(dets, n, protos, 0)
+        with timer("K7_label_cleanup"):
+            ops.label_cleanup(code, body)
+        launches["n"] += 11 + 1 + 1 + 1 + 18
+        return code, n
+
+    flat_dev = px_dev.view(S * nl, SIZE, SIZE)
+    flat_host = px_host.view(S * nl, SIZE, SIZE)
+    flat_labels_host = labels_host.view(S * nl, SIZE, SIZE)
+    ndet_total = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def step_device():
+        sel = rib_stage(px_dev)
+        for c0 in range(0, S * nl, args.chunk):
+            code, n = slice_stage(flat_dev[c0:c0 + args.chunk])
+            ndet_total.add_(n.sum())
+        return sel
+
+    stage_buf = torch.empty((S * nl, SIZE, SIZE), dtype=torch.int16, device=dev)
+
+    def step_e2e():
+        """Same pass from pinned host memory: H2D of the pixels, D2H of the label maps and indices."""
+        main = torch.cuda.current_stream(dev)
+        copy_in.wait_stream(main)
+        evs = []
+        with torch.cuda.stream(copy_in):
+            for c0 in range(0, S * nl, args.chunk):
+                stage_buf[c0:c0 + args.chunk].copy_(flat_host[c0:c0 + args.chunk], non_blocking=True)
+                e = torch.cuda.Event(); e.record(copy_in); evs.append(e)
+        keep = []
+        for ci, c0 in enumerate(range(0, S * nl, args.chunk)):
+            main.wait_event(evs[ci])
+            code, n = slice_stage(stage_buf[c0:c0 + args.chunk])
+            e = torch.cuda.Event(); e.record(main)
+            copy_out.wait_event(e)
+            with torch.cuda.stream(copy_out):
+                flat_labels_host[c0:c0 + args.chunk].copy_(code, non_blocking=True)
+            code.record_stream(copy_out)
+            keep.append(code)
+        sel = rib_stage(stage_buf.view(S, nl, SIZE, SIZE))
+        main.wait_stream(copy_out)
+        return sel.cpu()                                          # result read on the host
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        timer.on = True
+        timer.pairs = {}
+        l0 = launches["n"]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()                                # no-op unless run under ncu --profile-from-start off
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        timer.on = False
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, out, launches["n"] - l0, timer.totals()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, sel, n_launch, stages = timed(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    total_slices = S * nslices                                     # all ranks together
+    value = total_slices / (ms_dev / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+        e2e = {"value": total_slices / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(px_host.numel() * 2), "d2h_bytes_per_step": int(labels_host.numel() + S * 16)}
+
+    # ---------------------------------------------------------------- roofline of the dominant own kernel
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    per_slice_bytes = {           # algorithmic bytes per 512x512 slice, DESIGN.md §4
+        "K1_hu_window_nchw": SIZE * SIZE * (2 + 1 + 6),           # int16 in, u8 mask in, 3 x fp16 out
+        "K2_body_mask": SIZE * SIZE * (2 + 1),                    # int16 in, u8 mask out
+        "K5_nms": 40 * 5376 * 2 + MAX_DET * 38 * 4,               # fp16 head in, dets out
+        "K6_mask_decode": 32 * 128 * 128 * 2 + MAX_DET * 38 * 4 + SIZE * SIZE,   # fp16 protos + dets in, u8 codes out
+        "K7_label_cleanup": SIZE * SIZE * (1 + 1 + 1),            # codes in/out, body in
+    }
+    own = {k: v for k, v in stages.items() if k in per_slice_bytes}
+    roof = None
+    if own:
+        top = max(own, key=own.get)
+        n_calls = args.steps * ((S * nl + args.chunk - 1) // args.chunk)
+        ms_call = own[top] / n_calls
+        ach = per_slice_bytes[top] * min(args.chunk, S * nl) / (ms_call / 1e3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "traffic": None, "ms_per_launch": ms_call, "slices_per_launch": min(args.chunk, S * nl),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            rate, sample, _ = cpu_path_rate(20.0, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 (CNN) / int16,u8,f32 (kernels)", "data": "synthetic",
+                "config": dict(config(world), chunk=args.chunk, class_bias_shift=pipe.bias_shift,
+                               mean_detections_per_slice=float(ndet_total) / max(1, (max(args.warmup, 3) + args.steps) * S * nl)),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roof, "cpu_baseline": cpu,
+                "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stages.items())},
+                "selected_slices": sel.cpu().tolist()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

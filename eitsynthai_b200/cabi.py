@@ -41,6 +41,7 @@ SIGNATURES = {
     "eitb_minmax_u8": (_i, [_p, _i64, _p, _p, _p]),
     "eitb_letterbox_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "eitb_rib_select": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),
+    "eitb_scale_boxes": (_i, [_p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _p, _p]),
     "eitb_nms_workspace_bytes": (_sz, [_i, _i]),
     "eitb_nms": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _sz, _p]),
     "eitb_mask_decode_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -20,7 +20,7 @@ namespace eitb_cc {
 constexpr int kStripPixels = 16384;     // 64 KB of int32 labels per CTA
 constexpr int kThreads = 512;
 
-enum Pred { PRED_U8_NONZERO = 0, PRED_U8_ZERO = 1, PRED_LABEL_NOT_OUT = 2, PRED_CODE_NE = 3, PRED_CODE_NOT_BG = 4 };
+enum Pred { PRED_U8_NONZERO = 0, PRED_U8_ZERO = 1, PRED_LABEL_NOT_OUT = 2, PRED_CODE_NE = 3, PRED_CODE_NOT_BG = 4, PRED_BIT_ZERO = 5 };
 
 // is pixel i of this image in the set?
 template <int PRED>
@@ -29,6 +29,7 @@ __device__ __forceinline__ bool in_set(const void* __restrict__ src, long long i
     if (PRED == PRED_U8_ZERO) return reinterpret_cast<const uint8_t*>(src)[i] == 0;
     if (PRED == PRED_LABEL_NOT_OUT) return reinterpret_cast<const int32_t*>(src)[i] != CC_OUT;
     if (PRED == PRED_CODE_NE) return reinterpret_cast<const uint8_t*>(src)[i] != (uint8_t)arg;
+    if (PRED == PRED_BIT_ZERO) return ((reinterpret_cast<const uint32_t*>(src)[i >> 5] >> (i & 31)) & 1u) == 0;
     const uint8_t c = reinterpret_cast<const uint8_t*>(src)[i];           // PRED_CODE_NOT_BG
     return c != EITB_CODE_BLACK && c != EITB_CODE_MUSCLE;
 }
@@ -70,6 +71,11 @@ __device__ __forceinline__ void gunion(int* L, int a, int b) {     // a: pixel i
     }
 }
 
+// Strip-local labelling.  Pixels are visited in 32-pixel row segments, one per warp iteration:
+// the segment's occupancy word comes from a ballot (or straight from a bit image), every pixel is
+// pointed at the first pixel of its run inside the segment, and unions are issued only where runs
+// meet -- segment to segment along a row, and at the first pixel of every overlap with the row
+// above -- so a uniform region costs a handful of shared-memory atomics per row, not per pixel.
 template <int PRED, int CONN>
 __global__ void __launch_bounds__(kThreads)
 cc_local_kernel(const void* __restrict__ src, size_t src_img_stride_bytes, int arg, int H, int W, int strip_h,
@@ -80,19 +86,42 @@ cc_local_kernel(const void* __restrict__ src, size_t src_img_stride_bytes, int a
     const int y0 = sidx * strip_h;
     const int rows = min(strip_h, H - y0);
     const int n = rows * W;
+    const int spr = (W + 31) >> 5;                       // segments per row
+    const int nseg = rows * spr;
+    unsigned* segmask = reinterpret_cast<unsigned*>(sl + kStripPixels);
     const void* img = reinterpret_cast<const char*>(src) + (size_t)b * src_img_stride_bytes;
     const long long base = (long long)y0 * W;
-    for (int i = threadIdx.x; i < n; i += kThreads) sl[i] = in_set<PRED>(img, base + i, arg) ? i : CC_NONE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads >> 5;
+
+    for (int sg = warp; sg < nseg; sg += nwarps) {
+        const int y = sg / spr, x = ((sg - y * spr) << 5) + lane;
+        const int i = y * W + x;
+        const bool in = x < W && in_set<PRED>(img, base + i, arg);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) segmask[sg] = m;
+        if (x < W) {
+            int l = CC_NONE;
+            if (in) l = i - (__clz(~(m << (31 - lane))) - 1);          // first pixel of the run within the segment
+            sl[i] = l;
+        }
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        if (sl[i] == CC_NONE) continue;
-        const int y = i / W, x = i - y * W;
-        if (x > 0 && sl[i - 1] != CC_NONE) sunion(sl, i, i - 1);
+    for (int sg = warp; sg < nseg; sg += nwarps) {
+        const unsigned m = segmask[sg];
+        if (m == 0) continue;
+        const int y = sg / spr, sx = sg - y * spr, x = (sx << 5) + lane;
+        const int i = y * W + x;
+        const bool in = (m >> lane) & 1u;
+        if (lane == 0 && in && sx > 0 && (segmask[sg - 1] >> 31)) sunion(sl, i, i - 1);
         if (y > 0) {
-            if (sl[i - W] != CC_NONE) sunion(sl, i, i - W);
-            if (CONN == 8) {
-                if (x > 0 && sl[i - W - 1] != CC_NONE) sunion(sl, i, i - W - 1);
-                if (x + 1 < W && sl[i - W + 1] != CC_NONE) sunion(sl, i, i - W + 1);
+            const unsigned up = segmask[sg - spr];
+            const unsigned both = m & up;
+            if ((both & ~(both << 1)) >> lane & 1u) sunion(sl, i, i - W);
+            if (CONN == 8 && in && !((up >> lane) & 1u)) {
+                const unsigned upl = (up << 1) | (sx > 0 ? segmask[sg - spr - 1] >> 31 : 0u);
+                const unsigned upr = (up >> 1) | (sx + 1 < spr ? segmask[sg - spr + 1] << 31 : 0u);
+                if ((upl >> lane) & 1u) sunion(sl, i, i - W - 1);
+                if ((upr >> lane) & 1u) sunion(sl, i, i - W + 1);
             }
         }
     }
@@ -167,8 +196,8 @@ int cc_label(const void* src, size_t src_img_stride_bytes, int arg, int B, int H
     if (W > kStripPixels) return EITB_ERR_UNSUPPORTED;
     const int sh = strip_rows(H, W);
     const int spi = eitb_div_up(H, sh);
-    const size_t smem = (size_t)sh * W * sizeof(int);
-    if (cudaFuncSetAttribute(cc_local_kernel<PRED, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStripPixels * sizeof(int))) != cudaSuccess)
+    const size_t smem = kStripPixels * sizeof(int) + (size_t)sh * ((W + 31) / 32) * sizeof(unsigned);
+    if (cudaFuncSetAttribute(cc_local_kernel<PRED, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     cc_local_kernel<PRED, CONN><<<B * spi, kThreads, smem, s>>>(src, src_img_stride_bytes, arg, H, W, sh, spi, labels);
     EITB_CHECK_LAUNCH();

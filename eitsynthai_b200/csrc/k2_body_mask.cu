@@ -75,6 +75,58 @@ dilate_kernel(const uint8_t* __restrict__ er, int B, int H, int W, uint8_t* __re
     }
 }
 
+// ---- bit-image path (W % 32 == 0): one bit per pixel, 32 pixels per word, LSB = lowest x
+__global__ void __launch_bounds__(256)
+thr_bits_kernel(const int16_t* __restrict__ px, long long n_units, int H, int W, int slope, int intercept, int flipud,
+                uint32_t* __restrict__ bits) {
+    const int upr = W >> 3;                                       // 8-pixel units per row
+    const long long nround = (n_units + 31) & ~31LL;              // keep whole warps in the shuffles below
+    for (long long uu = (long long)blockIdx.x * blockDim.x + threadIdx.x; uu < nround; uu += (long long)gridDim.x * blockDim.x) {
+        const bool active = uu < n_units;
+        const long long u = active ? uu : n_units - 1;
+        const long long rowid = u / upr;                          // b * H + y (output orientation)
+        const int c = (int)(u - rowid * upr);
+        const long long b = rowid / H;
+        const int y = (int)(rowid - b * H);
+        const int sy = flipud ? H - 1 - y : y;
+        const int4 raw = ld_stream_int4(reinterpret_cast<const int4*>(px + ((b * H + sy) * (long long)W + c * 8)));
+        const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+        unsigned v = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = (int)(short)((w[j >> 1] >> ((j & 1) * 16)) & 0xffff);
+            v |= (hu_in_range(p, slope, intercept) ? 1u : 0u) << j;
+        }
+        v <<= 8 * (threadIdx.x & 3);                               // 4 neighbouring threads make one word
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        if (active && (threadIdx.x & 3) == 0) bits[u >> 2] = v;
+    }
+}
+
+// 5x5 box erosion (ERODE: outside the image counts as set) or dilation (outside counts as unset)
+template <bool ERODE>
+__global__ void __launch_bounds__(256)
+morph5_bits_kernel(const uint32_t* __restrict__ in, long long n_words, int H, int wpr, uint32_t* __restrict__ out) {
+    const uint32_t fill = ERODE ? 0xffffffffu : 0u;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_words; t += (long long)gridDim.x * blockDim.x) {
+        const long long rowid = t / wpr;
+        const int wx = (int)(t - rowid * wpr);
+        const int y = (int)(rowid % H);
+        uint32_t acc = fill;
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy) {
+            if (y + dy < 0 || y + dy >= H) continue;
+            const uint32_t* r = in + (rowid + dy) * wpr;
+            const uint32_t C = r[wx], L = wx > 0 ? r[wx - 1] : fill, R = wx + 1 < wpr ? r[wx + 1] : fill;
+            const uint32_t m1 = (C << 1) | (L >> 31), m2 = (C << 2) | (L >> 30);
+            const uint32_t p1 = (C >> 1) | (R << 31), p2 = (C >> 2) | (R << 30);
+            if (ERODE) acc &= C & m1 & m2 & p1 & p2; else acc |= C | m1 | m2 | p1 | p2;
+        }
+        out[t] = acc;
+    }
+}
+
 // 2*contourArea per component: +2 for every full 2x2 block, +1 for every block with 3 pixels.
 // Blocks are anchored at (y, x) = top-left pixel, y in [-1, H-1], x in [-1, W-1].
 __global__ void __launch_bounds__(256)
@@ -161,11 +213,26 @@ extern "C" int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope,
     long long* best = reinterpret_cast<long long*>(p);
     const int grid = eitb_grid((long long)n, 256, 8);
 
-    thr_erode_kernel<<<grid, 256, 0, s>>>(px, B, H, W, slope, intercept, flipud, er);
-    EITB_CHECK_LAUNCH();
-    dilate_kernel<<<grid, 256, 0, s>>>(er, B, H, W, opened);
-    EITB_CHECK_LAUNCH();
-    int rc = cc_label<PRED_U8_ZERO, 4>(opened, (size_t)H * W, 0, B, H, W, 1, labA, s);       // background, frame-linked
+    int rc;
+    if ((W & 31) == 0 && !(reinterpret_cast<uintptr_t>(px) & 15)) {
+        // bit images: threshold -> erode -> dilate touch 1/16 of the bytes of the u8 path
+        uint32_t* b0 = reinterpret_cast<uint32_t*>(er);
+        uint32_t* b1 = reinterpret_cast<uint32_t*>(opened);
+        const long long n_words = (long long)n / 32;
+        thr_bits_kernel<<<eitb_grid((long long)n / 8, 256, 8), 256, 0, s>>>(px, (long long)n / 8, H, W, slope, intercept, flipud, b0);
+        EITB_CHECK_LAUNCH();
+        morph5_bits_kernel<true><<<eitb_grid(n_words, 256, 8), 256, 0, s>>>(b0, n_words, H, W / 32, b1);
+        EITB_CHECK_LAUNCH();
+        morph5_bits_kernel<false><<<eitb_grid(n_words, 256, 8), 256, 0, s>>>(b1, n_words, H, W / 32, b0);
+        EITB_CHECK_LAUNCH();
+        rc = cc_label<PRED_BIT_ZERO, 4>(b0, (size_t)H * W / 8, 0, B, H, W, 1, labA, s);         // background, frame-linked
+    } else {
+        thr_erode_kernel<<<grid, 256, 0, s>>>(px, B, H, W, slope, intercept, flipud, er);
+        EITB_CHECK_LAUNCH();
+        dilate_kernel<<<grid, 256, 0, s>>>(er, B, H, W, opened);
+        EITB_CHECK_LAUNCH();
+        rc = cc_label<PRED_U8_ZERO, 4>(opened, (size_t)H * W, 0, B, H, W, 1, labA, s);
+    }
     if (rc != EITB_OK) return rc;
     rc = cc_label<PRED_LABEL_NOT_OUT, 8>(labA, (size_t)H * W * 4, 0, B, H, W, 0, labB, s);   // filled regions
     if (rc != EITB_OK) return rc;

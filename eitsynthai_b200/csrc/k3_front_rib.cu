@@ -178,7 +178,37 @@ __global__ void rib_select_kernel(const float* __restrict__ xyxy, const int32_t*
     }
 }
 
+// ultralytics scale_boxes: network-input px -> original-image px.
+__global__ void scale_boxes_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n, int B, int max_det,
+                                   int D, float gain, float pad_x, float pad_y, float w0, float h0,
+                                   float* __restrict__ xyxy) {
+    const int total = B * max_det;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = i / max_det, r = i - b * max_det;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n[b]) {
+            const float* d = dets + (long long)i * D;
+            o.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(d[0], pad_x), gain), 0.f), w0);
+            o.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(d[1], pad_y), gain), 0.f), h0);
+            o.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(d[2], pad_x), gain), 0.f), w0);
+            o.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(d[3], pad_y), gain), 0.f), h0);
+        }
+        reinterpret_cast<float4*>(xyxy)[i] = o;
+    }
+}
+
 }  // namespace
+
+extern "C" int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, int row_floats, float gain,
+                                float pad_x, float pad_y, float orig_w, float orig_h, float* xyxy,
+                                eitb_stream_t stream) {
+    if (!dets || !n || !xyxy || B < 0 || max_det <= 0 || row_floats < 4 || !(gain > 0.f)) return EITB_ERR_BAD_ARG;
+    if (B == 0) return EITB_OK;
+    scale_boxes_kernel<<<eitb_grid((long long)B * max_det, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        dets, n, B, max_det, row_floats, gain, pad_x, pad_y, orig_w, orig_h, xyxy);
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
+}
 
 extern "C" int eitb_front_rows(const int16_t* px, const int32_t* order, int n, int H, int W, int row,
                                int flip_x, int flip_z, int16_t* rows, int32_t* minmax, eitb_stream_t stream) {

@@ -152,6 +152,19 @@ def nms(head: torch.Tensor, nc: int, conf: float = 0.3, iou: float = 0.7, max_de
     return dets, idx, n
 
 
+def scale_boxes(dets: torch.Tensor, n: torch.Tensor, gain: float, pad_x: float, pad_y: float, orig_w: float,
+                orig_h: float) -> torch.Tensor:
+    """dets [B,max_det,D] (network px) -> xyxy [B,max_det,4] in original-image px (ultralytics scale_boxes)."""
+    _chk(dets, torch.float32, "dets")
+    _chk(n, torch.int32, "n")
+    B, max_det, D = dets.shape
+    out = torch.empty((B, max_det, 4), dtype=torch.float32, device=dets.device)
+    with torch.cuda.device(dets.device):
+        cabi.call("eitb_scale_boxes", dets.data_ptr(), n.data_ptr(), B, max_det, D, float(gain), float(pad_x),
+                  float(pad_y), float(orig_w), float(orig_h), out.data_ptr(), _stream(dets))
+    return out
+
+
 # ------------------------------------------------------------------------------------ K6
 def mask_decode(dets: torch.Tensor, n_det: torch.Tensor, protos: torch.Tensor, variant: int = 0,
                 want_area: bool = False, want_bits: bool = False):

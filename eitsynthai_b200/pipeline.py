@@ -1,0 +1,203 @@
+"""Device-resident imaging pipeline: series -> coronal rib scan -> slice pick -> per-slice
+body mask / window / CNN / NMS / mask decode / label clean-up, and mesh labelling.
+
+Mirrors the order of ``DICOMSequencesToMask.get_coordinate_slice_from_dicom``
+(kt_service/ai_tools/ai_tools.py:188-231) and of the other four entry points; every stage except
+the CNN is one libeitb200 call (``ops``).  Host buffers come in pinned, go to HBM on a copy
+stream and the label maps come back the same way, chunk by chunk, so copies overlap compute.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import host, ops
+from .yolo_seg import build_model
+
+CONF = 0.3          # ai_tools.py:121,153
+IOU = 0.7           # ultralytics default
+MAX_DET = 300
+
+
+@dataclass
+class SeriesMeta:
+    """The DICOM tags the hot path reads (utils.py:96-105, 621-656; ai_tools.py:384)."""
+    instance_numbers: np.ndarray                       # per file, any order
+    patient_position: str = "HFS"
+    image_orientation: tuple = (1, 0, 0, 0, 1, 0)
+    patient_orientation: tuple | None = None
+    rescale_slope: int = 1
+    rescale_intercept: int = -1024
+    pixel_spacing: tuple = (0.753906, 0.753906)
+
+
+@dataclass
+class SeriesResult:
+    labels: torch.Tensor | None = None                 # [n, H, W] u8 code image per processed slice (device)
+    body: torch.Tensor | None = None
+    selected: list = field(default_factory=list)       # [y6, y7, mid(+custom)] or [] (reference sentinel)
+    front_u8: torch.Tensor | None = None               # [N, W] coronal image
+    rib_boxes: torch.Tensor | None = None              # [k, 4] in coronal px
+    n_det: torch.Tensor | None = None
+
+
+class ImagingPipeline:
+    """Owns the three networks (rib, axial 256, axial 512 -- ai_tools.py:52,66-67) and scratch memory."""
+
+    def __init__(self, device="cuda:0", dtype=torch.float16, seed: int = 0, calibrate: bool = True,
+                 mask_variant: int = 0):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.mask_variant = mask_variant
+        self.ribs_model = build_model(1, self.device, dtype, seed)
+        self.axial_model_512 = build_model(4, self.device, dtype, seed + 1)
+        self.axial_model_256 = build_model(4, self.device, dtype, seed + 2)
+        self.bias_shift = {}
+        if calibrate:
+            self._calibrate()
+
+    # ------------------------------------------------------------------ random-init calibration
+    @torch.no_grad()
+    def _calibrate(self):
+        """Random-init class heads score ~0: shift the class bias so ~1 % of the anchors
+        of a phantom batch pass conf=0.3.  The shifts are reported by bench.py."""
+        from . import synth
+        px = torch.from_numpy(np.stack([synth.phantom_slice(s) for s in range(4)])).to(self.device)
+        body = ops.body_mask(px, 1, -1024, True)
+        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype)
+        x = x.contiguous(memory_format=torch.channels_last)
+        self.bias_shift["axial512"] = self.axial_model_512.shift_class_bias(x)
+        x256 = torch.nn.functional.interpolate(x, size=(256, 256)).contiguous(memory_format=torch.channels_last)
+        self.bias_shift["axial256"] = self.axial_model_256.shift_class_bias(x256)
+        vol, inst = synth.phantom_series(64, seed=0)
+        front = self.coronal(torch.from_numpy(vol).to(self.device), SeriesMeta(inst))
+        self.bias_shift["ribs"] = self.ribs_model.shift_class_bias(self._rib_input(front[None])[0], frac=0.004)
+
+    # ------------------------------------------------------------------ a2/a3: coronal image
+    def coronal(self, px: torch.Tensor, meta: SeriesMeta, minmax: torch.Tensor | None = None,
+                return_rows: bool = False):
+        """[N,H,W] int16 in file order -> coronal image [N,W] u8 (one row per slice, MINMAX-normalised)."""
+        n, H, W = px.shape
+        order = torch.from_numpy(host.instance_order(meta.instance_numbers)).to(px.device, non_blocking=True)
+        row, fx, fz = host.front_geometry(H, meta.patient_position, meta.image_orientation, meta.patient_orientation)
+        rows, mm = ops.front_rows(px, order, n, row, fx, fz, minmax)
+        if return_rows:
+            return rows, mm
+        return ops.minmax_u8(rows, mm)
+
+    def _rib_input(self, front: torch.Tensor):
+        """[S,N,W] u8 -> letterboxed network input (imgsz 640, auto) + the scale_boxes parameters."""
+        S, N, W = front.shape
+        nh, nw, top, bottom, left, right = host.letterbox_geometry(N, W, 640)
+        x = ops.letterbox_nchw(front, nh, nw, top, left, nh + top + bottom, nw + left + right, self.dtype)
+        x = x.contiguous(memory_format=torch.channels_last)
+        gain, pad_x, pad_y = host.scale_boxes_params((nh + top + bottom, nw + left + right), (N, W))
+        return x, (gain, pad_x, pad_y, W, N)
+
+    # ------------------------------------------------------------------ a4/a5: rib detection + slice pick
+    @torch.no_grad()
+    def rib_select(self, front: torch.Tensor, custom: torch.Tensor | None = None):
+        """[S,N,W] coronal images -> ([S,4] int32 (y6, y7, mid+custom, ok), boxes [S,300,4], k [S])."""
+        x, (gain, pad_x, pad_y, w0, h0) = self._rib_input(front)
+        head, _ = self.ribs_model(x)
+        dets, _, k = ops.nms(head.contiguous(), 1, CONF, IOU, MAX_DET, want_idx=False)
+        boxes = ops.scale_boxes(dets, k, gain, pad_x, pad_y, w0, h0)
+        # image_width is hard-coded to 512 in the reference (utils.py:166)
+        return ops.rib_select(boxes, k, 512.0, custom), boxes, k
+
+    # ------------------------------------------------------------------ a6-a19: per-slice path
+    @torch.no_grad()
+    def segment(self, px: torch.Tensor, slope: int = 1, intercept: int = -1024, use_body: bool = True,
+                rot180: bool = True):
+        """[B,S,S] int16 stored pixels -> (labels [B,S,S] u8 codes, body [B,S,S] u8, n_det [B])."""
+        B, H, W = px.shape
+        body = ops.body_mask(px, slope, intercept, True) if use_body else None
+        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype, rot180=rot180)
+        return self._segment_nchw(x, body)
+
+    @torch.no_grad()
+    def segment_u8(self, gray: torch.Tensor):
+        """jpg_png route (ai_tools.py:365-400): [B,S,S] u8, no windowing, no body mask."""
+        return self._segment_nchw(ops.u8_to_nchw(gray, self.dtype), None)
+
+    def _segment_nchw(self, x: torch.Tensor, body):
+        S = x.shape[-1]
+        # get_axial_slice_size / model choice, ai_tools.py:138-146: 256 -> the 256 model, else the 512 one
+        model = self.axial_model_256 if S == 256 else self.axial_model_512
+        head, protos = model(x.contiguous(memory_format=torch.channels_last))
+        dets, _, n = ops.nms(head.contiguous(), 4, CONF, IOU, MAX_DET, want_idx=False)
+        code, _, _ = ops.mask_decode(dets, n, protos.contiguous(), self.mask_variant)
+        ops.label_cleanup(code, body)
+        return code, body, n
+
+    # ------------------------------------------------------------------ whole series from host memory
+    @torch.no_grad()
+    def run_series(self, px_host: torch.Tensor, meta: SeriesMeta, labels_host: torch.Tensor | None = None,
+                   chunk: int = 64, custom: int = 0, all_slices: bool = True) -> SeriesResult:
+        """px_host [N,H,W] int16 (pinned) in file order.  ``all_slices`` pushes every slice through the
+        per-slice path (throughput mode); otherwise only the three selected slices (service mode).
+        ``labels_host`` (pinned, [N,H,W] u8, file order) receives the label maps."""
+        dev = self.device
+        N, H, W = px_host.shape
+        res = SeriesResult()
+        copy_in, copy_out = self._streams()
+        main = torch.cuda.current_stream(dev)
+        px = torch.empty((N, H, W), dtype=torch.int16, device=dev)
+        labels = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+        ready = []
+        with torch.cuda.stream(copy_in):
+            for c0 in range(0, N, chunk):
+                px[c0:c0 + chunk].copy_(px_host[c0:c0 + chunk], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_in)
+                ready.append(ev)
+        ndet = torch.empty((N,), dtype=torch.int32, device=dev)
+        done = []
+        for ci, c0 in enumerate(range(0, N, chunk)):
+            main.wait_event(ready[ci])
+            if all_slices:
+                code, _, n = self.segment(px[c0:c0 + chunk], meta.rescale_slope, meta.rescale_intercept)
+                labels[c0:c0 + chunk] = code
+                ndet[c0:c0 + chunk] = n
+                if labels_host is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    copy_out.wait_event(ev)
+                    with torch.cuda.stream(copy_out):
+                        labels_host[c0:c0 + chunk].copy_(labels[c0:c0 + chunk], non_blocking=True)
+        # coronal scan needs every slice resident
+        front = self.coronal(px, meta)
+        cus = torch.tensor([custom], dtype=torch.int32, device=dev)
+        sel, boxes, k = self.rib_select(front[None], cus)
+        res.front_u8, res.rib_boxes, res.n_det = front, boxes[0], ndet
+        sel_host = sel.cpu()[0].tolist()                # the one host sync of the series
+        res.selected = sel_host[:3] if sel_host[3] else []
+        if not all_slices and res.selected:
+            order = host.instance_order(meta.instance_numbers)
+            idx = [int(order[min(max(i, 0), N - 1)]) for i in res.selected]
+            code, body, n = self.segment(px[idx].contiguous(), meta.rescale_slope, meta.rescale_intercept)
+            labels, res.body = code, body
+            if labels_host is not None:
+                labels_host[:len(idx)].copy_(code)
+        main.wait_stream(copy_out)
+        res.labels = labels
+        return res
+
+    def _streams(self):
+        if not hasattr(self, "_copy_in"):
+            self._copy_in = torch.cuda.Stream(self.device)
+            self._copy_out = torch.cuda.Stream(self.device)
+        return self._copy_in, self._copy_out
+
+    # ------------------------------------------------------------------ a22-a24: mesh labelling
+    def label_mesh(self, nodes_xy: np.ndarray, triangles: np.ndarray, polygon_strings, outer_class: int = 4):
+        """Per-element classes for a triangle mesh (the CLASS vector of export_mesh_for_femm)."""
+        strs = list(polygon_strings)
+        contours = host.parse_contours(strs, host.find_outer_index(strs))
+        xy, off, cls = host.prepare_polygons(contours)
+        dev = self.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        return ops.tri_label(t(np.asarray(nodes_xy, np.float64)), t(np.asarray(triangles, np.int64)), t(xy), t(off),
+                             t(cls), outer_class)

@@ -63,16 +63,17 @@ def rib_marker_rows(n_slices: int = 320):
 
 
 def phantom_series(n_slices: int = 320, seed: int = 0, intercept: int = -1024,
-                   shuffle_seed: int | None = 1, size: int = SLICE):
+                   shuffle_seed: int | None = 1, size: int = SLICE, z_range: tuple | None = None):
     """Synthetic series.
 
     Returns ``(pixels[n,H,W] int16 in *file order*, instance_numbers[n] int32)``; file
     order is a seeded shuffle of z so the InstanceNumber sort (utils.py:96) is exercised.
     Slice z carries phantom ``P(seed*1000 + z)`` with a z-dependent lung scale and, near
-    each rib position, 400-HU blobs on row H/2 at x = W/2 +- (120 + 4 r).
+    each rib position, 400-HU blobs on row H/2 at x = W/2 +- (120 + 4 r).  ``z_range=(z0, z1)``
+    generates only that shard of the series (slice content does not depend on the shard).
     """
-    zs = np.arange(n_slices)
-    vol = np.empty((n_slices, size, size), np.int16)
+    zs = np.arange(n_slices) if z_range is None else np.arange(z_range[0], z_range[1])
+    vol = np.empty((len(zs), size, size), np.int16)
     ribs = rib_marker_rows(n_slices)
     yy, xx = np.mgrid[0:size, 0:size]
     for z in zs:
@@ -85,10 +86,10 @@ def phantom_series(n_slices: int = 320, seed: int = 0, intercept: int = -1024,
                 for sgn in (-1, 1):
                     cx = size // 2 + sgn * (120 + 4 * r) * size // 512
                     hu[(yy - size // 2) ** 2 + (xx - cx) ** 2 <= rad2] = 400
-        vol[z] = (hu - intercept).astype(np.int16)
+        vol[z - zs[0]] = (hu - intercept).astype(np.int16)
     inst = (zs + 1).astype(np.int32)
     if shuffle_seed is not None:
-        perm = np.random.default_rng(shuffle_seed).permutation(n_slices)
+        perm = np.random.default_rng(shuffle_seed).permutation(len(zs))
         vol, inst = vol[perm], inst[perm]
     return vol, inst
 

@@ -1,0 +1,262 @@
+"""YOLO11s-seg in plain PyTorch (random-init): the CNN between K1 and K5.
+
+The reference reaches the network only through ``ultralytics.YOLO(path, task='segment')``
+(kt_service/ai_tools/ai_tools.py:69-71, 121-122, 153); ultralytics is not installed here and the
+weights are unavailable offline, so the architecture is restated from the published
+``yolo11-seg.yaml`` at scale ``s`` and initialised randomly.  It runs
+through cuDNN (channels-last, half precision); it is PyTorch-owned and not one of the
+hand-written kernels.  Output: ``head [B, 4+nc+32, A]`` (xywh in input pixels, sigmoid class
+scores, mask coefficients) and ``protos [B, 32, S/4, S/4]`` -- the operands of K5 and K6.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Conv(nn.Module):
+    def __init__(self, c1, c2, k=1, s=1, g=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, k // 2, groups=g, bias=False)
+        self.bn = nn.BatchNorm2d(c2, eps=1e-3, momentum=0.03)
+        self.act = nn.SiLU(inplace=True) if act else nn.Identity()
+
+    def forward(self, x):
+        return self.act(self.bn(self.conv(x)))
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, c1, c2, shortcut=True, k=(3, 3), e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, k[0])
+        self.cv2 = Conv(c_, c2, k[1])
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        y = self.cv2(self.cv1(x))
+        return x + y if self.add else y
+
+
+class C3k(nn.Module):
+    def __init__(self, c1, c2, n=2, shortcut=True, e=0.5, k=3):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1)
+        self.cv2 = Conv(c1, c_, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, (k, k), 1.0) for _ in range(n)))
+
+    def forward(self, x):
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+
+
+class C3k2(nn.Module):
+    def __init__(self, c1, c2, n=1, c3k=False, e=0.5, shortcut=True):
+        super().__init__()
+        self.c = int(c2 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1)
+        self.cv2 = Conv((2 + n) * self.c, c2, 1)
+        self.m = nn.ModuleList(C3k(self.c, self.c, 2, shortcut) if c3k else Bottleneck(self.c, self.c, shortcut, (3, 3), 0.5)
+                               for _ in range(n))
+
+    def forward(self, x):
+        y = list(self.cv1(x).chunk(2, 1))
+        y.extend(m(y[-1]) for m in self.m)
+        return self.cv2(torch.cat(y, 1))
+
+
+class SPPF(nn.Module):
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1)
+        self.m = nn.MaxPool2d(k, 1, k // 2)
+
+    def forward(self, x):
+        y = [self.cv1(x)]
+        y.extend(self.m(y[-1]) for _ in range(3))
+        return self.cv2(torch.cat(y, 1))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, num_heads, attn_ratio=0.5):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.key_dim = int(self.head_dim * attn_ratio)
+        self.scale = self.key_dim ** -0.5
+        self.qkv = Conv(dim, dim + self.key_dim * num_heads * 2, 1, act=False)
+        self.proj = Conv(dim, dim, 1, act=False)
+        self.pe = Conv(dim, dim, 3, 1, g=dim, act=False)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        N = H * W
+        qkv = self.qkv(x).reshape(B, self.num_heads, self.key_dim * 2 + self.head_dim, N)
+        q, k, v = qkv.split([self.key_dim, self.key_dim, self.head_dim], dim=2)
+        attn = (q.transpose(-2, -1) @ k) * self.scale
+        attn = attn.softmax(dim=-1)
+        o = (v @ attn.transpose(-2, -1)).reshape(B, C, H, W) + self.pe(v.reshape(B, C, H, W))
+        return self.proj(o)
+
+
+class PSABlock(nn.Module):
+    def __init__(self, c, attn_ratio=0.5, num_heads=4):
+        super().__init__()
+        self.attn = Attention(c, num_heads, attn_ratio)
+        self.ffn = nn.Sequential(Conv(c, c * 2, 1), Conv(c * 2, c, 1, act=False))
+
+    def forward(self, x):
+        x = x + self.attn(x)
+        return x + self.ffn(x)
+
+
+class C2PSA(nn.Module):
+    def __init__(self, c1, c2, n=1, e=0.5):
+        super().__init__()
+        assert c1 == c2
+        self.c = int(c1 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1)
+        self.cv2 = Conv(2 * self.c, c1, 1)
+        self.m = nn.Sequential(*(PSABlock(self.c, 0.5, self.c // 64) for _ in range(n)))
+
+    def forward(self, x):
+        a, b = self.cv1(x).split((self.c, self.c), dim=1)
+        return self.cv2(torch.cat((a, self.m(b)), 1))
+
+
+class Proto(nn.Module):
+    def __init__(self, c1, c_=256, c2=32):
+        super().__init__()
+        self.cv1 = Conv(c1, c_, 3)
+        self.upsample = nn.ConvTranspose2d(c_, c_, 2, 2, 0, bias=True)
+        self.cv2 = Conv(c_, c_, 3)
+        self.cv3 = Conv(c_, c2, 1)
+
+    def forward(self, x):
+        return self.cv3(self.cv2(self.upsample(self.cv1(x))))
+
+
+class Segment(nn.Module):
+    """YOLO11 Segment head (Detect with DFL + mask coefficients + prototypes), inference form."""
+    reg_max = 16
+
+    def __init__(self, nc, ch, nm=32, npr=128):
+        super().__init__()
+        self.nc, self.nm, self.nl = nc, nm, len(ch)
+        self.stride = (8, 16, 32)
+        c2 = max(16, ch[0] // 4, self.reg_max * 4)
+        c3 = max(ch[0], min(nc, 100))
+        c4 = max(ch[0] // 4, nm)
+        self.cv2 = nn.ModuleList(nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), nn.Conv2d(c2, 4 * self.reg_max, 1)) for x in ch)
+        self.cv3 = nn.ModuleList(nn.Sequential(nn.Sequential(Conv(x, x, 3, g=x), Conv(x, c3, 1)),
+                                               nn.Sequential(Conv(c3, c3, 3, g=c3), Conv(c3, c3, 1)),
+                                               nn.Conv2d(c3, nc, 1)) for x in ch)
+        self.cv4 = nn.ModuleList(nn.Sequential(Conv(x, c4, 3), Conv(c4, c4, 3), nn.Conv2d(c4, nm, 1)) for x in ch)
+        self.proto = Proto(ch[0], npr, nm)
+        self.register_buffer("bins", torch.arange(self.reg_max, dtype=torch.float32).view(1, 1, self.reg_max, 1), persistent=False)
+        self._anchors = {}
+
+    def bias_init(self):
+        for a, b, s in zip(self.cv2, self.cv3, self.stride):
+            a[-1].bias.data[:] = 1.0
+            b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / s) ** 2)
+
+    def _grid(self, shapes, device, dtype):
+        key = (tuple(shapes), str(device), dtype)
+        if key not in self._anchors:
+            pts, strides = [], []
+            for (h, w), s in zip(shapes, self.stride):
+                sy, sx = torch.meshgrid(torch.arange(h, device=device, dtype=torch.float32) + 0.5,
+                                        torch.arange(w, device=device, dtype=torch.float32) + 0.5, indexing="ij")
+                pts.append(torch.stack((sx, sy), -1).view(-1, 2))
+                strides.append(torch.full((h * w, 1), float(s), device=device))
+            self._anchors[key] = (torch.cat(pts).t().contiguous().to(dtype), torch.cat(strides).t().contiguous().to(dtype))
+        return self._anchors[key]
+
+    def forward(self, feats):
+        protos = self.proto(feats[0])
+        B = protos.shape[0]
+        box, cls, mc, shapes = [], [], [], []
+        for i, x in enumerate(feats):
+            shapes.append(x.shape[2:])
+            box.append(self.cv2[i](x).flatten(2))
+            cls.append(self.cv3[i](x).flatten(2))
+            mc.append(self.cv4[i](x).flatten(2))
+        box, cls, mc = torch.cat(box, 2), torch.cat(cls, 2), torch.cat(mc, 2)
+        A = box.shape[2]
+        anchors, strides = self._grid(shapes, box.device, box.dtype)
+        dist = (box.view(B, 4, self.reg_max, A).softmax(2) * self.bins.to(box.dtype)).sum(2)       # DFL
+        lt, rb = dist.chunk(2, 1)
+        x1y1, x2y2 = anchors.unsqueeze(0) - lt, anchors.unsqueeze(0) + rb
+        xywh = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * strides
+        head = torch.cat((xywh, cls.sigmoid(), mc), 1)
+        return head, protos
+
+
+class YOLO11sSeg(nn.Module):
+    """yolo11-seg.yaml, scale s (depth 0.50, width 0.50, max_channels 1024)."""
+
+    def __init__(self, nc=4):
+        super().__init__()
+        self.nc = nc
+        self.l0 = Conv(3, 32, 3, 2)
+        self.l1 = Conv(32, 64, 3, 2)
+        self.l2 = C3k2(64, 128, 1, False, 0.25)
+        self.l3 = Conv(128, 128, 3, 2)
+        self.l4 = C3k2(128, 256, 1, False, 0.25)
+        self.l5 = Conv(256, 256, 3, 2)
+        self.l6 = C3k2(256, 256, 1, True)
+        self.l7 = Conv(256, 512, 3, 2)
+        self.l8 = C3k2(512, 512, 1, True)
+        self.l9 = SPPF(512, 512, 5)
+        self.l10 = C2PSA(512, 512, 1)
+        self.l13 = C3k2(512 + 256, 256, 1, False)
+        self.l16 = C3k2(256 + 256, 128, 1, False)
+        self.l17 = Conv(128, 128, 3, 2)
+        self.l19 = C3k2(128 + 256, 256, 1, False)
+        self.l20 = Conv(256, 256, 3, 2)
+        self.l22 = C3k2(256 + 512, 512, 1, True)
+        self.head = Segment(nc, (128, 256, 512), 32, 128)
+        self.head.bias_init()
+
+    def forward(self, x):
+        x = self.l2(self.l1(self.l0(x)))
+        p3 = self.l4(self.l3(x))
+        p4 = self.l6(self.l5(p3))
+        p5 = self.l10(self.l9(self.l8(self.l7(p4))))
+        u4 = self.l13(torch.cat((F.interpolate(p5, scale_factor=2.0, mode="nearest"), p4), 1))
+        n3 = self.l16(torch.cat((F.interpolate(u4, scale_factor=2.0, mode="nearest"), p3), 1))
+        n4 = self.l19(torch.cat((self.l17(n3), u4), 1))
+        n5 = self.l22(torch.cat((self.l20(n4), p5), 1))
+        return self.head((n3, n4, n5))
+
+    @torch.no_grad()
+    def shift_class_bias(self, sample: torch.Tensor, conf: float = 0.3, frac: float = 0.01) -> float:
+        """Random-init weights score ~0 everywhere, so nothing would reach NMS.  Shift the
+        class-branch biases by one constant so that ``frac`` of the anchors of ``sample`` exceed ``conf``.
+        Returns the shift (reported with every benchmark)."""
+        head, _ = self(sample)
+        s = head[:, 4:4 + self.nc].amax(1).float().flatten().clamp(1e-6, 1 - 1e-6)
+        logit = torch.log(s) - torch.log1p(-s)
+        q = torch.quantile(logit[torch.randperm(logit.numel(), device=logit.device)[:1_000_000]], 1.0 - frac)
+        shift = float(math.log(conf / (1 - conf)) - q)
+        for b in self.head.cv3:
+            b[-1].bias.data += shift
+        return shift
+
+
+def build_model(nc: int, device, dtype=torch.float16, seed: int = 0) -> YOLO11sSeg:
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    m = YOLO11sSeg(nc).eval()
+    torch.random.set_rng_state(g)
+    m = m.to(device=device, dtype=dtype).to(memory_format=torch.channels_last)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m

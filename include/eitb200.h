@@ -138,6 +138,14 @@ int eitb_nms(const void* head, int head_dtype, int B, int nc, int nm, int A, flo
              float iou, int max_det, float max_wh, float* dets, int32_t* keep_idx,
              int32_t* n_out, void* ws, size_t ws_bytes, eitb_stream_t stream);
 
+/* ultralytics scale_boxes, the step between the NMS output and
+ * sv.Detections.xyxy (ai_tools.py:123): x = clamp((x - pad) / gain, 0, orig) in float32.
+ *   dets [B,max_det,row_floats] as written by eitb_nms (xyxy first), n [B];
+ *   xyxy [B,max_det,4] float32 out (rows >= n[b] are zeroed) -- the input of eitb_rib_select. */
+int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, int row_floats, float gain,
+                     float pad_x, float pad_y, float orig_w, float orig_h, float* xyxy,
+                     eitb_stream_t stream);
+
 /* ---- K6: mask decode fused with the label-image overlay ---------------------------------------
  * Restates ultralytics process_mask(upsample=True) -- coef x proto
  * contraction, crop to box/4, bilinear x(H/mh) upsample, threshold -- fused with

@@ -390,6 +390,12 @@ def test_body_mask_adversarial_vs_oracle(ops):
     for k in range(len(cases)):
         want = O.body_mask(px[k], -1024, 1)
         assert np.array_equal(got[k], want), (k, int((got[k] != want).sum()))
+    for shape in ((3, 100, 72), (2, 40, 96), (1, 7, 32)):           # u8 fallback path and tiny bit-image cases
+        odd = rng.integers(900, 1300, shape).astype(np.int16)
+        odd[:, shape[1] // 4: 3 * shape[1] // 4, shape[2] // 5: 4 * shape[2] // 5] = 1100
+        got = ops.body_mask(dev(odd), 1, -1024, True).cpu().numpy()
+        for k in range(shape[0]):
+            assert np.array_equal(got[k], O.body_mask(odd[k], -1024, 1)), (shape, k)
     small = rng.integers(0, 2000, (5, 256, 256)).astype(np.int16)
     small[:, 60:200, 50:210] = 1050
     got = ops.body_mask(dev(small), 1, -1024, True).cpu().numpy()
