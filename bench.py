@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--slices", type=int, default=N_SLICES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -192,7 +193,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from eitsynthai_b200 import host, ops, sharded, synth
+    from eitsynthai_b200 import cabi, host, ops, sharded, synth
     from eitsynthai_b200.pipeline import CONF, IOU, MAX_DET, ImagingPipeline, SeriesMeta
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,6 +224,7 @@ def run_b200(args):
     timer = StageTimer(torch)
     copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     launches = {"n": 0}
+    profiling = {"on": False}
 
     def rib_stage(px):
         """coronal rows of the local shard -> exchange -> rib model on the owned series -> indices."""
@@ -273,19 +275,42 @@ def run_b200(args):
         launches["n"] += 11 + 1 + 1 + 1 + 18
         return code, n
 
-    flat_dev = px_dev.view(S * nl, SIZE, SIZE)
+    flat_dev = px_dev.view(S * nl, SIZE, SIZE)                     # the HBM-resident batch
     flat_host = px_host.view(S * nl, SIZE, SIZE)
     flat_labels_host = labels_host.view(S * nl, SIZE, SIZE)
-    ndet_total = torch.zeros((), dtype=torch.int64, device=dev)
+    stage_buf = flat_dev                                          # e2e copies the host pixels over it, chunk by chunk
+    chunks = list(range(0, S * nl, args.chunk))
+
+    def step_eager():
+        sel = rib_stage(px_dev)
+        for c0 in chunks:
+            slice_stage(flat_dev[c0:c0 + args.chunk])
+        return sel
+
+    # ---- CUDA graphs: one per chunk of the per-slice path (fixed addresses inside the resident batch)
+    for _ in range(2):                                            # cuDNN autotune + lazy module loading, eagerly
+        step_eager()
+    torch.cuda.synchronize(dev)
+    graphs, outs = [], []
+    if not args.no_graphs:
+        pool = torch.cuda.graph_pool_handle()
+        for c0 in chunks:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                o = slice_stage(flat_dev[c0:c0 + args.chunk])
+            graphs.append(g); outs.append(o)
+
+    def run_chunk(ci):
+        if graphs:
+            graphs[ci].replay()
+            return outs[ci]
+        return slice_stage(flat_dev[chunks[ci]:chunks[ci] + args.chunk])
 
     def step_device():
         sel = rib_stage(px_dev)
-        for c0 in range(0, S * nl, args.chunk):
-            code, n = slice_stage(flat_dev[c0:c0 + args.chunk])
-            ndet_total.add_(n.sum())
+        for ci in range(len(chunks)):
+            run_chunk(ci)
         return sel
-
-    stage_buf = torch.empty((S * nl, SIZE, SIZE), dtype=torch.int16, device=dev)
 
     def step_e2e():
         """Same pass from pinned host memory: H2D of the pixels, D2H of the label maps and indices."""
@@ -296,16 +321,14 @@ def run_b200(args):
             for c0 in range(0, S * nl, args.chunk):
                 stage_buf[c0:c0 + args.chunk].copy_(flat_host[c0:c0 + args.chunk], non_blocking=True)
                 e = torch.cuda.Event(); e.record(copy_in); evs.append(e)
-        keep = []
-        for ci, c0 in enumerate(range(0, S * nl, args.chunk)):
+        for ci, c0 in enumerate(chunks):
             main.wait_event(evs[ci])
-            code, n = slice_stage(stage_buf[c0:c0 + args.chunk])
+            code, n = run_chunk(ci)
             e = torch.cuda.Event(); e.record(main)
             copy_out.wait_event(e)
             with torch.cuda.stream(copy_out):
                 flat_labels_host[c0:c0 + args.chunk].copy_(code, non_blocking=True)
             code.record_stream(copy_out)
-            keep.append(code)
         sel = rib_stage(stage_buf.view(S, nl, SIZE, SIZE))
         main.wait_stream(copy_out)
         return sel.cpu()                                          # result read on the host
@@ -313,6 +336,7 @@ def run_b200(args):
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
+        cabi.profile_enable(profiling["on"])                       # drops what the warm-up recorded
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -340,8 +364,18 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, sel, n_launch, stages = timed(step_device, args.steps, max(args.warmup, 3))
+    ms_dev, sel, _, _ = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
+    # ---- eager pass with per-stage and per-kernel CUDA events (same work, no graphs)
+    profiling["on"] = True
+    torch.cuda.synchronize(dev)
+    ms_eager, _, _, stages = timed(step_eager, args.steps, 0)
+    kernels = cabi.profile_report()
+    profiling["on"] = False
+    cabi.profile_enable(False)
+    n_launch = sum(c for c, _ in kernels.values())                 # own kernels per timed region (graphs replay the same)
+    with torch.no_grad():
+        ndet_mean = float(torch.cat([o[1] for o in outs]).float().mean()) if outs else float("nan")
     total_slices = S * nslices                                     # all ranks together
     value = total_slices / (ms_dev / 1e3)
 
@@ -359,24 +393,29 @@ def run_b200(args):
     except OSError:
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
-    per_slice_bytes = {           # algorithmic bytes per 512x512 slice, DESIGN.md §4
-        "K1_hu_window_nchw": SIZE * SIZE * (2 + 1 + 6),           # int16 in, u8 mask in, 3 x fp16 out
-        "K2_body_mask": SIZE * SIZE * (2 + 1),                    # int16 in, u8 mask out
-        "K5_nms": 40 * 5376 * 2 + MAX_DET * 38 * 4,               # fp16 head in, dets out
-        "K6_mask_decode": 32 * 128 * 128 * 2 + MAX_DET * 38 * 4 + SIZE * SIZE,   # fp16 protos + dets in, u8 codes out
-        "K7_label_cleanup": SIZE * SIZE * (1 + 1 + 1),            # codes in/out, body in
+    px = SIZE * SIZE
+    # algorithmic bytes per 512x512 slice and launch; CC passes count source + label traffic
+    per_slice_bytes = {
+        "hu_window_kernel": px * (2 + 1 + 6), "thr_bits_kernel": px * 2 + px // 8, "morph5_bits_kernel": px // 4,
+        "cc_local_kernel": px * 5, "cc_merge_kernel": 15 * SIZE * 8, "cc_flatten_kernel": px * 8,
+        "area_kernel": px * 4, "best_kernel": px * 8, "write_mask_kernel": px * 5,
+        "nms_kernel": 40 * 5376 * 2 + MAX_DET * 38 * 4,
+        "mask_decode_kernel": 32 * 128 * 128 * 2 + MAX_DET * 38 * 4 + px,
+        "fill_body_kernel": px * 3, "small_first_kernel": px, "small_repaint_kernel": px // 8,
+        "contour_cand_kernel": px * 5, "contour_repaint_kernel": px // 8,
     }
-    own = {k: v for k, v in stages.items() if k in per_slice_bytes}
+    own = {k: v for k, v in kernels.items() if k in per_slice_bytes}
     roof = None
     if own:
-        top = max(own, key=own.get)
-        n_calls = args.steps * ((S * nl + args.chunk - 1) // args.chunk)
-        ms_call = own[top] / n_calls
+        top = max(own, key=lambda k: own[k][1])
+        cnt, tot_ms = own[top]
+        ms_call = tot_ms / cnt
         ach = per_slice_bytes[top] * min(args.chunk, S * nl) / (ms_call / 1e3) / 1e9
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": None, "ms_per_launch": ms_call, "slices_per_launch": min(args.chunk, S * nl),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"}
-
+                "traffic": None, "ms_per_launch": ms_call, "launches": cnt, "slices_per_launch": min(args.chunk, S * nl),
+                "algorithmic_bytes_per_slice": per_slice_bytes[top],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                "how": "CUDA events around every launch of the kernel (libeitb200 launch profiler) over an eager pass of the same steps"}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -387,9 +426,11 @@ def run_b200(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 (CNN) / int16,u8,f32 (kernels)", "data": "synthetic",
                 "config": dict(config(world), chunk=args.chunk, class_bias_shift=pipe.bias_shift,
-                               mean_detections_per_slice=float(ndet_total) / max(1, (max(args.warmup, 3) + args.steps) * S * nl)),
+                               mean_detections_per_slice=ndet_mean, cuda_graphs=bool(graphs)),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roof, "cpu_baseline": cpu,
+                "eager_ms_per_step": ms_eager,
                 "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stages.items())},
+                "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1][1])},
                 "selected_slices": sel.cpu().tolist()}
         print(json.dumps(line), flush=True)
     if world > 1:

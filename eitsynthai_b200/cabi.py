@@ -32,6 +32,8 @@ _p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 SIGNATURES = {
     "eitb_strerror": (C.c_char_p, [_i]),
     "eitb_version": (_i, []),
+    "eitb_profile_enable": (_i, [_i]),
+    "eitb_profile_report": (C.c_longlong, [C.c_char_p, _sz]),
     "eitb_hu_window_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "eitb_u8_to_nchw": (_i, [_p, _i, _i, _i, _p, _i, _p]),
     "eitb_body_mask_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -49,6 +51,7 @@ SIGNATURES = {
     "eitb_label_cleanup_workspace_bytes": (_sz, [_i, _i, _i]),
     "eitb_label_cleanup": (_i, [_p, _p, _i, _i, _i, _p, _sz, _p]),
     "eitb_codes_to_bgr": (_i, [_p, _p, _i64, _p]),
+    "eitb_bias_act_nhwc": (_i, [_p, _i, C.c_longlong, _i, _p, _i, _p]),
     "eitb_tri_label_workspace_bytes": (_sz, [_i]),
     "eitb_tri_label": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _p, _p, _sz, _p]),
     "eitb_tri_label_raster": (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _p, _p]),
@@ -89,3 +92,20 @@ def call(name: str, *args) -> None:
     rc = getattr(load(), name)(*args)
     if rc != OK:
         raise EitbError(name, rc, strerror(rc))
+
+
+def profile_enable(on: bool) -> None:
+    load().eitb_profile_enable(int(on))
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, total ms)} recorded since ``profile_enable(True)``."""
+    lib = load()
+    need = lib.eitb_profile_report(None, 0)
+    buf = C.create_string_buffer(int(need) + 16)
+    lib.eitb_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out

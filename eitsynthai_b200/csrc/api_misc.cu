@@ -12,6 +12,79 @@ extern "C" const char* eitb_strerror(int code) {
 }
 extern "C" int eitb_version(void) { return 100; }
 
+// ---------------------------------------------------------------------------------------------
+// Launch profiler: when enabled, every kernel launch of the library is bracketed by two CUDA
+// events on its own stream; eitb_profile_report() aggregates them per kernel name.  Meant for
+// bench.py's roofline line (timing "live, with CUDA events on the launching stream"); not
+// usable while a CUDA graph is being captured.
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+thread_local ProfRec t_pending = {nullptr, nullptr, nullptr};
+thread_local cudaStream_t t_stream = nullptr;
+}  // namespace
+
+void eitb_prof_begin(const char* kernel_name, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    ProfRec r{kernel_name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, stream);
+    t_pending = r;
+    t_stream = stream;
+}
+
+void eitb_prof_end() {
+    if (!t_pending.name) return;
+    cudaEventRecord(t_pending.b, t_stream);
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_recs.push_back(t_pending);
+    }
+    t_pending.name = nullptr;
+}
+
+extern "C" int eitb_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof_recs.clear();
+    g_prof_on = on != 0;
+    return EITB_OK;
+}
+
+extern "C" long long eitb_profile_report(char* buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : g_prof_recs) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        auto& e = agg[r.name];
+        e.first += 1;
+        e.second += ms;
+    }
+    std::string out;
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && cap > 0) {
+        const size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (long long)out.size() + 1;
+}
+
 __global__ void codes_to_bgr_kernel(const uint8_t* __restrict__ code, uint8_t* __restrict__ bgr, int64_t n) {
     // 4 codes -> 12 bytes per thread
     int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -43,6 +116,7 @@ extern "C" int eitb_codes_to_bgr(const uint8_t* code, uint8_t* bgr, int64_t n, e
     if (!code || !bgr || n < 0) return EITB_ERR_BAD_ARG;
     if (n == 0) return EITB_OK;
     if ((reinterpret_cast<uintptr_t>(code) & 3) || (reinterpret_cast<uintptr_t>(bgr) & 3)) return EITB_ERR_BAD_ARG;
+    eitb_prof_begin("codes_to_bgr_kernel", (cudaStream_t)stream);
     codes_to_bgr_kernel<<<eitb_grid((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(code, bgr, n);
     EITB_CHECK_LAUNCH();
     return EITB_OK;

@@ -72,10 +72,11 @@ __device__ __forceinline__ void gunion(int* L, int a, int b) {     // a: pixel i
 }
 
 // Strip-local labelling.  Pixels are visited in 32-pixel row segments, one per warp iteration:
-// the segment's occupancy word comes from a ballot (or straight from a bit image), every pixel is
-// pointed at the first pixel of its run inside the segment, and unions are issued only where runs
-// meet -- segment to segment along a row, and at the first pixel of every overlap with the row
-// above -- so a uniform region costs a handful of shared-memory atomics per row, not per pixel.
+// the segment's occupancy word comes from a ballot, one thread per row then chains the segments
+// so that every pixel points straight at the first pixel of its row run, and unions are issued
+// only at the first pixel of every overlap between a run and the row above -- a uniform region
+// costs one shared-memory atomic per row, not per pixel.  Run starts are compressed to their
+// roots before the labels are written.
 template <int PRED, int CONN>
 __global__ void __launch_bounds__(kThreads)
 cc_local_kernel(const void* __restrict__ src, size_t src_img_stride_bytes, int arg, int H, int W, int strip_h,
@@ -85,51 +86,99 @@ cc_local_kernel(const void* __restrict__ src, size_t src_img_stride_bytes, int a
     const int sidx = blockIdx.x - b * strips_per_img;
     const int y0 = sidx * strip_h;
     const int rows = min(strip_h, H - y0);
-    const int n = rows * W;
     const int spr = (W + 31) >> 5;                       // segments per row
     const int nseg = rows * spr;
     unsigned* segmask = reinterpret_cast<unsigned*>(sl + kStripPixels);
+    int* segstart = reinterpret_cast<int*>(segmask + nseg);          // start of the run entering the segment from the left
     const void* img = reinterpret_cast<const char*>(src) + (size_t)b * src_img_stride_bytes;
     const long long base = (long long)y0 * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads >> 5;
+    const int wy0 = warp / spr, wsx0 = warp - wy0 * spr;             // the only division: first (row, segment) of the warp
+    const int dy = nwarps / spr, dsx = nwarps - dy * spr;             // and its stride
 
-    for (int sg = warp; sg < nseg; sg += nwarps) {
-        const int y = sg / spr, x = ((sg - y * spr) << 5) + lane;
-        const int i = y * W + x;
-        const bool in = x < W && in_set<PRED>(img, base + i, arg);
+    // ---- occupancy word of every segment
+    for (int y = wy0, sx = wsx0; y < rows;) {
+        const int x = (sx << 5) + lane;
+        const bool in = x < W && in_set<PRED>(img, base + y * W + x, arg);
         const unsigned m = __ballot_sync(0xffffffffu, in);
-        if (lane == 0) segmask[sg] = m;
-        if (x < W) {
-            int l = CC_NONE;
-            if (in) l = i - (__clz(~(m << (31 - lane))) - 1);          // first pixel of the run within the segment
-            sl[i] = l;
+        if (lane == 0) segmask[y * spr + sx] = m;
+        y += dy; sx += dsx;
+        if (sx >= spr) { sx -= spr; ++y; }
+    }
+    __syncthreads();
+    // ---- chain the segments of every row: where does the run that crosses into segment s begin?
+    for (int y = threadIdx.x; y < rows; y += kThreads) {
+        int start = -1;                                   // first pixel of the run touching the right edge of the previous segment
+        for (int sx = 0; sx < spr; ++sx) {
+            const unsigned m = segmask[y * spr + sx];
+            const int entering = (m & 1u) ? start : -1;
+            segstart[y * spr + sx] = entering;
+            if (m == 0xffffffffu) { if (entering < 0) start = y * W + (sx << 5); }
+            else if (m >> 31) start = y * W + (sx << 5) + (32 - __clz(~m));
+            else start = -1;
         }
     }
     __syncthreads();
-    for (int sg = warp; sg < nseg; sg += nwarps) {
+    // ---- every pixel points at the first pixel of its row run
+    for (int y = wy0, sx = wsx0; y < rows;) {
+        const int sg = y * spr + sx, x = (sx << 5) + lane;
         const unsigned m = segmask[sg];
-        if (m == 0) continue;
-        const int y = sg / spr, sx = sg - y * spr, x = (sx << 5) + lane;
-        const int i = y * W + x;
-        const bool in = (m >> lane) & 1u;
-        if (lane == 0 && in && sx > 0 && (segmask[sg - 1] >> 31)) sunion(sl, i, i - 1);
-        if (y > 0) {
+        if (x < W) {
+            int l = CC_NONE;
+            if ((m >> lane) & 1u) {
+                const int ones = __clz(~(m << (31 - lane)));            // set pixels ending here, within the segment
+                l = y * W + x - (ones - 1);
+                if (ones == lane + 1 && segstart[sg] >= 0) l = segstart[sg];
+            }
+            sl[y * W + x] = l;
+        }
+        y += dy; sx += dsx;
+        if (sx >= spr) { sx -= spr; ++y; }
+    }
+    __syncthreads();
+    // ---- one union per overlap between a run and the row above
+    for (int y = wy0, sx = wsx0; y < rows;) {
+        const int sg = y * spr + sx;
+        const unsigned m = y > 0 ? segmask[sg] : 0u;
+        if (m) {
+            const int i = y * W + (sx << 5) + lane;
             const unsigned up = segmask[sg - spr];
             const unsigned both = m & up;
-            if ((both & ~(both << 1)) >> lane & 1u) sunion(sl, i, i - W);
-            if (CONN == 8 && in && !((up >> lane) & 1u)) {
+            const unsigned carry = sx > 0 ? (segmask[sg - 1] & segmask[sg - spr - 1]) >> 31 : 0u;
+            if (((both & ~((both << 1) | carry)) >> lane) & 1u) sunion(sl, i, i - W);
+            if (CONN == 8 && ((m >> lane) & 1u) && !((up >> lane) & 1u)) {
                 const unsigned upl = (up << 1) | (sx > 0 ? segmask[sg - spr - 1] >> 31 : 0u);
                 const unsigned upr = (up >> 1) | (sx + 1 < spr ? segmask[sg - spr + 1] << 31 : 0u);
                 if ((upl >> lane) & 1u) sunion(sl, i, i - W - 1);
                 if ((upr >> lane) & 1u) sunion(sl, i, i - W + 1);
             }
         }
+        y += dy; sx += dsx;
+        if (sx >= spr) { sx -= spr; ++y; }
+    }
+    __syncthreads();
+    // ---- compress the run starts; afterwards every pixel is two hops from its root
+    for (int y = wy0, sx = wsx0; y < rows;) {
+        const int sg = y * spr + sx;
+        const unsigned m = segmask[sg];
+        const bool start = ((m >> lane) & 1u) && (lane == 0 ? segstart[sg] < 0 : !((m >> (lane - 1)) & 1u));
+        if (start) {
+            const int i = y * W + (sx << 5) + lane;
+            sl[i] = sfind(sl, i);
+        }
+        y += dy; sx += dsx;
+        if (sx >= spr) { sx -= spr; ++y; }
     }
     __syncthreads();
     int32_t* out = labels + (long long)b * H * W + base;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const int l = sl[i];
-        out[i] = l == CC_NONE ? CC_NONE : (int)base + sfind(sl, i);
+    for (int y = wy0, sx = wsx0; y < rows;) {
+        const int x = (sx << 5) + lane;
+        if (x < W) {
+            const int i = y * W + x, l = sl[i];
+            out[i] = l == CC_NONE ? CC_NONE : (int)base + sl[l];
+        }
+        y += dy; sx += dsx;
+        if (sx >= spr) { sx -= spr; ++y; }
     }
 }
 
@@ -149,8 +198,10 @@ cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __r
             int* L = labels + (long long)b * H * W;
             const int i = y * W + x;
             if (L[i] == CC_NONE) continue;
-            if (L[i - W] != CC_NONE) gunion(L, i, i - W);
-            if (CONN == 8) {
+            if (L[i - W] != CC_NONE) {
+                // one union per run of vertically adjacent pairs
+                if (x == 0 || L[i - 1] == CC_NONE || L[i - W - 1] == CC_NONE) gunion(L, i, i - W);
+            } else if (CONN == 8) {
                 if (x > 0 && L[i - W - 1] != CC_NONE) gunion(L, i, i - W - 1);
                 if (x + 1 < W && L[i - W + 1] != CC_NONE) gunion(L, i, i - W + 1);
             }
@@ -171,14 +222,12 @@ cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __r
 }
 
 static __global__ void __launch_bounds__(256)
-cc_flatten_kernel(long long n_total, int hw, int32_t* __restrict__ labels) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (long long)gridDim.x * blockDim.x) {
-        const long long b = t / hw;
-        const int i = (int)(t - b * hw);
-        const int* L = labels + b * hw;
+cc_flatten_kernel(int hw, int32_t* __restrict__ labels) {       // grid (x: pixel blocks, y: image)
+    int* L = labels + (long long)blockIdx.y * hw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
         const int l = L[i];
         if (l == CC_NONE) continue;
-        labels[t] = gfind(L, i);
+        L[i] = gfind(L, l);                               // l is the strip root (or CC_OUT) already
     }
 }
 
@@ -190,24 +239,29 @@ inline int strip_rows(int H, int W) {
 }
 
 // labels [B,H,W] int32 out.  src: per-image stride in bytes (u8 images: H*W, int32 labels: 4*H*W).
+// flatten == 0 leaves every pixel pointing at its strip root; callers then resolve the few labels
+// they need with gfind().
 template <int PRED, int CONN>
 int cc_label(const void* src, size_t src_img_stride_bytes, int arg, int B, int H, int W, int link_outside,
-             int32_t* labels, cudaStream_t s) {
+             int32_t* labels, cudaStream_t s, int flatten = 1) {
     if (W > kStripPixels) return EITB_ERR_UNSUPPORTED;
     const int sh = strip_rows(H, W);
     const int spi = eitb_div_up(H, sh);
-    const size_t smem = kStripPixels * sizeof(int) + (size_t)sh * ((W + 31) / 32) * sizeof(unsigned);
+    const size_t smem = kStripPixels * sizeof(int) + (size_t)sh * ((W + 31) / 32) * 2 * sizeof(unsigned);
     if (cudaFuncSetAttribute(cc_local_kernel<PRED, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
+    eitb_prof_begin("cc_local_kernel", s);
     cc_local_kernel<PRED, CONN><<<B * spi, kThreads, smem, s>>>(src, src_img_stride_bytes, arg, H, W, sh, spi, labels);
     EITB_CHECK_LAUNCH();
     const long long items = (long long)B * ((H - 1) / sh) * W + (link_outside ? (long long)B * (2LL * W + 2LL * H) : 0);
     if (items > 0) {
+        eitb_prof_begin("cc_merge_kernel", s);
         cc_merge_kernel<CONN><<<eitb_grid(items, 256, 8), 256, 0, s>>>(B, H, W, sh, link_outside, labels);
         EITB_CHECK_LAUNCH();
     }
-    const long long n = (long long)B * H * W;
-    cc_flatten_kernel<<<eitb_grid(n, 256, 8), 256, 0, s>>>(n, H * W, labels);
+    if (!flatten) return EITB_OK;
+    eitb_prof_begin("cc_flatten_kernel", s);
+    cc_flatten_kernel<<<dim3(eitb_grid_per_image((long long)H * W, 256, B), B), 256, 0, s>>>(H * W, labels);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

@@ -8,8 +8,13 @@
 
 #define EITB_NUM_SMS 148
 
+// Per-launch CUDA-event timing (api_misc.cu); both calls are no-ops unless eitb_profile_enable(1).
+void eitb_prof_begin(const char* kernel_name, cudaStream_t stream);
+void eitb_prof_end();
+
 #define EITB_CHECK_LAUNCH()                                    \
     do {                                                       \
+        eitb_prof_end();                                       \
         if (cudaGetLastError() != cudaSuccess) return EITB_ERR_LAUNCH; \
     } while (0)
 
@@ -19,6 +24,15 @@ static inline int eitb_div_up(long long a, long long b) { return (int)((a + b - 
 static inline int eitb_grid(long long work_items, int threads, int ctas_per_sm) {
     long long need = (work_items + threads - 1) / threads;
     long long cap = (long long)EITB_NUM_SMS * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// x-extent of a (pixel blocks, image) grid: enough CTAs per image to fill the chip across B images
+static inline int eitb_grid_per_image(long long items_per_image, int threads, int B) {
+    long long need = (items_per_image + threads - 1) / threads;
+    long long cap = ((long long)EITB_NUM_SMS * 8 + B - 1) / (B > 0 ? B : 1);
+    if (cap < 1) cap = 1;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }

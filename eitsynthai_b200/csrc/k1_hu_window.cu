@@ -104,8 +104,10 @@ int launch_hu(const int16_t* px, int B, int H, int W, int lo, int hi, int rot180
     const int grid = eitb_grid(n_units, kThreads, 8);
     if (d <= kMaxLut) {
         size_t smem = (size_t)(d + 1) * (sizeof(T) + 1);
+        eitb_prof_begin("hu_window_kernel", s);
         hu_window_kernel<T, true><<<grid, kThreads, smem, s>>>(px, n_units, ups, lo, hi, rot180, mask, out_u8, (T*)out_nchw);
     } else {
+        eitb_prof_begin("hu_window_kernel", s);
         hu_window_kernel<T, false><<<grid, kThreads, 0, s>>>(px, n_units, ups, lo, hi, rot180, mask, out_u8, (T*)out_nchw);
     }
     EITB_CHECK_LAUNCH();
@@ -161,6 +163,7 @@ extern "C" int eitb_u8_to_nchw(const uint8_t* gray, int B, int H, int W, void* o
     const int ups = H * W / 8;
     const int grid = eitb_grid(n_units, kThreads, 8);
     cudaStream_t s = (cudaStream_t)stream;
+    eitb_prof_begin("u8_to_nchw_kernel", s);
     switch (out_dtype) {
         case EITB_F32: u8_to_nchw_kernel<float><<<grid, kThreads, 0, s>>>(gray, n_units, ups, (float*)out_nchw); break;
         case EITB_F16: u8_to_nchw_kernel<__half><<<grid, kThreads, 0, s>>>(gray, n_units, ups, (__half*)out_nchw); break;

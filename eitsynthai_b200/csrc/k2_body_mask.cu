@@ -131,18 +131,15 @@ morph5_bits_kernel(const uint32_t* __restrict__ in, long long n_words, int H, in
 // Blocks are anchored at (y, x) = top-left pixel, y in [-1, H-1], x in [-1, W-1].
 __global__ void __launch_bounds__(256)
 area_kernel(const int32_t* __restrict__ lab, int B, int H, int W, int32_t* __restrict__ area2) {
-    const int bw = W + 1, bh = H + 1;
-    const long long per = (long long)bw * bh;
-    const long long n = (long long)B * per;
-    const long long nround = (n + 31) / 32 * 32;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += (long long)gridDim.x * blockDim.x) {
+    // grid (x: block-row chunks, y: block row + 1, z: image); one thread per 2x2 block anchor
+    const int b = blockIdx.z, y = (int)blockIdx.y - 1;
+    const int bw = W + 1;
+    const int nround = (bw + 31) & ~31;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
         int root = -1, add = 0;
-        long long b = 0;
-        if (t < n) {
-            b = t / per;
-            const int r = (int)(t - b * per);
-            const int y = r / bw - 1, x = r - (r / bw) * bw - 1;
-            const int32_t* L = lab + b * H * W;
+        if (t < bw) {
+            const int x = t - 1;
+            const int32_t* L = lab + (long long)b * H * W;
             int cnt = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -156,33 +153,43 @@ area_kernel(const int32_t* __restrict__ lab, int B, int H, int W, int32_t* __res
             if (!add) root = -1;
         }
         // warp-aggregate by (image, root)
-        const long long key = root < 0 ? -1 : b * H * W + root;
-        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const unsigned grp = __match_any_sync(0xffffffffu, root);
         const int sum = __reduce_add_sync(grp, add);
-        if (root >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(area2 + key, sum);
+        if (root >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(area2 + (long long)b * H * W + root, sum);
     }
 }
 
 // best[b] = max over roots of (area2 << 32 | root)
 __global__ void __launch_bounds__(256)
-best_kernel(const int32_t* __restrict__ lab, const int32_t* __restrict__ area2, long long n, int hw,
-            long long* __restrict__ best) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const long long b = t / hw;
-        const int i = (int)(t - b * hw);
-        if (lab[t] == i) atomicMax(best + b, ((long long)area2[t] << 32) | (long long)i);
+best_kernel(const int32_t* __restrict__ lab, const int32_t* __restrict__ area2, int hw,
+            long long* __restrict__ best) {                  // grid (x: pixel blocks, y: image)
+    const long long off = (long long)blockIdx.y * hw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
+        if (lab[off + i] == i) atomicMax(best + blockIdx.y, ((long long)area2[off + i] << 32) | (long long)i);
+}
+
+__global__ void __launch_bounds__(256)
+write_mask_kernel(const int32_t* __restrict__ lab, const long long* __restrict__ best, int hw,
+                  uint8_t* __restrict__ mask) {              // grid (x: 4-pixel blocks, y: image); hw % 4 == 0
+    const long long off = (long long)blockIdx.y * hw;
+    const long long k = best[blockIdx.y];
+    const int root = k >= 0 ? (int)(k & 0xffffffffLL) : -3;     // -3 matches no label
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hw; i += gridDim.x * blockDim.x * 4) {
+        const int4 l = *reinterpret_cast<const int4*>(lab + off + i);
+        const uint32_t v = (l.x == root ? 0xffu : 0u) | (l.y == root ? 0xff00u : 0u) | (l.z == root ? 0xff0000u : 0u) |
+                           (l.w == root ? 0xff000000u : 0u);
+        *reinterpret_cast<uint32_t*>(mask + off + i) = v;
     }
 }
 
 __global__ void __launch_bounds__(256)
-write_mask_kernel(const int32_t* __restrict__ lab, const long long* __restrict__ best, long long n, int hw,
-                  uint8_t* __restrict__ mask) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const long long b = t / hw;
-        const long long k = best[b];
-        const int l = lab[t];
-        mask[t] = (k >= 0 && l >= 0 && l == (int)(k & 0xffffffffLL)) ? 255 : 0;
-    }
+write_mask_scalar_kernel(const int32_t* __restrict__ lab, const long long* __restrict__ best, int hw,
+                         uint8_t* __restrict__ mask) {
+    const long long off = (long long)blockIdx.y * hw;
+    const long long k = best[blockIdx.y];
+    const int root = k >= 0 ? (int)(k & 0xffffffffLL) : -3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x)
+        mask[off + i] = lab[off + i] == root ? 255 : 0;
 }
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -219,16 +226,21 @@ extern "C" int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope,
         uint32_t* b0 = reinterpret_cast<uint32_t*>(er);
         uint32_t* b1 = reinterpret_cast<uint32_t*>(opened);
         const long long n_words = (long long)n / 32;
+        eitb_prof_begin("thr_bits_kernel", s);
         thr_bits_kernel<<<eitb_grid((long long)n / 8, 256, 8), 256, 0, s>>>(px, (long long)n / 8, H, W, slope, intercept, flipud, b0);
         EITB_CHECK_LAUNCH();
+        eitb_prof_begin("morph5_bits_kernel", s);
         morph5_bits_kernel<true><<<eitb_grid(n_words, 256, 8), 256, 0, s>>>(b0, n_words, H, W / 32, b1);
         EITB_CHECK_LAUNCH();
+        eitb_prof_begin("morph5_bits_kernel", s);
         morph5_bits_kernel<false><<<eitb_grid(n_words, 256, 8), 256, 0, s>>>(b1, n_words, H, W / 32, b0);
         EITB_CHECK_LAUNCH();
         rc = cc_label<PRED_BIT_ZERO, 4>(b0, (size_t)H * W / 8, 0, B, H, W, 1, labA, s);         // background, frame-linked
     } else {
+        eitb_prof_begin("thr_erode_kernel", s);
         thr_erode_kernel<<<grid, 256, 0, s>>>(px, B, H, W, slope, intercept, flipud, er);
         EITB_CHECK_LAUNCH();
+        eitb_prof_begin("dilate_kernel", s);
         dilate_kernel<<<grid, 256, 0, s>>>(er, B, H, W, opened);
         EITB_CHECK_LAUNCH();
         rc = cc_label<PRED_U8_ZERO, 4>(opened, (size_t)H * W, 0, B, H, W, 1, labA, s);
@@ -238,11 +250,18 @@ extern "C" int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope,
     if (rc != EITB_OK) return rc;
     if (cudaMemsetAsync(area2, 0, n * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
     if (cudaMemsetAsync(best, 0xff, (size_t)B * 8, s) != cudaSuccess) return EITB_ERR_LAUNCH;  // -1
-    area_kernel<<<eitb_grid((long long)B * (H + 1) * (W + 1), 256, 8), 256, 0, s>>>(labB, B, H, W, area2);
+    eitb_prof_begin("area_kernel", s);
+    if (H + 1 > 65535 || B > 65535) return EITB_ERR_UNSUPPORTED;
+    area_kernel<<<dim3(eitb_div_up(W + 1, 256), H + 1, B), 256, 0, s>>>(labB, B, H, W, area2);
     EITB_CHECK_LAUNCH();
-    best_kernel<<<grid, 256, 0, s>>>(labB, area2, (long long)n, H * W, best);
+    eitb_prof_begin("best_kernel", s);
+    best_kernel<<<dim3(eitb_grid_per_image((long long)H * W, 256, B), B), 256, 0, s>>>(labB, area2, H * W, best);
     EITB_CHECK_LAUNCH();
-    write_mask_kernel<<<grid, 256, 0, s>>>(labB, best, (long long)n, H * W, mask);
+    eitb_prof_begin("write_mask_kernel", s);
+    if (((H * W) & 3) == 0 && !(reinterpret_cast<uintptr_t>(mask) & 3))
+        write_mask_kernel<<<dim3(eitb_grid_per_image((long long)H * W / 4, 256, B), B), 256, 0, s>>>(labB, best, H * W, mask);
+    else
+        write_mask_scalar_kernel<<<dim3(eitb_grid_per_image((long long)H * W, 256, B), B), 256, 0, s>>>(labB, best, H * W, mask);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

@@ -204,6 +204,7 @@ extern "C" int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int 
                                 eitb_stream_t stream) {
     if (!dets || !n || !xyxy || B < 0 || max_det <= 0 || row_floats < 4 || !(gain > 0.f)) return EITB_ERR_BAD_ARG;
     if (B == 0) return EITB_OK;
+    eitb_prof_begin("scale_boxes_kernel", (cudaStream_t)stream);
     scale_boxes_kernel<<<eitb_grid((long long)B * max_det, 256, 4), 256, 0, (cudaStream_t)stream>>>(
         dets, n, B, max_det, row_floats, gain, pad_x, pad_y, orig_w, orig_h, xyxy);
     EITB_CHECK_LAUNCH();
@@ -216,6 +217,7 @@ extern "C" int eitb_front_rows(const int16_t* px, const int32_t* order, int n, i
     if (W % 8) return EITB_ERR_UNSUPPORTED;
     if (n == 0) return EITB_OK;
     const long long units = (long long)n * (W / 8);
+    eitb_prof_begin("front_rows_kernel", (cudaStream_t)stream);
     front_rows_kernel<<<eitb_grid(units, 256, 4), 256, 0, (cudaStream_t)stream>>>(px, order, n, H, W, row, flip_x, flip_z, rows, minmax);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
@@ -225,6 +227,7 @@ extern "C" int eitb_minmax_u8(const int16_t* rows, int64_t count, const int32_t*
                               eitb_stream_t stream) {
     if (!rows || !minmax || !out || count < 0) return EITB_ERR_BAD_ARG;
     if (count == 0) return EITB_OK;
+    eitb_prof_begin("minmax_u8_kernel", (cudaStream_t)stream);
     minmax_u8_kernel<<<eitb_grid(count, 256, 4), 256, 0, (cudaStream_t)stream>>>(rows, count, minmax, out);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
@@ -239,6 +242,7 @@ extern "C" int eitb_letterbox_nchw(const uint8_t* gray, int B, int H, int W, int
     const long long total = (long long)B * outH * outW;
     const int grid = eitb_grid(total, 256, 8);
     cudaStream_t s = (cudaStream_t)stream;
+    eitb_prof_begin("letterbox_kernel", s);
     switch (out_dtype) {
         case EITB_F32: letterbox_kernel<float><<<grid, 256, 0, s>>>(gray, B, H, W, nh, nw, top, left, outH, outW, (float*)out); break;
         case EITB_F16: letterbox_kernel<__half><<<grid, 256, 0, s>>>(gray, B, H, W, nh, nw, top, left, outH, outW, (__half*)out); break;
@@ -254,6 +258,7 @@ extern "C" int eitb_rib_select(const float* xyxy, const int32_t* k, int S, int m
     if (!xyxy || !k || !out || S < 0 || max_k <= 0) return EITB_ERR_BAD_ARG;
     if (S == 0) return EITB_OK;
     const int warps = 4;
+    eitb_prof_begin("rib_select_kernel", (cudaStream_t)stream);
     rib_select_kernel<<<eitb_div_up(S, warps), warps * 32, 0, (cudaStream_t)stream>>>(xyxy, k, S, max_k, image_width, custom, out);
     EITB_CHECK_LAUNCH();
     return EITB_OK;

@@ -207,6 +207,7 @@ int launch_nms(const void* head, int B, int nc, int nm, int A, float conf, float
     if (smem > 220 * 1024) return EITB_ERR_UNSUPPORTED;
     if (cudaFuncSetAttribute(nms_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
+    eitb_prof_begin("nms_kernel", s);
     nms_kernel<T><<<B, kThreads, smem, s>>>((const T*)head, nc, nm, A, npad_cap, conf, iou, max_det, max_wh, dets, keep_idx, n_out);
     EITB_CHECK_LAUNCH();
     return EITB_OK;

@@ -188,6 +188,7 @@ int launch_decode(const float* dets, const int32_t* n_det, int max_det, const vo
         return EITB_ERR_LAUNCH;
     const long long grid = (long long)B * tiles_x * tiles_y;
     if (grid > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
+    eitb_prof_begin("mask_decode_kernel", s);
     mask_decode_kernel<T><<<(unsigned)grid, kThreads, smem, s>>>(dets, n_det, max_det, (const T*)protos, nm, mh, mw, H, W,
                                                                  tiles_x, tiles_x * tiles_y, variant, code, inst_area,
                                                                  inst_bits);

@@ -33,15 +33,30 @@ __device__ __forceinline__ uint8_t ldv(const uint8_t* p) { return __ldcg(p); }  
 
 // ------------------------------------------------------------------ stage A: black in body -> muscle
 __global__ void __launch_bounds__(256)
-fill_body_kernel(uint8_t* __restrict__ code, const uint8_t* __restrict__ body, long long n, int hw, int* __restrict__ anybody) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const uint8_t m = body[t];
-        if (m) {
-            const int b = (int)(t / hw);
-            if (anybody[b] == 0) anybody[b] = 1;                  // benign race: everyone writes 1
-            if (m == 255 && code[t] == EITB_CODE_BLACK) code[t] = EITB_CODE_MUSCLE;
+fill_body_kernel(uint8_t* __restrict__ code, const uint8_t* __restrict__ body, int hw, int* __restrict__ anybody) {
+    // grid (x: pixel blocks, y: image)
+    const long long off = (long long)blockIdx.y * hw;
+    bool any = false;
+    if ((hw & 3) == 0 && !((reinterpret_cast<uintptr_t>(code) | reinterpret_cast<uintptr_t>(body)) & 3)) {
+        for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hw; i += gridDim.x * blockDim.x * 4) {
+            const uint32_t m = *reinterpret_cast<const uint32_t*>(body + off + i);
+            if (!m) continue;
+            any = true;
+            uint32_t c = *reinterpret_cast<const uint32_t*>(code + off + i), o = c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (((m >> (8 * j)) & 0xffu) == 255u && ((c >> (8 * j)) & 0xffu) == EITB_CODE_BLACK) o |= (uint32_t)EITB_CODE_MUSCLE << (8 * j);
+            if (o != c) *reinterpret_cast<uint32_t*>(code + off + i) = o;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+            const uint8_t m = body[off + i];
+            if (!m) continue;
+            any = true;
+            if (m == 255 && code[off + i] == EITB_CODE_BLACK) code[off + i] = EITB_CODE_MUSCLE;
         }
     }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) anybody[blockIdx.y] = 1;   // benign race: everyone writes 1
 }
 
 // ------------------------------------------------------------------ stage B: components with < 5 px
@@ -72,14 +87,13 @@ __device__ __forceinline__ int small_component(const uint8_t* img, int H, int W,
 __global__ void __launch_bounds__(256)
 small_first_kernel(const uint8_t* __restrict__ code, const int* __restrict__ anybody, int B, int H, int W,
                    unsigned* __restrict__ bitmap, int words_per_img) {
-    const long long n = (long long)B * H * W;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(t / ((long long)H * W));
-        if (!anybody[b]) continue;
-        const int p = (int)(t - (long long)b * H * W);
-        const uint8_t* img = code + (long long)b * H * W;
+    // grid (x: row chunks, y: row, z: image)
+    const int b = blockIdx.z, y = blockIdx.y;
+    if (!anybody[b]) return;
+    const uint8_t* img = code + (long long)b * H * W;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+        const int p = y * W + x;
         if (!not_bg(img[p])) continue;
-        const int y = p / W, x = p - y * W;
         if ((x > 0 && not_bg(img[p - 1])) || (y > 0 && not_bg(img[p - W]))) continue;   // cannot be a first pixel
         int px[5];
         if (small_component(img, H, W, p, px) < 5 && px[0] == p)
@@ -168,28 +182,51 @@ __device__ int trace_simple(const uint8_t* img, int H, int W, int y0, int x0, in
     return n;
 }
 
+// Eight pixels per thread: the "first pixel of a component" test (no set neighbour earlier in
+// raster order) is evaluated on byte masks; the few survivors resolve the label of their left
+// neighbour on demand and trace their border.
 __global__ void __launch_bounds__(256)
 contour_cand_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ lab, int B, int H, int W, int t,
                     unsigned* __restrict__ bitmap, int words_per_img) {
-    const long long n = (long long)B * H * W;
+    const int upr = (W + 7) >> 3;
+    const long long n = (long long)B * H * upr;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(i / ((long long)H * W));
-        const int p = (int)(i - (long long)b * H * W);
+        const long long rowid = i / upr;
+        const int x0 = (int)(i - rowid * upr) << 3;
+        const int b = (int)(rowid / H), y = (int)(rowid - (long long)b * H);
         const uint8_t* img = src + (long long)b * H * W;
-        if (img[p] != (uint8_t)t) continue;
-        const int y = p / W, x = p - y * W;
+        const uint8_t* row = img + (long long)y * W;
+        unsigned cur = 0, up = 0;
+        if (x0 + 8 <= W && !((reinterpret_cast<uintptr_t>(row + x0)) & 7)) {
+            const uint2 v = *reinterpret_cast<const uint2*>(row + x0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur |= ((((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xffu) == (unsigned)t ? 1u : 0u) << j;
+        } else {
+            for (int j = 0; j < 8 && x0 + j < W; ++j) cur |= (row[x0 + j] == (uint8_t)t ? 1u : 0u) << j;
+        }
+        if (!cur) continue;
+        unsigned left = x0 > 0 && row[x0 - 1] == (uint8_t)t, upl = 0, upright = 0;
+        if (y > 0) {
+            const uint8_t* prow = row - W;
+            for (int j = 0; j < 8 && x0 + j < W; ++j) up |= (prow[x0 + j] == (uint8_t)t ? 1u : 0u) << j;
+            upl = x0 > 0 && prow[x0 - 1] == (uint8_t)t;
+            upright = x0 + 8 < W && prow[x0 + 8] == (uint8_t)t;
+        }
         // a component's first pixel has no set neighbour earlier in raster order ...
-        if (is_t(img, H, W, y, x - 1, t) || is_t(img, H, W, y - 1, x - 1, t) || is_t(img, H, W, y - 1, x, t) ||
-            is_t(img, H, W, y - 1, x + 1, t))
-            continue;
-        // ... and an external contour has the frame-connected background on its left
-        if (x > 0 && lab[(long long)b * H * W + p - 1] != CC_OUT) continue;
-        int vx[5], vy[5];
-        const int nv = trace_simple(img, H, W, y, x, t, vx, vy);
-        if (nv > 5) continue;
-        bool first = true;                                          // p must be the raster-first vertex
-        for (int k = 0; k < nv; ++k) first = first && (vy[k] > y || (vy[k] == y && vx[k] >= x));
-        if (first) atomicOr(bitmap + (long long)b * words_per_img + (p >> 5), 1u << (p & 31));
+        unsigned tips = cur & ~((cur << 1) | left) & ~up & ~((up << 1) | upl) & ~((up >> 1) | (upright << 7)) & 0xffu;
+        while (tips) {
+            const int j = __ffs(tips) - 1;
+            tips &= tips - 1;
+            const int x = x0 + j, p = y * W + x;
+            // ... and an external contour has the frame-connected background on its left
+            if (x > 0 && gfind(lab + (long long)b * H * W, p - 1) != CC_OUT) continue;
+            int vx[5], vy[5];
+            const int nv = trace_simple(img, H, W, y, x, t, vx, vy);
+            if (nv > 5) continue;
+            bool first = true;                                      // p must be the raster-first vertex
+            for (int k = 0; k < nv; ++k) first = first && (vy[k] > y || (vy[k] == y && vx[k] >= x));
+            if (first) atomicOr(bitmap + (long long)b * words_per_img + (p >> 5), 1u << (p & 31));
+        }
     }
 }
 
@@ -320,10 +357,14 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
     if (body) {
         if (cudaMemsetAsync(anybody, 0, (size_t)B * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
         if (cudaMemsetAsync(bitmap, 0, (size_t)B * words * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
-        fill_body_kernel<<<grid, 256, 0, s>>>(code, body, (long long)n, H * W, anybody);
+        eitb_prof_begin("fill_body_kernel", s);
+        fill_body_kernel<<<dim3(eitb_grid_per_image((long long)H * W / 4 + 1, 256, B), B), 256, 0, s>>>(code, body, H * W, anybody);
         EITB_CHECK_LAUNCH();
-        small_first_kernel<<<grid, 256, 0, s>>>(code, anybody, B, H, W, bitmap, words);
+        eitb_prof_begin("small_first_kernel", s);
+        if (H > 65535 || B > 65535) return EITB_ERR_UNSUPPORTED;
+        small_first_kernel<<<dim3(eitb_div_up(W, 256), H, B), 256, 0, s>>>(code, anybody, B, H, W, bitmap, words);
         EITB_CHECK_LAUNCH();
+        eitb_prof_begin("small_repaint_kernel", s);
         small_repaint_kernel<<<B, 32, 0, s>>>(code, anybody, H, W, bitmap, words);
         EITB_CHECK_LAUNCH();
     }
@@ -331,11 +372,13 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
     const int targets[3] = {EITB_CODE_BONE, EITB_CODE_MUSCLE, EITB_CODE_ADIPOSE};            // dict order, utils.py:782-787
     for (int k = 0; k < 3; ++k) {
         const int t = targets[k];
-        const int rc = cc_label<PRED_CODE_NE, 4>(snap, (size_t)H * W, t, B, H, W, 1, lab, s);
+        const int rc = cc_label<PRED_CODE_NE, 4>(snap, (size_t)H * W, t, B, H, W, 1, lab, s, /*flatten=*/0);
         if (rc != EITB_OK) return rc;
         if (cudaMemsetAsync(bitmap, 0, (size_t)B * words * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
+        eitb_prof_begin("contour_cand_kernel", s);
         contour_cand_kernel<<<grid, 256, 0, s>>>(snap, lab, B, H, W, t, bitmap, words);
         EITB_CHECK_LAUNCH();
+        eitb_prof_begin("contour_repaint_kernel", s);
         contour_repaint_kernel<<<B, 32, 0, s>>>(snap, code, H, W, t, bitmap, words);
         EITB_CHECK_LAUNCH();
     }

@@ -218,10 +218,12 @@ extern "C" int eitb_tri_label(const double* nodes_xy, int64_t n_nodes, const int
     double* bbox = reinterpret_cast<double*>(ws);
     double* orient = bbox + (size_t)P * 4;
     if (P > 0) {
+        eitb_prof_begin("poly_prep_kernel", s);
         poly_prep_kernel<<<eitb_div_up(P, 4), 128, 0, s>>>(poly_xy, poly_off, P, bbox, orient);
         EITB_CHECK_LAUNCH();
     }
     const int grid = eitb_grid(T * 32, 256, 8);
+    eitb_prof_begin("tri_label_kernel", s);
     tri_label_kernel<<<grid, 256, 0, s>>>(nodes_xy, tri, T, poly_xy, poly_off, poly_cls, P, outer_cls, bbox, orient, cls_out);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
@@ -234,6 +236,7 @@ extern "C" int eitb_tri_label_raster(const double* nodes_xy, int64_t n_nodes, co
     if (T == 0) return EITB_OK;
     if (!nodes_xy || !tri || !code || !cls_out) return EITB_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(nodes_xy) & 15) return EITB_ERR_BAD_ARG;
+    eitb_prof_begin("tri_label_raster_kernel", (cudaStream_t)stream);
     tri_label_raster_kernel<<<eitb_grid(T, 256, 8), 256, 0, (cudaStream_t)stream>>>(nodes_xy, tri, T, code, H, W, outer_cls, cls_out);
     EITB_CHECK_LAUNCH();
     return EITB_OK;

@@ -210,6 +210,19 @@ def codes_to_bgr(code: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------ K9
+def bias_act_(x: torch.Tensor, bias: torch.Tensor | None, silu: bool = True) -> torch.Tensor:
+    """In-place bias + SiLU on a channels-last [B,C,H,W] half tensor (conv epilogue of the CNN)."""
+    if not x.is_cuda or x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("x must be a channels-last CUDA tensor")
+    B, Cc, H, W = x.shape
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    with torch.cuda.device(x.device):
+        cabi.call("eitb_bias_act_nhwc", x.data_ptr(), _DT[x.dtype], B * H * W, Cc, _ptr(bias), int(silu), _stream(x))
+    return x
+
+
 # ------------------------------------------------------------------------------------ K8
 def tri_label(nodes_xy: torch.Tensor, tri: torch.Tensor, poly_xy: torch.Tensor, poly_off: torch.Tensor,
               poly_cls: torch.Tensor, outer_cls: int = 4) -> torch.Tensor:

@@ -18,14 +18,40 @@ import torch.nn.functional as F
 
 
 class Conv(nn.Module):
+    """Conv2d(bias=False) + BatchNorm2d + SiLU.  ``fuse()`` folds the BatchNorm into the convolution
+    (what ultralytics does before predicting); on a CUDA half tensor the folded bias and the SiLU
+    then run as one in-place libeitb200 pass (K9) right after cuDNN's convolution."""
+
     def __init__(self, c1, c2, k=1, s=1, g=1, act=True):
         super().__init__()
         self.conv = nn.Conv2d(c1, c2, k, s, k // 2, groups=g, bias=False)
         self.bn = nn.BatchNorm2d(c2, eps=1e-3, momentum=0.03)
         self.act = nn.SiLU(inplace=True) if act else nn.Identity()
+        self.has_act = act
+        self.fused_bias = None
+
+    @torch.no_grad()
+    def fuse(self):
+        bn = self.bn
+        scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        self.conv.weight.data = (self.conv.weight.float() * scale.view(-1, 1, 1, 1)).to(self.conv.weight.dtype)
+        self.fused_bias = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+        self.bn = nn.Identity()
 
     def forward(self, x):
-        return self.act(self.bn(self.conv(x)))
+        if self.fused_bias is None:
+            return self.act(self.bn(self.conv(x)))
+        y = self.conv(x)
+        if y.is_cuda and y.dtype != torch.float32 and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
+            from . import ops
+            return ops.bias_act_(y, self.fused_bias, self.has_act)
+        return self.act(y + self.fused_bias.to(y.dtype).view(1, -1, 1, 1))
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        if self.fused_bias is not None:
+            self.fused_bias = fn(self.fused_bias).float()
+        return self
 
 
 class Bottleneck(nn.Module):
@@ -251,11 +277,15 @@ class YOLO11sSeg(nn.Module):
         return shift
 
 
-def build_model(nc: int, device, dtype=torch.float16, seed: int = 0) -> YOLO11sSeg:
+def build_model(nc: int, device, dtype=torch.float16, seed: int = 0, fuse: bool = True) -> YOLO11sSeg:
     g = torch.random.get_rng_state()
     torch.manual_seed(seed)
     m = YOLO11sSeg(nc).eval()
     torch.random.set_rng_state(g)
+    if fuse:
+        for mod in m.modules():
+            if isinstance(mod, Conv):
+                mod.fuse()
     m = m.to(device=device, dtype=dtype).to(memory_format=torch.channels_last)
     for p in m.parameters():
         p.requires_grad_(False)

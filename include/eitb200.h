@@ -52,6 +52,14 @@ typedef void* eitb_stream_t;
 const char* eitb_strerror(int code);
 int eitb_version(void);
 
+/* Launch profiler (the reference only wall-clocks the segmentation call, ai_tools.py:152-155).
+ * enable(1) clears the records and starts bracketing every kernel launch of the library with CUDA
+ * events on its stream; enable(0) stops.  report() synchronises on the recorded events and writes
+ * one "kernel_name launches total_ms" line per kernel into buf (NUL-terminated, truncated to cap);
+ * returns the size needed.  Host pointers; do not enable while capturing a CUDA graph. */
+int eitb_profile_enable(int on);
+long long eitb_profile_report(char* buf, size_t cap);
+
 /* ---- K1: HU window + normalise + rot180 + body-mask AND + NCHW ------------------------
  * Replaces classic_norm (utils.py:272-313), cv2.bitwise_and(norm, norm, mask=body)
  * (ai_tools.py:212-213,287-288,339-340,433-434) and, for the square 256/512 inputs the
@@ -172,6 +180,14 @@ int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int H, int W, 
 
 /* code image -> the reference's BGR colour image, [n] -> [n,3]. */
 int eitb_codes_to_bgr(const uint8_t* code, uint8_t* bgr, int64_t n, eitb_stream_t stream);
+
+/* ---- K9: conv epilogue of the CNN ------------------------------------------------------------------
+ * In-place per-channel bias (BatchNorm folded into the convolution, as ultralytics' fuse() does for
+ * the models loaded at ai_tools.py:69-71) + SiLU on a channels-last activation tensor.
+ *   x [n_pixels, C] of dtype (EITB_F16 / EITB_BF16), C % 8 == 0; bias [C] float32 or NULL;
+ *   act 1: SiLU, 0: bias only. */
+int eitb_bias_act_nhwc(void* x, int dtype, long long n_pixels, int C, const float* bias, int act,
+                       eitb_stream_t stream);
 
 /* ---- K8: per-triangle tissue labelling ----------------------------------------------------------
  * Replaces divide_triangles_into_groups / process_triangle / the CLASS vector of
