@@ -262,10 +262,10 @@ def run_b200(args):
         with timer("K2_body_mask"):
             body = ops.body_mask(px_chunk, 1, -1024, True)
         with timer("K1_hu_window_nchw"):
-            _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=torch.float16)
+            _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=torch.float16, channels_last=True)
         with timer("CNN_axial"):
-            head, protos = pipe.axial_model_512(x.contiguous(memory_format=torch.channels_last))
-            head, protos = head.contiguous(), protos.contiguous()
+            head, protos = pipe.axial_model_512(x)
+            head = head.contiguous()
         with timer("K5_nms"):
             dets, _, n = ops.nms(head, 4, CONF, IOU, MAX_DET, want_idx=False)
         with timer("K6_mask_decode"):

@@ -34,7 +34,7 @@ SIGNATURES = {
     "eitb_version": (_i, []),
     "eitb_profile_enable": (_i, [_i]),
     "eitb_profile_report": (C.c_longlong, [C.c_char_p, _sz]),
-    "eitb_hu_window_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "eitb_hu_window_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p]),
     "eitb_u8_to_nchw": (_i, [_p, _i, _i, _i, _p, _i, _p]),
     "eitb_body_mask_workspace_bytes": (_sz, [_i, _i, _i]),
     "eitb_body_mask": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
@@ -47,7 +47,7 @@ SIGNATURES = {
     "eitb_nms_workspace_bytes": (_sz, [_i, _i]),
     "eitb_nms": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _sz, _p]),
     "eitb_mask_decode_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "eitb_mask_decode": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "eitb_mask_decode": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "eitb_label_cleanup_workspace_bytes": (_sz, [_i, _i, _i]),
     "eitb_label_cleanup": (_i, [_p, _p, _i, _i, _i, _p, _sz, _p]),
     "eitb_codes_to_bgr": (_i, [_p, _p, _i64, _p]),

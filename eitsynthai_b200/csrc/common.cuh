@@ -31,10 +31,25 @@ static inline int eitb_grid(long long work_items, int threads, int ctas_per_sm) 
 // x-extent of a (pixel blocks, image) grid: enough CTAs per image to fill the chip across B images
 static inline int eitb_grid_per_image(long long items_per_image, int threads, int B) {
     long long need = (items_per_image + threads - 1) / threads;
-    long long cap = ((long long)EITB_NUM_SMS * 8 + B - 1) / (B > 0 ? B : 1);
+    long long cap = ((long long)EITB_NUM_SMS * 8) / (B > 0 ? B : 1);    // floor: never spill into a second, mostly empty wave
     if (cap < 1) cap = 1;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+// CTAs that are resident at once for this kernel (SMs x occupancy): the grid of a grid-stride
+// streaming kernel, so that it runs as exactly one full wave.
+template <typename K>
+static inline int eitb_resident_ctas(K kernel, int threads, size_t smem) {
+    // one query per (kernel, smem bucket) and thread; the driver call costs tens of microseconds
+    static thread_local K last_kernel = nullptr;
+    static thread_local size_t last_smem = ~(size_t)0;
+    static thread_local int last = 0;
+    if (last_kernel == kernel && last_smem == smem && last > 0) return last;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    last_kernel = kernel; last_smem = smem; last = EITB_NUM_SMS * per_sm;
+    return last;
 }
 
 __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {

@@ -38,9 +38,11 @@ __device__ __forceinline__ void store8(T* dst, const T (&x)[8]) {
 
 template <typename T, bool USE_LUT>
 __global__ void __launch_bounds__(kThreads)
-hu_window_kernel(const int16_t* __restrict__ px, long long n_units, int units_per_slice, int lo,
-                 int hi, int rot180, const uint8_t* __restrict__ mask, uint8_t* __restrict__ out_u8,
-                 T* __restrict__ out_nchw) {
+hu_window_kernel(const int16_t* __restrict__ px_all, long long n_units, int units_per_slice, int lo,
+                 int hi, int rot180, const uint8_t* __restrict__ mask_all, uint8_t* __restrict__ out_u8_all,
+                 T* __restrict__ out_nchw_all) {
+    // grid (x: unit blocks, y: slice): no per-unit division
+    (void)n_units;
     extern __shared__ __align__(16) unsigned char smem[];
     const int d = hi - lo;
     T* lutT = reinterpret_cast<T*>(smem);
@@ -53,15 +55,17 @@ hu_window_kernel(const int16_t* __restrict__ px, long long n_units, int units_pe
         }
         __syncthreads();
     }
-    const long long hw = (long long)units_per_slice * 8;
-    const long long stride = (long long)gridDim.x * kThreads;
-    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < n_units; u += stride) {
-        const long long b = u / units_per_slice;
-        const int o = (int)(u - b * units_per_slice);
-        const long long in_off = rot180 ? (b * hw + hw - 8 - (long long)o * 8) : (b * hw + (long long)o * 8);
+    const int hw = units_per_slice * 8;
+    const long long b = blockIdx.y;
+    const int16_t* px = px_all + b * hw;
+    const uint8_t* mask = mask_all ? mask_all + b * hw : nullptr;
+    uint8_t* out_u8 = out_u8_all ? out_u8_all + b * hw : nullptr;
+    T* out_nchw = out_nchw_all ? out_nchw_all + b * 3 * hw : nullptr;
+    for (int o = blockIdx.x * kThreads + threadIdx.x; o < units_per_slice; o += gridDim.x * kThreads) {
+        const int in_off = rot180 ? hw - 8 - o * 8 : o * 8;
         const int4 raw = ld_stream_int4(reinterpret_cast<const int4*>(px + in_off));
         uint2 mk = make_uint2(0xffffffffu, 0xffffffffu);
-        if (mask) mk = ld_stream_uint2(reinterpret_cast<const uint2*>(mask + b * hw + (long long)o * 8));
+        if (mask) mk = ld_stream_uint2(reinterpret_cast<const uint2*>(mask + o * 8));
         const int w[4] = {raw.x, raw.y, raw.z, raw.w};
         T vals[8];
         uint32_t u8lo = 0, u8hi = 0;
@@ -84,15 +88,114 @@ hu_window_kernel(const int16_t* __restrict__ px, long long n_units, int units_pe
             vals[j] = t;
             if (j < 4) u8lo |= (uint32_t)u8 << (8 * j); else u8hi |= (uint32_t)u8 << (8 * (j - 4));
         }
-        const long long out_pix = b * hw + (long long)o * 8;
+        const int out_pix = o * 8;
         if (out_u8) st_stream_uint2(reinterpret_cast<uint2*>(out_u8 + out_pix), make_uint2(u8lo, u8hi));
         if (out_nchw) {
-            T* base = out_nchw + b * 3 * hw + (long long)o * 8;
+            T* base = out_nchw + o * 8;
             store8(base, vals);
             store8(base + hw, vals);
             store8(base + 2 * hw, vals);
         }
     }
+}
+
+// ---- 16-bit outputs (fp16 / bf16), window <= 2048: the production path ---------------------
+// Two pixels per 32-bit lane all the way: SIMD clamp, one LDS per pixel for the 16-bit pattern of
+// u8/255, byte-mask expanded with PRMT, 16-byte stores.  NHWC writes the three equal channels
+// interleaved (48 contiguous bytes per 8 pixels), which is what a channels-last cuDNN network reads.
+__device__ __forceinline__ uint16_t unit16_bits(int u, int bf16) {
+    const float f = __fdiv_rn((float)u, 255.0f);
+    return bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(f)) : __half_as_ushort(__float2half_rn(f));
+}
+
+template <bool NHWC, bool WANT_U8>
+__global__ void __launch_bounds__(kThreads)
+hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int lo, int hi, int rot180,
+                   const uint8_t* __restrict__ mask_all, uint8_t* __restrict__ out_u8_all,
+                   uint16_t* __restrict__ out_all, int bf16) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int d = hi - lo;
+    uint16_t* lutT = reinterpret_cast<uint16_t*>(smem);
+    uint8_t* lut8 = smem + (size_t)(d + 1) * 2;
+    for (int v = threadIdx.x; v <= d; v += kThreads) {
+        const int u = (v * 255) / d;
+        lutT[v] = unit16_bits(u, bf16);
+        if (WANT_U8) lut8[v] = (uint8_t)u;
+    }
+    __syncthreads();
+    const int hw = units_per_slice * 8;
+    const long long b = blockIdx.y;
+    const int16_t* px = px_all + b * hw;
+    const uint8_t* mask = mask_all ? mask_all + b * hw : nullptr;
+    const unsigned lo2 = ((unsigned)lo & 0xffffu) | ((unsigned)lo << 16), hi2 = ((unsigned)hi & 0xffffu) | ((unsigned)hi << 16);
+    for (int o = blockIdx.x * kThreads + threadIdx.x; o < units_per_slice; o += gridDim.x * kThreads) {
+        const int4 raw = ld_stream_int4(reinterpret_cast<const int4*>(px + (rot180 ? hw - 8 - o * 8 : o * 8)));
+        unsigned w[4];
+        if (rot180) {
+            w[0] = __byte_perm(raw.w, 0, 0x1032); w[1] = __byte_perm(raw.z, 0, 0x1032);
+            w[2] = __byte_perm(raw.y, 0, 0x1032); w[3] = __byte_perm(raw.x, 0, 0x1032);
+        } else {
+            w[0] = raw.x; w[1] = raw.y; w[2] = raw.z; w[3] = raw.w;
+        }
+        uint2 mb = make_uint2(0xffffffffu, 0xffffffffu);
+        if (mask) {
+            const uint2 mk = ld_stream_uint2(reinterpret_cast<const uint2*>(mask + o * 8));
+            mb.x = __vcmpne4(mk.x, 0u); mb.y = __vcmpne4(mk.y, 0u);
+        }
+        unsigned v[4], u8lo = 0, u8hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned idx = __vsub2(__vmins2(__vmaxs2(w[k], lo2), hi2), lo2);
+            const unsigned i0 = idx & 0xffffu, i1 = idx >> 16;
+            const unsigned pair = (unsigned)lutT[i0] | ((unsigned)lutT[i1] << 16);
+            const unsigned mw = k < 2 ? mb.x : mb.y;
+            v[k] = pair & __byte_perm(mw, 0, (k & 1) ? 0x3322 : 0x1100);
+            if (WANT_U8) {
+                const unsigned two = ((unsigned)lut8[i0] | ((unsigned)lut8[i1] << 8)) << (16 * (k & 1));
+                if (k < 2) u8lo |= two; else u8hi |= two;
+            }
+        }
+        if (WANT_U8)
+            st_stream_uint2(reinterpret_cast<uint2*>(out_u8_all + b * hw + o * 8), make_uint2(u8lo & mb.x, u8hi & mb.y));
+        if (out_all) {
+            if (NHWC) {
+                unsigned t[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    t[3 * k] = __byte_perm(v[k], 0, 0x1010); t[3 * k + 1] = v[k]; t[3 * k + 2] = __byte_perm(v[k], 0, 0x3232);
+                }
+                int4* dst = reinterpret_cast<int4*>(out_all + (b * hw + (long long)o * 8) * 3);
+                st_stream_int4(dst, make_int4(t[0], t[1], t[2], t[3]));
+                st_stream_int4(dst + 1, make_int4(t[4], t[5], t[6], t[7]));
+                st_stream_int4(dst + 2, make_int4(t[8], t[9], t[10], t[11]));
+            } else {
+                uint16_t* base = out_all + b * 3 * hw + o * 8;
+                const int4 q = make_int4(v[0], v[1], v[2], v[3]);
+                st_stream_int4(reinterpret_cast<int4*>(base), q);
+                st_stream_int4(reinterpret_cast<int4*>(base + hw), q);
+                st_stream_int4(reinterpret_cast<int4*>(base + 2 * hw), q);
+            }
+        }
+    }
+}
+
+int launch_hu16(const int16_t* px, int B, int H, int W, int lo, int hi, int rot180, const uint8_t* mask, uint8_t* out_u8,
+                void* out, int bf16, int nhwc, cudaStream_t s) {
+    const int ups = H * W / 8;
+    const int d = hi - lo;
+    if (B > 65535) return EITB_ERR_UNSUPPORTED;
+    const dim3 grid(eitb_grid_per_image(ups, kThreads, B), B);
+    const size_t smem = (size_t)(d + 1) * 3 + 16;
+    eitb_prof_begin("hu_window_kernel", s);
+    if (nhwc) {
+        if (out_u8) hu_window16_kernel<true, true><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
+        else hu_window16_kernel<true, false><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
+    } else {
+        if (out_u8) hu_window16_kernel<false, true><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
+        else hu_window16_kernel<false, false><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
+    }
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
 }
 
 template <typename T>
@@ -101,7 +204,8 @@ int launch_hu(const int16_t* px, int B, int H, int W, int lo, int hi, int rot180
     const long long n_units = (long long)B * H * W / 8;
     const int ups = H * W / 8;
     const int d = hi - lo;
-    const int grid = eitb_grid(n_units, kThreads, 8);
+    if (B > 65535) return EITB_ERR_UNSUPPORTED;
+    const dim3 grid(eitb_grid_per_image(ups, kThreads, B), B);
     if (d <= kMaxLut) {
         size_t smem = (size_t)(d + 1) * (sizeof(T) + 1);
         eitb_prof_begin("hu_window_kernel", s);
@@ -140,12 +244,16 @@ u8_to_nchw_kernel(const uint8_t* __restrict__ gray, long long n_units, int units
 
 extern "C" int eitb_hu_window_nchw(const int16_t* px, int B, int H, int W, int lo, int hi, int rot180,
                                    const uint8_t* body_mask, uint8_t* out_u8, void* out_nchw,
-                                   int out_dtype, eitb_stream_t stream) {
+                                   int out_dtype, int channels_last, eitb_stream_t stream) {
     if (!px || B < 0 || H <= 0 || W <= 0 || hi <= lo || lo < -32768 || hi > 32767) return EITB_ERR_BAD_ARG;
     if (!out_u8 && !out_nchw) return EITB_ERR_BAD_ARG;
     if ((W % 8) != 0) return EITB_ERR_UNSUPPORTED;
     if (B == 0) return EITB_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if ((out_dtype == EITB_F16 || out_dtype == EITB_BF16 || !out_nchw) && hi - lo <= kMaxLut &&
+        !(reinterpret_cast<uintptr_t>(px) & 15) && !(reinterpret_cast<uintptr_t>(out_nchw) & 15))
+        return launch_hu16(px, B, H, W, lo, hi, rot180, body_mask, out_u8, out_nchw, out_dtype == EITB_BF16, channels_last, s);
+    if (channels_last) return EITB_ERR_UNSUPPORTED;
     switch (out_dtype) {
         case EITB_F32: return launch_hu<float>(px, B, H, W, lo, hi, rot180, body_mask, out_u8, out_nchw, s);
         case EITB_F16: return launch_hu<__half>(px, B, H, W, lo, hi, rot180, body_mask, out_u8, out_nchw, s);

@@ -38,7 +38,7 @@ __device__ __forceinline__ int class_code(float cls) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n_det, int max_det,
-                   const T* __restrict__ protos, int nm, int mh, int mw, int H, int W, int tiles_x,
+                   const T* __restrict__ protos, int proto_nhwc, int nm, int mh, int mw, int H, int W, int tiles_x,
                    int tiles_per_img, int variant, uint8_t* __restrict__ code, int32_t* __restrict__ inst_area,
                    uint8_t* __restrict__ inst_bits) {
     extern __shared__ __align__(16) float smem[];
@@ -63,12 +63,22 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
     // ---- stage the prototype tile (halo replicated at the frame)
     {
         const T* pimg = protos + (long long)b * nm * mh * mw;
-        for (int idx = tid; idx < nm * HP; idx += kThreads) {
-            const int k = idx / HP, h = idx - k * HP;
-            const int hy = h / HT, hx = h - hy * HT;
-            const int py = min(max(ty * PT - 1 + hy, 0), mh - 1);
-            const int px = min(max(tx * PT - 1 + hx, 0), mw - 1);
-            P[idx] = ld_f32(pimg + ((long long)k * mh + py) * mw + px);
+        if (proto_nhwc) {                                  // [mh][mw][nm]: the nm values of a pixel are contiguous
+            for (int idx = tid; idx < nm * HP; idx += kThreads) {
+                const int h = idx / nm, k = idx - h * nm;
+                const int hy = h / HT, hx = h - hy * HT;
+                const int py = min(max(ty * PT - 1 + hy, 0), mh - 1);
+                const int px = min(max(tx * PT - 1 + hx, 0), mw - 1);
+                P[k * HP + h] = ld_f32(pimg + ((long long)py * mw + px) * nm + k);
+            }
+        } else {
+            for (int idx = tid; idx < nm * HP; idx += kThreads) {
+                const int k = idx / HP, h = idx - k * HP;
+                const int hy = h / HT, hx = h - hy * HT;
+                const int py = min(max(ty * PT - 1 + hy, 0), mh - 1);
+                const int px = min(max(tx * PT - 1 + hx, 0), mw - 1);
+                P[idx] = ld_f32(pimg + ((long long)k * mh + py) * mw + px);
+            }
         }
     }
     __syncthreads();
@@ -178,7 +188,7 @@ size_t decode_smem(int nm, int max_det) {
 }
 
 template <typename T>
-int launch_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos, int B, int nm, int mh,
+int launch_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos, int nhwc, int B, int nm, int mh,
                   int mw, int H, int W, int variant, uint8_t* code, int32_t* inst_area, uint8_t* inst_bits,
                   cudaStream_t s) {
     const int tiles_x = eitb_div_up(mw, PT), tiles_y = eitb_div_up(mh, PT);
@@ -189,7 +199,7 @@ int launch_decode(const float* dets, const int32_t* n_det, int max_det, const vo
     const long long grid = (long long)B * tiles_x * tiles_y;
     if (grid > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
     eitb_prof_begin("mask_decode_kernel", s);
-    mask_decode_kernel<T><<<(unsigned)grid, kThreads, smem, s>>>(dets, n_det, max_det, (const T*)protos, nm, mh, mw, H, W,
+    mask_decode_kernel<T><<<(unsigned)grid, kThreads, smem, s>>>(dets, n_det, max_det, (const T*)protos, nhwc, nm, mh, mw, H, W,
                                                                  tiles_x, tiles_x * tiles_y, variant, code, inst_area,
                                                                  inst_bits);
     EITB_CHECK_LAUNCH();
@@ -204,8 +214,8 @@ extern "C" size_t eitb_mask_decode_workspace_bytes(int B, int max_det, int nm, i
 }
 
 extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos,
-                                int proto_dtype, int B, int nm, int mh, int mw, int H, int W, int variant,
-                                uint8_t* code, int32_t* inst_area, uint8_t* inst_bits, void* ws, size_t ws_bytes,
+                                int proto_dtype, int proto_channels_last, int B, int nm, int mh, int mw, int H, int W,
+                                int variant, uint8_t* code, int32_t* inst_area, uint8_t* inst_bits, void* ws, size_t ws_bytes,
                                 eitb_stream_t stream) {
     (void)ws; (void)ws_bytes;
     if (!dets || !n_det || !protos || !code || B < 0 || nm <= 0 || mh <= 0 || mw <= 0 || max_det <= 0 ||
@@ -219,9 +229,9 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
     if (inst_bits && cudaMemsetAsync(inst_bits, 0, (size_t)B * max_det * H * (W / 8), s) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     switch (proto_dtype) {
-        case EITB_F32: return launch_decode<float>(dets, n_det, max_det, protos, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
-        case EITB_F16: return launch_decode<__half>(dets, n_det, max_det, protos, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
-        case EITB_BF16: return launch_decode<__nv_bfloat16>(dets, n_det, max_det, protos, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
+        case EITB_F32: return launch_decode<float>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
+        case EITB_F16: return launch_decode<__half>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
+        case EITB_BF16: return launch_decode<__nv_bfloat16>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
         default: return EITB_ERR_BAD_ARG;
     }
 }

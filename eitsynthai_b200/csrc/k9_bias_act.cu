@@ -37,25 +37,26 @@ template <> struct Vec8<__nv_bfloat16> {
     }
 };
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
-bias_act_kernel(T* __restrict__ x, const float* __restrict__ bias, long long n_vec, int C, int act) {
+bias_act_kernel(T* __restrict__ x, const float* __restrict__ bias, I n_vec, int C, int act) {
     extern __shared__ float sb[];
     for (int c = threadIdx.x; c < C; c += blockDim.x) sb[c] = bias ? bias[c] : 0.f;
     __syncthreads();
-    const int vpc = C >> 3;                                       // 8-element vectors per pixel
+    const unsigned vpc = (unsigned)C >> 3;                        // 8-element vectors per pixel
+    const bool pow2 = (vpc & (vpc - 1)) == 0;
     int4* xv = reinterpret_cast<int4*>(x);
     constexpr int U = 4;                                           // 64 bytes in flight per thread
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += stride * U) {
+    const I stride = (I)gridDim.x * blockDim.x;
+    for (I i0 = (I)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += stride * U) {
         int4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) if (i0 + u * stride < n_vec) v[u] = xv[i0 + u * stride];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
+            const I i = i0 + u * stride;
             if (i >= n_vec) break;
-            const int c0 = (int)(i % vpc) << 3;
+            const int c0 = (int)(pow2 ? ((unsigned)i & (vpc - 1)) : (unsigned)(i % vpc)) << 3;
             float f[8];
             Vec8<T>::unpack(v[u], f);
 #pragma unroll
@@ -76,15 +77,26 @@ extern "C" int eitb_bias_act_nhwc(void* x, int dtype, long long n_pixels, int C,
     if ((C & 7) || (reinterpret_cast<uintptr_t>(x) & 15) || C > 8192) return EITB_ERR_UNSUPPORTED;
     if (n_pixels == 0) return EITB_OK;
     const long long n_vec = n_pixels * (C >> 3);
-    const int grid = eitb_grid(n_vec, 256, 8);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = (size_t)C * sizeof(float);
+    const bool small = n_vec < (1LL << 30);                        // 32-bit indexing whenever it fits
+    const long long need = (n_vec + 256 * 4 - 1) / (256 * 4);      // 4 vectors per thread per trip
+#define EITB_BIAS_ACT(T, I)                                                                               \
+    do {                                                                                                  \
+        const long long cap = eitb_resident_ctas(bias_act_kernel<T, I>, 256, smem);                       \
+        bias_act_kernel<T, I><<<(int)(need < cap ? need : cap), 256, smem, s>>>((T*)x, bias, (I)n_vec, C, act); \
+    } while (0)
     eitb_prof_begin("bias_act_kernel", s);
     switch (dtype) {
-        case EITB_F16: bias_act_kernel<__half><<<grid, 256, smem, s>>>((__half*)x, bias, n_vec, C, act); break;
-        case EITB_BF16: bias_act_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((__nv_bfloat16*)x, bias, n_vec, C, act); break;
+        case EITB_F16:
+            if (small) EITB_BIAS_ACT(__half, unsigned); else EITB_BIAS_ACT(__half, long long);
+            break;
+        case EITB_BF16:
+            if (small) EITB_BIAS_ACT(__nv_bfloat16, unsigned); else EITB_BIAS_ACT(__nv_bfloat16, long long);
+            break;
         default: return EITB_ERR_UNSUPPORTED;
     }
+#undef EITB_BIAS_ACT
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

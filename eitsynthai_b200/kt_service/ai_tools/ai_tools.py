@@ -1,0 +1,235 @@
+"""Mirror of the reference's kt_service/ai_tools/ai_tools.py: ``DICOMabc`` and its five
+subclasses with the same constructor, method names and log-and-return-``[]`` behaviour
+(ai_tools.py:37-450), driving the device-resident ``ImagingPipeline``.
+
+Seams to what is outside the hot path:
+* series ingest -- a zip of DICOM files is decoded with pydicom when it is importable
+  (utils.py:26-70); a series can also be handed over as a list of duck-typed datasets
+  (``.pixel_array``, ``.InstanceNumber``, ``ds[(group, elem)].value``), which is what the tests
+  and the benchmark do (pydicom / nibabel are not installed in this image);
+* Gmsh meshing -- ``mesh=(nodes, triangles)`` or the Delaunay stand-in (mesh_tools.femm_generator);
+* the pyEIT simulation and the PNG collage (``get_synthetic_dataset``, ``create_answer``) are not
+  mirrored: the answer is a dict with the label image, the polygon list and ``mesh_data``.
+"""
+from __future__ import annotations
+
+import abc
+import logging
+import time
+import zipfile
+
+import numpy as np
+import torch
+
+from .. import config, kt_service_config
+from ...pipeline import ImagingPipeline, SeriesMeta
+from . import utils
+from .mesh_tools.femm_generator import create_mesh
+
+logging.basicConfig(level=logging.INFO)
+logger = logging.getLogger(__name__)
+
+_PIPELINES = {}
+
+
+def _shared_pipeline(device) -> ImagingPipeline:
+    """The reference builds 5 pipeline objects x 3 models at import (main_kt_service.py:24-28);
+    one set of networks per device is enough."""
+    key = str(device)
+    if key not in _PIPELINES:
+        _PIPELINES[key] = ImagingPipeline(device)
+    return _PIPELINES[key]
+
+
+def _tag(ds, t, default=None):
+    try:
+        return ds[t].value
+    except Exception:
+        return default
+
+
+class DICOMabc(abc.ABC):
+    def __init__(self, ribs_model_path=None, axial_model_256_path=None, axial_model_512_path=None):
+        self.ribs_model_path = ribs_model_path or kt_service_config.ribs_segm_model
+        self.axial_model_256_path = axial_model_256_path or kt_service_config.axial_slice_segm_model_256
+        self.axial_model_512_path = axial_model_512_path or kt_service_config.axial_slice_segm_model_512
+        self.device = torch.device(config.device())
+        utils.set_device(self.device)
+        self.pipeline = _shared_pipeline(self.device)
+        self.ribs_model = self.pipeline.ribs_model
+        self.axial_model_256 = self.pipeline.axial_model_256
+        self.axial_model_512 = self.pipeline.axial_model_512
+
+    # ------------------------------------------------------------------ ingest seam
+    def _read_series(self, zip_buffer):
+        """utils.py:26-70 create_dicom_dict: largest series of the archive + custom_input.txt."""
+        if isinstance(zip_buffer, (list, tuple)):
+            return list(zip_buffer), 0
+        if isinstance(zip_buffer, dict):
+            return list(zip_buffer["slices"]), int(zip_buffer.get("custom_number_slise", 0))
+        import pydicom                                             # not installed here: explicit seam
+        from pydicom.filebase import DicomBytesIO
+        series, custom = {}, 0
+        with zipfile.ZipFile(zip_buffer, "r") as zf:
+            for name in zf.namelist():
+                if name.endswith(".txt"):
+                    if name.endswith("custom_input.txt"):
+                        custom = int(zf.read(name).decode().strip() or 0)
+                    continue
+                ds = pydicom.dcmread(DicomBytesIO(zf.read(name)))
+                series.setdefault(ds.SeriesInstanceUID, []).append(ds)
+        return max(series.values(), key=len), custom
+
+    def _series_arrays(self, i_slices):
+        px = np.stack([np.asarray(s.pixel_array, np.int16) for s in i_slices])
+        s0 = i_slices[0]
+        meta = SeriesMeta(np.asarray([int(s.InstanceNumber) for s in i_slices]),
+                          _tag(s0, (0x0018, 0x5100), "HFS"), _tag(s0, (0x0020, 0x0037), (1, 0, 0, 0, 1, 0)),
+                          _tag(s0, (0x0020, 0x0020)), int(_tag(s0, (0x0028, 0x1053), 1)),
+                          int(_tag(s0, (0x0028, 0x1052), -1024)),
+                          tuple(float(v) for v in _tag(s0, (0x0028, 0x0030), (0.753906, 0.753906))))
+        return px, meta
+
+    def _search_front_slise(self, zip_buffer):
+        """ai_tools.py:73-105 -> (front_slice u8 (N,W), pixels (N,H,W) in file order, sorted slices, custom)."""
+        front, px, i_slices, custom = [], [], [], []
+        try:
+            i_slices, custom = self._read_series(zip_buffer)
+            px, meta = self._series_arrays(i_slices)
+            self._meta = meta
+            front = self.pipeline.coronal(torch.from_numpy(px).to(self.device), meta).cpu().numpy()
+            i_slices.sort(key=lambda s: int(s.InstanceNumber))     # convert_to_3d sorts in place, utils.py:96
+        except Exception as e:
+            logger.error(f"_search_front_slise failed: {e}")
+        return front, px, i_slices, custom
+
+    def _ribs_predict(self, front_slice):
+        """ai_tools.py:107-127 -> object with .xyxy / .confidence / .class_id (sv.Detections' fields)."""
+        class _Det:
+            xyxy = np.zeros((0, 4), np.float32); confidence = np.zeros(0, np.float32); class_id = np.zeros(0, int)
+        det = _Det()
+        try:
+            front = torch.from_numpy(np.ascontiguousarray(front_slice)).to(self.device)
+            sel, boxes, k = self.pipeline.rib_select(front[None])
+            n = int(k[0])
+            det.xyxy = boxes[0, :n].cpu().numpy()
+            det.class_id = np.zeros(n, int)
+            self._sel = sel[0].cpu().tolist()
+        except Exception as e:
+            logger.error(f"_ribs_predict failed: {e}")
+        return det
+
+    def _search_axial_slice(self, detections, i_slices, custom_number_slise=0):
+        """ai_tools.py:160-182"""
+        axial, numbers = [], []
+        try:
+            numbers = utils.search_number_axial_slice(detections, custom_number_slise)
+            for i in numbers:
+                axial.append(i_slices[i])
+        except Exception as e:
+            logger.error(f"_search_axial_slice failed: {e}")
+        return axial, numbers
+
+    def _axial_slice_predict(self, px_or_u8, ds=None):
+        """ai_tools.py:129-158 fused with everything up to the label image: returns
+        (labels code image (S,S) u8, body mask or None, n_detections, segmentation_time)."""
+        t1 = time.time()
+        if ds is not None:
+            px = torch.from_numpy(np.ascontiguousarray(ds.pixel_array, np.int16)[None]).to(self.device)
+            code, body, n = self.pipeline.segment(px, int(_tag(ds, (0x0028, 0x1053), 1)), int(_tag(ds, (0x0028, 0x1052), -1024)))
+            body = body[0].cpu().numpy()
+        else:
+            code, body, n = self.pipeline.segment_u8(torch.from_numpy(np.ascontiguousarray(px_or_u8, np.uint8)[None]).to(self.device))
+        out = code[0].cpu().numpy()
+        return out, body, int(n[0]), round(time.time() - t1, 3)
+
+    def _finish(self, code, body, pixel_spacing, n_det, seg_time, mesh=None, extra=None):
+        polygons = utils.codes_to_polygons(code, pixel_spacing, body)
+        img_mesh, mesh_data = create_mesh(polygons[:2], polygons[2:], mesh=mesh) if (mesh is not None or body is not None) else (None, [])
+        ans = {"label_codes": code, "polygons": polygons, "mesh_data": mesh_data, "text_data": {"detections": n_det},
+               "segmentation_time": seg_time, "status": "success", "message": "Processing completed successfully"}
+        if extra:
+            ans.update(extra)
+        return ans
+
+
+class DICOMSequencesToMask(DICOMabc):
+    def get_coordinate_slice_from_dicom(self, zip_buffer, mesh=None):
+        """ai_tools.py:188-231"""
+        answer = []
+        try:
+            front, _, i_slices, _ = self._search_front_slise(zip_buffer)
+            det = self._ribs_predict(front)
+            axial, numbers = self._search_axial_slice(det, i_slices)
+            ds = axial[-1]
+            code, body, n, t = self._axial_slice_predict(None, ds)
+            answer = self._finish(code, body, utils.get_pixel_spacing(ds), n, t, mesh, {"number_slice_eit_list": numbers})
+        except Exception as e:
+            logger.error(f"DICOMSequencesToMask.get_coordinate_slice_from_dicom failed: {e}")
+        return answer
+
+
+class DICOMSequencesToMaskCustom(DICOMSequencesToMask):
+    def get_coordinate_slice_from_dicom_custom(self, zip_buffer, answer=None, mesh=None):
+        """ai_tools.py:263-307"""
+        answer = []
+        try:
+            front, _, i_slices, custom = self._search_front_slise(zip_buffer)
+            det = self._ribs_predict(front)
+            axial, numbers = self._search_axial_slice(det, i_slices, custom)
+            ds = axial[-1]
+            code, body, n, t = self._axial_slice_predict(None, ds)
+            answer = self._finish(code, body, utils.get_pixel_spacing(ds), n, t, mesh, {"number_slice_eit_list": numbers})
+        except Exception as e:
+            logger.error(f"DICOMSequencesToMaskCustom.get_coordinate_slice_from_dicom_custom failed: {e}")
+        return answer
+
+
+class DICOMToMask(DICOMSequencesToMask):
+    def get_coordinate_slice_from_dicom_frame(self, zip_buffer, answer=None, mesh=None):
+        """ai_tools.py:315-356: the last dataset of the archive, no rib stage."""
+        answer = []
+        try:
+            i_slices, _ = self._read_series(zip_buffer)
+            ds = i_slices[-1]
+            code, body, n, t = self._axial_slice_predict(None, ds)
+            answer = self._finish(code, body, utils.get_pixel_spacing(ds), n, t, mesh)
+        except Exception as e:
+            logger.error(f"DICOMToMask.get_coordinate_slice_from_dicom_frame failed: {e}")
+        return answer
+
+
+class ImageToMask(DICOMSequencesToMask):
+    def get_coordinate_slice_from_image(self, axial_slice_norm_body, mesh=None):
+        """ai_tools.py:365-400: a normalised u8 image; no windowing, no body mask, fixed spacing."""
+        answer = []
+        try:
+            img = np.asarray(axial_slice_norm_body)
+            if img.ndim == 3:
+                img = img[..., 0]
+            code, body, n, t = self._axial_slice_predict(img)
+            answer = self._finish(code, None, [0.753906, 0.753906], n, t, mesh)
+        except Exception as e:
+            logger.error(f"ImageToMask.get_coordinate_slice_from_image failed: {e}")
+        return answer
+
+
+class NIIToMask(DICOMSequencesToMask):
+    def get_coordinate_slice_from_nii(self, zip_buffer, answer=None, mesh=None):
+        """ai_tools.py:408-450: the middle slice of the volume as an HU image.  ``zip_buffer`` may be a
+        dict(hu=(H,W) int16, pixel_spacing=[..]) -- the NIfTI decode (utils.py:1062-1119, nibabel) is a seam.
+        classic_norm rotates by 180 and the caller rotates back (ai_tools.py:430-431): net no rotation."""
+        answer = []
+        try:
+            hu = np.asarray(zip_buffer["hu"], np.int16)
+            spacing = list(zip_buffer.get("pixel_spacing", [0.662, 0.662]))
+            px = torch.from_numpy(hu[None].copy()).to(self.device)
+            t1 = time.time()
+            from ... import ops
+            body = ops.body_mask(px, 1, 0, False)
+            _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.pipeline.dtype, rot180=False)
+            code, body, n = self.pipeline._segment_nchw(x, body)
+            answer = self._finish(code[0].cpu().numpy(), body[0].cpu().numpy(), spacing, int(n[0]), round(time.time() - t1, 3), mesh)
+        except Exception as e:
+            logger.error(f"NIIToMask.get_coordinate_slice_from_nii failed: {e}")
+        return answer

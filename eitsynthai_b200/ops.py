@@ -32,18 +32,22 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------ K1
 def hu_window(px: torch.Tensor, lo: int = -160, hi: int = 240, rot180: bool = True,
               body_mask: torch.Tensor | None = None, want_u8: bool = True,
-              nchw_dtype: torch.dtype | None = torch.float16):
-    """[B,H,W] int16 -> (u8 [B,H,W] or None, NCHW [B,3,H,W] or None).  classic_norm + mask + /255."""
+              nchw_dtype: torch.dtype | None = torch.float16, channels_last: bool = False):
+    """[B,H,W] int16 -> (u8 [B,H,W] or None, NCHW [B,3,H,W] or None).  classic_norm + mask + /255.
+    ``channels_last`` returns the same logical tensor in torch.channels_last memory format."""
     _chk(px, torch.int16, "px")
     B, H, W = px.shape
     if body_mask is not None:
         _chk(body_mask, torch.uint8, "body_mask")
         assert body_mask.shape == px.shape
     u8 = torch.empty((B, H, W), dtype=torch.uint8, device=px.device) if want_u8 else None
-    nchw = torch.empty((B, 3, H, W), dtype=nchw_dtype, device=px.device) if nchw_dtype is not None else None
+    nchw = None
+    if nchw_dtype is not None:
+        nchw = torch.empty((B, 3, H, W), dtype=nchw_dtype, device=px.device,
+                           memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     with torch.cuda.device(px.device):
         cabi.call("eitb_hu_window_nchw", px.data_ptr(), B, H, W, lo, hi, int(rot180), _ptr(body_mask),
-                  _ptr(u8), _ptr(nchw), _DT.get(nchw_dtype, cabi.F32), _stream(px))
+                  _ptr(u8), _ptr(nchw), _DT.get(nchw_dtype, cabi.F32), int(channels_last), _stream(px))
     return u8, nchw
 
 
@@ -172,8 +176,15 @@ def mask_decode(dets: torch.Tensor, n_det: torch.Tensor, protos: torch.Tensor, v
     (+ per-instance areas [B,max_det] i32, + per-instance bit masks [B,max_det,H,W/8] u8)."""
     _chk(dets, torch.float32, "dets")
     _chk(n_det, torch.int32, "n_det")
-    _chk(protos, None, "protos")
+    if not protos.is_cuda:
+        raise ValueError("protos must be a CUDA tensor")
     B, nm, mh, mw = protos.shape
+    if protos.is_contiguous():
+        nhwc = 0
+    elif protos.is_contiguous(memory_format=torch.channels_last):
+        nhwc = 1
+    else:
+        raise ValueError("protos must be contiguous (NCHW) or channels-last")
     max_det = dets.shape[1]
     assert dets.shape[2] == 6 + nm and dets.shape[0] == B
     H, W = 4 * mh, 4 * mw
@@ -182,7 +193,7 @@ def mask_decode(dets: torch.Tensor, n_det: torch.Tensor, protos: torch.Tensor, v
     bits = torch.empty((B, max_det, H, W // 8), dtype=torch.uint8, device=dets.device) if want_bits else None
     with torch.cuda.device(dets.device):
         cabi.call("eitb_mask_decode", dets.data_ptr(), n_det.data_ptr(), max_det, protos.data_ptr(),
-                  _DT[protos.dtype], B, nm, mh, mw, H, W, variant, code.data_ptr(), _ptr(area), _ptr(bits),
+                  _DT[protos.dtype], nhwc, B, nm, mh, mw, H, W, variant, code.data_ptr(), _ptr(area), _ptr(bits),
                   0, 0, _stream(dets))
     return code, area, bits
 

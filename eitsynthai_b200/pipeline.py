@@ -114,7 +114,7 @@ class ImagingPipeline:
         """[B,S,S] int16 stored pixels -> (labels [B,S,S] u8 codes, body [B,S,S] u8, n_det [B])."""
         B, H, W = px.shape
         body = ops.body_mask(px, slope, intercept, True) if use_body else None
-        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype, rot180=rot180)
+        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype, rot180=rot180, channels_last=True)
         return self._segment_nchw(x, body)
 
     @torch.no_grad()
@@ -128,7 +128,7 @@ class ImagingPipeline:
         model = self.axial_model_256 if S == 256 else self.axial_model_512
         head, protos = model(x.contiguous(memory_format=torch.channels_last))
         dets, _, n = ops.nms(head.contiguous(), 4, CONF, IOU, MAX_DET, want_idx=False)
-        code, _, _ = ops.mask_decode(dets, n, protos.contiguous(), self.mask_variant)
+        code, _, _ = ops.mask_decode(dets, n, protos, self.mask_variant)
         ops.label_cleanup(code, body)
         return code, body, n
 

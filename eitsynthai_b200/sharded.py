@@ -46,8 +46,11 @@ def gather_rows(rows_local: torch.Tensor, minmax_local: torch.Tensor, n_slices: 
     if nl < nmax:                                      # ragged shards: pad to the largest
         send = torch.zeros((S, nmax, W), dtype=rows_local.dtype, device=rows_local.device)
         send[:, :nl] = rows_local
-    parts = [torch.empty_like(send) for _ in range(ws)]
-    dist.all_gather(parts, send.contiguous())
+    # neither NCCL nor gloo has a 16-bit integer type: ship the rows as bytes
+    send8 = send.contiguous().view(torch.uint8)
+    parts8 = [torch.empty_like(send8) for _ in range(ws)]
+    dist.all_gather(parts8, send8)
+    parts = [p.view(rows_local.dtype) for p in parts8]
     mms = [torch.empty_like(minmax_local) for _ in range(ws)]
     dist.all_gather(mms, minmax_local.contiguous())
     rows = torch.cat([parts[r][:, :shard_range(n_slices, ws, r)[1] - shard_range(n_slices, ws, r)[0]] for r in range(ws)], 1)

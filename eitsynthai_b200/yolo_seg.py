@@ -54,6 +54,20 @@ class Conv(nn.Module):
         return self
 
 
+def _split_conv(cv: "Conv", c: int):
+    """Split a fused Conv with 2c output channels into two Convs with c channels each."""
+    assert cv.fused_bias is not None, "fuse() first"
+    out = []
+    for sl in (slice(0, c), slice(c, 2 * c)):
+        k = cv.conv.kernel_size[0]
+        n = Conv(cv.conv.in_channels, c, k, cv.conv.stride[0], cv.conv.groups, cv.has_act)
+        n.conv.weight.data = cv.conv.weight.data[sl].clone()
+        n.bn = nn.Identity()
+        n.fused_bias = cv.fused_bias[sl].clone()
+        out.append(n)
+    return out
+
+
 class Bottleneck(nn.Module):
     def __init__(self, c1, c2, shortcut=True, k=(3, 3), e=0.5):
         super().__init__()
@@ -89,8 +103,14 @@ class C3k2(nn.Module):
         self.m = nn.ModuleList(C3k(self.c, self.c, 2, shortcut) if c3k else Bottleneck(self.c, self.c, shortcut, (3, 3), 0.5)
                                for _ in range(n))
 
+    def split_cv1(self):
+        """Two convolutions instead of conv + channel split: the halves come out contiguous, so the
+        bottleneck that reads the second half (and adds it back) needs no strided copy."""
+        self.cv1a, self.cv1b = _split_conv(self.cv1, self.c)
+        del self.cv1
+
     def forward(self, x):
-        y = list(self.cv1(x).chunk(2, 1))
+        y = [self.cv1a(x), self.cv1b(x)] if hasattr(self, "cv1a") else list(self.cv1(x).chunk(2, 1))
         y.extend(m(y[-1]) for m in self.m)
         return self.cv2(torch.cat(y, 1))
 
@@ -151,8 +171,12 @@ class C2PSA(nn.Module):
         self.cv2 = Conv(2 * self.c, c1, 1)
         self.m = nn.Sequential(*(PSABlock(self.c, 0.5, self.c // 64) for _ in range(n)))
 
+    def split_cv1(self):
+        self.cv1a, self.cv1b = _split_conv(self.cv1, self.c)
+        del self.cv1
+
     def forward(self, x):
-        a, b = self.cv1(x).split((self.c, self.c), dim=1)
+        a, b = (self.cv1a(x), self.cv1b(x)) if hasattr(self, "cv1a") else self.cv1(x).split((self.c, self.c), dim=1)
         return self.cv2(torch.cat((a, self.m(b)), 1))
 
 
@@ -286,6 +310,9 @@ def build_model(nc: int, device, dtype=torch.float16, seed: int = 0, fuse: bool 
         for mod in m.modules():
             if isinstance(mod, Conv):
                 mod.fuse()
+        for mod in list(m.modules()):
+            if isinstance(mod, (C3k2, C2PSA)):
+                mod.split_cv1()
     m = m.to(device=device, dtype=dtype).to(memory_format=torch.channels_last)
     for p in m.parameters():
         p.requires_grad_(False)

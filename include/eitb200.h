@@ -71,10 +71,12 @@ long long eitb_profile_report(char* buf, size_t cap);
  *   body_mask [B,H,W] u8 or NULL; applied in OUTPUT orientation (nonzero keeps)
  *   out_u8    [B,H,W] u8 or NULL      -- classic_norm (+mask) result
  *   out_nchw  [B,3,H,W] of out_dtype or NULL -- u8/255 rounded once to out_dtype
+ *   channels_last  0: NCHW memory order; 1: the same logical tensor stored NHWC ([B,H,W,3]),
+ *             the layout a channels-last cuDNN network reads (fp16 / bf16 outputs only)
  * W must be a multiple of 8. */
 int eitb_hu_window_nchw(const int16_t* px, int B, int H, int W, int lo, int hi, int rot180,
                         const uint8_t* body_mask, uint8_t* out_u8, void* out_nchw,
-                        int out_dtype, eitb_stream_t stream);
+                        int out_dtype, int channels_last, eitb_stream_t stream);
 
 /* u8 gray image(s) -> 3-channel NCHW /255 (the jpg_png route, ai_tools.py:365-400). */
 int eitb_u8_to_nchw(const uint8_t* gray, int B, int H, int W, void* out_nchw, int out_dtype,
@@ -159,7 +161,8 @@ int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, in
  * contraction, crop to box/4, bilinear x(H/mh) upsample, threshold -- fused with
  * create_segmentations_masks + overlay_segmentation_masks (utils.py:437-523,395-434): per
  * pixel OR of the colour codes of every instance covering it.
- *   dets/n_det as written by eitb_nms; protos [B,nm,mh,mw] of proto_dtype
+ *   dets/n_det as written by eitb_nms; protos [B,nm,mh,mw] of proto_dtype, stored NCHW
+ *   (proto_channels_last 0) or NHWC, i.e. [B,mh,mw,nm] (1: what a channels-last network emits)
  *   variant   0: logits, interpolate, > 0 (8.3.x)   1: sigmoid, interpolate, > 0.5 (8.0-8.2)
  *   code      [B,H,W] u8 out: overlay codes
  *   inst_area [B,max_det] int32 out or NULL: mask pixel count (the empty-mask filter)
@@ -167,7 +170,7 @@ int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, in
  * H == 4*mh, W == 4*mw. */
 size_t eitb_mask_decode_workspace_bytes(int B, int max_det, int nm, int mh, int mw);
 int eitb_mask_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos,
-                     int proto_dtype, int B, int nm, int mh, int mw, int H, int W, int variant,
+                     int proto_dtype, int proto_channels_last, int B, int nm, int mh, int mw, int H, int W, int variant,
                      uint8_t* code, int32_t* inst_area, uint8_t* inst_bits, void* ws,
                      size_t ws_bytes, eitb_stream_t stream);
 

@@ -40,6 +40,11 @@ def test_hu_window_matches_reference_golden(ops, golden, dtype):
     want = u8m.cpu().to(dtype) / 255
     for c in range(3):
         assert torch.equal(nchwm[:, c].cpu(), want)
+    if dtype != torch.float32:                       # channels-last storage: same logical tensor
+        _, cl = ops.hu_window(dev(px), body_mask=dev(body), want_u8=False, nchw_dtype=dtype, channels_last=True)
+        assert cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(cl, nchwm)
+        _, cl2 = ops.hu_window(dev(px), rot180=False, want_u8=False, nchw_dtype=dtype, channels_last=True)
+        assert torch.equal(cl2, ops.hu_window(dev(px), rot180=False, nchw_dtype=dtype)[1])
 
 
 def test_hu_window_every_int16(ops, golden):
@@ -239,6 +244,8 @@ def test_mask_decode_batch_and_half_protos(ops):
     code16, _, _ = ops.mask_decode(dets, n, ph.to(DEV))
     code16ref, _, _ = ops.mask_decode(dets, n, ph.float().to(DEV))
     assert torch.equal(code16, code16ref)          # fp16 protos are widened exactly
+    cl = ph.to(DEV).contiguous(memory_format=torch.channels_last)     # NHWC storage, same result
+    assert torch.equal(ops.mask_decode(dets, n, cl)[0], code16)
 
 
 def test_codes_to_bgr(ops):
