@@ -208,6 +208,10 @@ int launch_decode(const float* dets, const int32_t* n_det, int max_det, const vo
 
 }  // namespace
 
+int eitb_mask_decode_tc(const float* dets, const int32_t* n_det, int max_det, const void* protos, int nhwc, int B, int mh,
+                        int mw, int H, int W, int variant, uint8_t* code, int32_t* inst_area, uint8_t* inst_bits,
+                        cudaStream_t s);                     // k6_mask_decode_tc.cu
+
 extern "C" size_t eitb_mask_decode_workspace_bytes(int B, int max_det, int nm, int mh, int mw) {
     (void)B; (void)max_det; (void)nm; (void)mh; (void)mw;
     return 0;
@@ -219,7 +223,7 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
                                 eitb_stream_t stream) {
     (void)ws; (void)ws_bytes;
     if (!dets || !n_det || !protos || !code || B < 0 || nm <= 0 || mh <= 0 || mw <= 0 || max_det <= 0 ||
-        max_det > kMaxDet || (variant != 0 && variant != 1))
+        max_det > kMaxDet || (variant & ~0x11))
         return EITB_ERR_BAD_ARG;
     if (H != 4 * mh || W != 4 * mw || (mw % 4) != 0) return EITB_ERR_UNSUPPORTED;
     if (B == 0) return EITB_OK;
@@ -228,6 +232,11 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
         return EITB_ERR_LAUNCH;
     if (inst_bits && cudaMemsetAsync(inst_bits, 0, (size_t)B * max_det * H * (W / 8), s) != cudaSuccess)
         return EITB_ERR_LAUNCH;
+    // fp16 prototypes with 32 channels (what the network emits): contraction on the tensor cores
+    if (proto_dtype == EITB_F16 && nm == 32 && !(variant & 0x10) && !(reinterpret_cast<uintptr_t>(protos) & 15))
+        return eitb_mask_decode_tc(dets, n_det, max_det, protos, proto_channels_last, B, mh, mw, H, W, variant & 1, code,
+                                   inst_area, inst_bits, s);
+    variant &= 1;
     switch (proto_dtype) {
         case EITB_F32: return launch_decode<float>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
         case EITB_F16: return launch_decode<__half>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);

@@ -163,7 +163,9 @@ int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, in
  * pixel OR of the colour codes of every instance covering it.
  *   dets/n_det as written by eitb_nms; protos [B,nm,mh,mw] of proto_dtype, stored NCHW
  *   (proto_channels_last 0) or NHWC, i.e. [B,mh,mw,nm] (1: what a channels-last network emits)
- *   variant   0: logits, interpolate, > 0 (8.3.x)   1: sigmoid, interpolate, > 0.5 (8.0-8.2)
+ *   variant   bit 0 -- 0: logits, interpolate, > 0 (8.3.x)   1: sigmoid, interpolate, > 0.5 (8.0-8.2)
+ *             bit 4 -- keep the contraction on the CUDA cores (fp16 prototypes with nm == 32 otherwise
+ *             go through tcgen05.mma with the accumulator in tensor memory; same semantics)
  *   code      [B,H,W] u8 out: overlay codes
  *   inst_area [B,max_det] int32 out or NULL: mask pixel count (the empty-mask filter)
  *   inst_bits [B,max_det,H,W/8] u8 out or NULL: per-instance bit masks (LSB = lowest x)

@@ -16,5 +16,6 @@ for r in rows:
         out.append((inst, smp, r[0], r[1][:110]))
 tot = sum(o[0] for o in out) or 1; ts = sum(o[1] for o in out) or 1
 print(fn[:120]); print("warp instructions", tot, "samples", ts)
-for o in sorted(out, key=lambda o: -o[1])[:topn]:
+key = 0 if len(sys.argv) > 4 and sys.argv[4] == "inst" else 1
+for o in sorted(out, key=lambda o: -o[key])[:topn]:
     print(f"{100*o[0]/tot:5.1f}% inst {100*o[1]/ts:5.1f}% samples  L{o[2]}: {o[3]}")

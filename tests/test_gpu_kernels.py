@@ -248,6 +248,33 @@ def test_mask_decode_batch_and_half_protos(ops):
     assert torch.equal(ops.mask_decode(dets, n, cl)[0], code16)
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("case", ["teacher", "random50", "random300", "empty"])
+def test_mask_decode_tensor_core_path(ops, case, variant):
+    """fp16 prototypes go through tcgen05.mma; the result must match the CUDA-core kernel (variant bit 4)
+    and the CPU restatement within the mask tolerance, for NCHW and channels-last prototypes."""
+    if case == "teacher":
+        head, protos = synth.teacher_heads(seed=4)
+        head, protos = head[None], protos[None]
+    else:
+        head, protos = synth.random_heads(2, {"random50": 50, "random300": 300, "empty": 0}[case], seed=31)
+    ph = torch.from_numpy(protos).half()
+    dets, idx, n = ops.nms(dev(head), 4)
+    tc, area_tc, bits_tc = ops.mask_decode(dets, n, ph.to(DEV), variant, want_area=True, want_bits=True)
+    cc, area_cc, bits_cc = ops.mask_decode(dets, n, ph.to(DEV), variant | 0x10, want_area=True, want_bits=True)
+    total = bits_cc.numel() * 8
+    diff = int((np.unpackbits(bits_tc.cpu().numpy()) != np.unpackbits(bits_cc.cpu().numpy())).sum())
+    assert diff <= 1e-5 * max(total, 1), (diff, total)
+    assert (tc != cc).float().mean().item() <= 1e-4
+    nhwc, _, _ = ops.mask_decode(dets, n, ph.to(DEV).contiguous(memory_format=torch.channels_last), variant)
+    assert torch.equal(nhwc, tc)
+    for b in range(head.shape[0]):
+        r = Y.postprocess(torch.from_numpy(head[b]), ph[b].float(), 4, (512, 512), (512, 512),
+                          variant="logit" if variant == 0 else "sigmoid", drop_empty=False)
+        want = O.overlay_codes(O.class_union_masks(r["masks"].numpy(), r["cls"].numpy().astype(int), 512))
+        assert (want != tc[b].cpu().numpy()).mean() <= 1e-4
+
+
 def test_codes_to_bgr(ops):
     code = np.random.default_rng(0).choice([0, 1, 3, 6, 7], (3, 64, 64)).astype(np.uint8)
     assert np.array_equal(ops.codes_to_bgr(dev(code)).cpu().numpy(), O.code_to_bgr(code))
