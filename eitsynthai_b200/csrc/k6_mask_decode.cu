@@ -107,6 +107,9 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
     const bool in_img = oy < H && ox0 < W;
     uint32_t codes[4] = {0, 0, 0, 0};        // 16 x u8
     const float thr = variant == 1 ? 0.5f : 0.0f;
+    // prototype rows read by the 8 output rows of this warp (clamped like the halo)
+    const float wrow_lo = (float)min(max(ty * PT - 1 + ((tid >> 5) << 1), 0), mh - 1);
+    const float wrow_hi = (float)min(max(ty * PT - 1 + ((tid >> 5) << 1) + 3, 0), mh - 1);
 
     for (int c0 = 0; c0 < nact; c0 += G) {
         const int ng = min(G, nact - c0);
@@ -148,12 +151,23 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
         __syncthreads();
         // x4 bilinear (align_corners=False) + threshold + OR
         for (int g = 0; g < ng; ++g) {
+            if (sbox[g * 4 + 3] <= wrow_lo || sbox[g * 4 + 1] > wrow_hi) continue;   // box misses this warp's rows (warp-uniform)
             const float* L0 = Ls + g * HP + hy0 * HT + cg * 4;
             const float* L1 = L0 + HT;
+            float a0[6], a1[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { a0[i] = L0[i]; a1[i] = L1[i]; }
+            float vmin = fminf(a0[0], a1[0]), vmax = fmaxf(a0[0], a1[0]);
+#pragma unroll
+            for (int i = 1; i < 6; ++i) { vmin = fminf(vmin, fminf(a0[i], a1[i])); vmax = fmaxf(vmax, fmaxf(a0[i], a1[i])); }
+            // every output is a convex combination of these 12 logits: all above / none above the threshold
+            // decides the 16 pixels without interpolating (only mask borders take the slow path)
+            uint32_t bits = vmin > thr ? 0xffffu : 0u;
+            if (vmax > thr && !(vmin > thr)) {
             float V[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) V[i] = (1.f - ly) * L0[i] + ly * L1[i];
-            uint32_t bits = 0;
+            for (int i = 0; i < 6; ++i) V[i] = (1.f - ly) * a0[i] + ly * a1[i];
+            bits = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int mm = j >> 2, jj = j & 3;
@@ -162,11 +176,12 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
                 const float v = (1.f - lx) * V[x0] + lx * V[x0 + 1];
                 bits |= (v > thr ? 1u : 0u) << j;
             }
+            }
             if (!in_img) bits = 0;
             const uint32_t cc = (uint32_t)sinfo[g * 2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if ((bits >> j) & 1u) codes[j >> 2] |= cc << (8 * (j & 3));
+            for (int k = 0; k < 4; ++k)                            // 4 mask bits -> 4 bytes of the class code
+                codes[k] |= ((((bits >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) * cc;
             if (inst_bits && in_img) {
                 const long long o = (((long long)b * max_det + sinfo[g * 2 + 1]) * H + oy) * (W >> 3) + (ox0 >> 3);
                 *reinterpret_cast<uint16_t*>(inst_bits + o) = (uint16_t)bits;

@@ -71,6 +71,8 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + OFF_ACT + max_det * 4 + ((8 - (max_det * 4) % 8) % 8));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
     int* s_nact = reinterpret_cast<int*>(tmem_slot + 1);
+    float* colx = reinterpret_cast<float*>(s_nact + 1);                       // [NCOL] prototype x of every halo column
+    float* coly = colx + NCOL;                                                // [NCOL] prototype y (columns >= HPT: -1, never inside a box)
 
     constexpr int nm = 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -82,6 +84,11 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
     const int n = min(n_det[b], max_det);
     const float rx = (float)((double)mw / (double)W), ry = (float)((double)mh / (double)H);
 
+    if (tid < NCOL) {
+        const int hy = tid / HTX, hx = tid - hy * HTX;
+        colx[tid] = tid < HPT ? (float)min(max((int)(blockIdx.x - (blockIdx.x / tiles_per_img) * tiles_per_img) % tiles_x * PTX_ - 1 + hx, 0), mw - 1) : -1.f;
+        coly[tid] = tid < HPT ? (float)min(max((int)(blockIdx.x - (blockIdx.x / tiles_per_img) * tiles_per_img) / tiles_x * PTY_ - 1 + hy, 0), mh - 1) : -1.f;
+    }
     if (smem_u32(sB) & 1023u) __trap();                                        // swizzled operand tiles need 1 KiB alignment
     if (tid == 0) {
         *s_nact = 0;
@@ -151,6 +158,8 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
     const bool in_img = row_ok && oy < H && ox0 < W;
     uint32_t codes[4] = {0, 0, 0, 0};
     const float thr = (variant & 1) ? 0.5f : 0.0f;
+    const float wrow_lo = (float)min(max(ty * PTY_ - 1 + (warp << 1), 0), mh - 1);      // prototype rows this warp reads
+    const float wrow_hi = (float)min(max(ty * PTY_ - 1 + (warp << 1) + 3, 0), mh - 1);
 
     // instruction descriptor: D fp32, A/B fp16, both K-major, N = 256, M = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(MROW >> 4) << 24);
@@ -229,16 +238,14 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (g < ng) {
+                        const int e_end = min(32, HPT - c0);
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            const int h = c0 + e;
-                            if (h < HPT) {
-                                const int hy = h / HTX, hx = h - hy * HTX;
-                                const float fy = (float)min(max(ty * PTY_ - 1 + hy, 0), mh - 1);
-                                const float fx = (float)min(max(tx * PTX_ - 1 + hx, 0), mw - 1);
+                            if (e < e_end) {
+                                const float fx = colx[c0 + e], fy = coly[c0 + e];        // broadcast reads
                                 float val = __uint_as_float(v[e]);
                                 if (variant & 1) val = 1.f / (1.f + expf(-val));
-                                Ls[g * LSTRIDE + h] = (fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2) ? val : 0.f;
+                                Ls[g * LSTRIDE + c0 + e] = (fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2) ? val : 0.f;
                             }
                         }
                     }
@@ -250,12 +257,23 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
             // ---- x4 bilinear (align_corners=False) + threshold + OR, all warps, 32 instances
             if (row_ok) {
                 for (int g = 0; g < ng; ++g) {
+                    if (sbox[(q * 32 + g) * 4 + 3] <= wrow_lo || sbox[(q * 32 + g) * 4 + 1] > wrow_hi) continue;   // warp-uniform
                     const float* L0 = Ls + g * LSTRIDE + hy0 * HTX + cg * 4;
                     const float* L1 = L0 + HTX;
+                    float a0[6], a1[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { a0[i] = L0[i]; a1[i] = L1[i]; }
+                    float vmin = fminf(a0[0], a1[0]), vmax = fmaxf(a0[0], a1[0]);
+#pragma unroll
+                    for (int i = 1; i < 6; ++i) { vmin = fminf(vmin, fminf(a0[i], a1[i])); vmax = fmaxf(vmax, fmaxf(a0[i], a1[i])); }
+                    // every output is a convex combination of these 12 logits: all above / none above the threshold
+                    // decides the 16 pixels without interpolating (only mask borders take the slow path)
+                    uint32_t bits = vmin > thr ? 0xffffu : 0u;
+                    if (vmax > thr && !(vmin > thr)) {
                     float V[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) V[i] = (1.f - ly) * L0[i] + ly * L1[i];
-                    uint32_t bits = 0;
+                    for (int i = 0; i < 6; ++i) V[i] = (1.f - ly) * a0[i] + ly * a1[i];
+                    bits = 0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int mm = j >> 2, jj = j & 3;
@@ -264,11 +282,12 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
                         const float vv = (1.f - lx) * V[x0] + lx * V[x0 + 1];
                         bits |= (vv > thr ? 1u : 0u) << j;
                     }
+                    }
                     if (!in_img) bits = 0;
                     const uint32_t cc = (uint32_t)sinfo[(q * 32 + g) * 2];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if ((bits >> j) & 1u) codes[j >> 2] |= cc << (8 * (j & 3));
+                    for (int k = 0; k < 4; ++k)                    // 4 mask bits -> 4 bytes of the class code
+                        codes[k] |= ((((bits >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) * cc;
                     const int inst = sinfo[(q * 32 + g) * 2 + 1];
                     if (inst_bits && in_img) {
                         const long long o = (((long long)b * max_det + inst) * H + oy) * (W >> 3) + (ox0 >> 3);
@@ -298,7 +317,7 @@ int eitb_mask_decode_tc(const float* dets, const int32_t* n_det, int max_det, co
                         int mw, int H, int W, int variant, uint8_t* code, int32_t* inst_area, uint8_t* inst_bits,
                         cudaStream_t s) {
     const int tiles_x = eitb_div_up(mw, PTX_), tiles_y = eitb_div_up(mh, PTY_);
-    const size_t smem = (size_t)OFF_ACT + (size_t)max_det * 4 + 64;
+    const size_t smem = (size_t)OFF_ACT + (size_t)max_det * 4 + 64 + 2 * NCOL * sizeof(float);
     if (cudaFuncSetAttribute(mask_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     const long long grid = (long long)B * tiles_x * tiles_y;
