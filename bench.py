@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunk", type=int, default=64, help="slices per CNN batch")
+    ap.add_argument("--chunk", type=int, default=160, help="slices per CNN batch / CUDA graph")
     ap.add_argument("--slices", type=int, default=N_SLICES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -404,6 +404,25 @@ def run_b200(args):
         "fill_body_kernel": px * 3, "small_first_kernel": px, "small_repaint_kernel": px // 8,
         "contour_cand_kernel": px * 5, "contour_repaint_kernel": px // 8,
     }
+    per_slice_bytes["mask_decode_tc_kernel"] = per_slice_bytes["mask_decode_kernel"]
+    kernels = dict(kernels)
+    if "conv_epilogue_kernel" in kernels:                          # K9 has two entry points; account them together
+        a, b_ = kernels.pop("conv_epilogue_kernel"), kernels.get("bias_act_kernel", (0, 0.0))
+        kernels["bias_act_kernel"] = (a[0] + b_[0], a[1] + b_[1])
+    # K9 (conv epilogue): one read + one write of every Conv output of the network, per slice
+    act_elems = {}
+    def _count(m, i, o):                                         # per slice: C_out x H_out x W_out of every Conv
+        st = m.conv.stride[0]
+        act_elems["n"] = act_elems.get("n", 0) + m.conv.out_channels * (-(-i[0].shape[2] // st)) * (-(-i[0].shape[3] // st))
+    from eitsynthai_b200.yolo_seg import Conv
+    hooks = [m.register_forward_hook(_count) for m in pipe.axial_model_512.modules() if isinstance(m, Conv)]
+    with torch.no_grad():
+        pipe.axial_model_512(torch.zeros((1, 3, SIZE, SIZE), dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last))
+    for h in hooks:
+        h.remove()
+    # exact bytes of the timed region for K9 are filled in below (the rib network adds its own launches)
+    axial_act_bytes = act_elems["n"] * 2 * 2                                    # fp16, read + write, per slice
+    per_slice_bytes["bias_act_kernel"] = axial_act_bytes
     own = {k: v for k, v in kernels.items() if k in per_slice_bytes}
     roof = None
     if own:
@@ -411,8 +430,18 @@ def run_b200(args):
         cnt, tot_ms = own[top]
         ms_call = tot_ms / cnt
         ach = per_slice_bytes[top] * min(args.chunk, S * nl) / (ms_call / 1e3) / 1e9
+        if top == "bias_act_kernel":                                # ~90 launches of different sizes per network call
+            n_rib_px = 416 * 640 if nslices == N_SLICES else 0
+            step_bytes = axial_act_bytes * S * nl + axial_act_bytes * n_rib_px / (SIZE * SIZE) * len([s for s in range(S) if s % world == rank])
+            ach = step_bytes * args.steps / (tot_ms / 1e3) / 1e9
+        traffic = None
+        try:                                                        # dram bytes per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f).get(top, {}).get("dram_bytes_per_launch")
+        except OSError:
+            pass
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": None, "ms_per_launch": ms_call, "launches": cnt, "slices_per_launch": min(args.chunk, S * nl),
+                "traffic": traffic, "ms_per_launch": ms_call, "launches": cnt, "slices_per_launch": min(args.chunk, S * nl),
                 "algorithmic_bytes_per_slice": per_slice_bytes[top],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                 "how": "CUDA events around every launch of the kernel (libeitb200 launch profiler) over an eager pass of the same steps"}
@@ -431,6 +460,8 @@ def run_b200(args):
                 "eager_ms_per_step": ms_eager,
                 "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stages.items())},
                 "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1][1])},
+                "kernel_gbs": {k: round(per_slice_bytes[k] * min(args.chunk, S * nl) * v[0] / (v[1] / 1e3) / 1e9, 1)
+                               for k, v in kernels.items() if k in per_slice_bytes and v[1] > 0 and k != "bias_act_kernel"},
                 "selected_slices": sel.cpu().tolist()}
         print(json.dumps(line), flush=True)
     if world > 1:

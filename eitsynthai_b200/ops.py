@@ -234,6 +234,39 @@ def bias_act_(x: torch.Tensor, bias: torch.Tensor | None, silu: bool = True) -> 
     return x
 
 
+def conv_epilogue(src: torch.Tensor, bias: torch.Tensor | None, silu: bool, residual: torch.Tensor | None = None,
+                  inplace: bool = True, out2: torch.Tensor | None = None, out2_off: int = 0):
+    """y = act(src + bias [+ residual]) for a channels-last half tensor; y replaces ``src`` (``inplace``)
+    and/or lands in channels [out2_off, out2_off + C) of the channels-last tensor ``out2``."""
+    cl = torch.channels_last
+    if not src.is_cuda or src.dim() != 4 or not src.is_contiguous(memory_format=cl):
+        raise ValueError("src must be a channels-last CUDA tensor")
+    B, Cc, H, W = src.shape
+    if residual is not None and (residual.shape != src.shape or not residual.is_contiguous(memory_format=cl)):
+        raise ValueError("residual must match src")
+    if out2 is not None and (not out2.is_contiguous(memory_format=cl) or out2.shape[0] != B or out2.shape[2:] != src.shape[2:]):
+        raise ValueError("out2 must be a channels-last tensor with the same batch and spatial size")
+    with torch.cuda.device(src.device):
+        cabi.call("eitb_conv_epilogue_nhwc", src.data_ptr(), _DT[src.dtype], B * H * W, Cc, _ptr(bias), int(silu),
+                  _ptr(residual), src.data_ptr() if inplace else 0, _ptr(out2), out2.shape[1] if out2 is not None else 0,
+                  out2_off, _stream(src))
+    return src if inplace else None
+
+
+def upsample2x_concat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """cat((nearest_upsample_x2(a), b), dim=1) for channels-last half tensors, in one pass."""
+    cl = torch.channels_last
+    if not (a.is_cuda and a.is_contiguous(memory_format=cl) and b.is_contiguous(memory_format=cl)):
+        raise ValueError("a and b must be channels-last CUDA tensors")
+    B, Ca, h, w = a.shape
+    Cb = b.shape[1]
+    assert b.shape[0] == B and b.shape[2] == 2 * h and b.shape[3] == 2 * w and a.dtype == b.dtype
+    out = torch.empty((B, Ca + Cb, 2 * h, 2 * w), dtype=a.dtype, device=a.device, memory_format=cl)
+    with torch.cuda.device(a.device):
+        cabi.call("eitb_upsample2x_concat_nhwc", a.data_ptr(), b.data_ptr(), out.data_ptr(), _DT[a.dtype], B, h, w, Ca, Cb, _stream(a))
+    return out
+
+
 # ------------------------------------------------------------------------------------ K8
 def tri_label(nodes_xy: torch.Tensor, tri: torch.Tensor, poly_xy: torch.Tensor, poly_off: torch.Tensor,
               poly_cls: torch.Tensor, outer_cls: int = 4) -> torch.Tensor:

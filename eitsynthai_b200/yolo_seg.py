@@ -38,14 +38,27 @@ class Conv(nn.Module):
         self.fused_bias = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
         self.bn = nn.Identity()
 
-    def forward(self, x):
+    def forward(self, x, residual=None, out=None, out_off=0, keep=True):
+        """``residual`` is added after the activation (Bottleneck shortcut); ``out``/``out_off`` also place
+        the result in a channel slice of a wider tensor (concat buffer); ``keep=False`` skips the
+        stand-alone result when only the slice is needed (returns None)."""
         if self.fused_bias is None:
-            return self.act(self.bn(self.conv(x)))
-        y = self.conv(x)
-        if y.is_cuda and y.dtype != torch.float32 and y.shape[1] % 8 == 0 and y.is_contiguous(memory_format=torch.channels_last):
-            from . import ops
-            return ops.bias_act_(y, self.fused_bias, self.has_act)
-        return self.act(y + self.fused_bias.to(y.dtype).view(1, -1, 1, 1))
+            y = self.act(self.bn(self.conv(x)))
+        else:
+            y = self.conv(x)
+            if (y.is_cuda and y.dtype != torch.float32 and y.shape[1] % 8 == 0
+                    and y.is_contiguous(memory_format=torch.channels_last)
+                    and (out is None or (out.shape[1] % 8 == 0 and out_off % 8 == 0))):
+                from . import ops
+                if residual is None and out is None:
+                    return ops.bias_act_(y, self.fused_bias, self.has_act)
+                return ops.conv_epilogue(y, self.fused_bias, self.has_act, residual, keep, out, out_off)
+            y = self.act(y + self.fused_bias.to(y.dtype).view(1, -1, 1, 1))
+        if residual is not None:
+            y = y + residual
+        if out is not None:
+            out[:, out_off:out_off + y.shape[1]] = y
+        return y if keep else None
 
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
@@ -76,9 +89,8 @@ class Bottleneck(nn.Module):
         self.cv2 = Conv(c_, c2, k[1])
         self.add = shortcut and c1 == c2
 
-    def forward(self, x):
-        y = self.cv2(self.cv1(x))
-        return x + y if self.add else y
+    def forward(self, x, out=None, out_off=0, keep=True):
+        return self.cv2(self.cv1(x), residual=x if self.add else None, out=out, out_off=out_off, keep=keep)
 
 
 class C3k(nn.Module):
@@ -90,8 +102,16 @@ class C3k(nn.Module):
         self.cv3 = Conv(2 * c_, c2, 1)
         self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, (k, k), 1.0) for _ in range(n)))
 
-    def forward(self, x):
-        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+    def forward(self, x, out=None, out_off=0, keep=True):
+        c_ = self.cv1.conv.out_channels
+        buf = torch.empty((x.shape[0], 2 * c_, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                          memory_format=torch.channels_last)
+        h = self.cv1(x)
+        for i, m in enumerate(self.m):
+            last = i == len(self.m) - 1
+            h = m(h, out=buf if last else None, out_off=0, keep=not last)
+        self.cv2(x, out=buf, out_off=c_, keep=False)
+        return self.cv3(buf, out=out, out_off=out_off, keep=keep)
 
 
 class C3k2(nn.Module):
@@ -110,9 +130,20 @@ class C3k2(nn.Module):
         del self.cv1
 
     def forward(self, x):
-        y = [self.cv1a(x), self.cv1b(x)] if hasattr(self, "cv1a") else list(self.cv1(x).chunk(2, 1))
-        y.extend(m(y[-1]) for m in self.m)
-        return self.cv2(torch.cat(y, 1))
+        if not hasattr(self, "cv1a"):
+            y = list(self.cv1(x).chunk(2, 1))
+            y.extend(m(y[-1]) for m in self.m)
+            return self.cv2(torch.cat(y, 1))
+        # every producer writes its channel slice of the concat buffer from its own epilogue
+        c, n = self.c, len(self.m)
+        buf = torch.empty((x.shape[0], (2 + n) * c, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                          memory_format=torch.channels_last)
+        self.cv1a(x, out=buf, out_off=0, keep=False)
+        h = self.cv1b(x, out=buf, out_off=c)
+        for i, m in enumerate(self.m):
+            last = i == n - 1
+            h = m(h, out=buf, out_off=(2 + i) * c, keep=not last)
+        return self.cv2(buf)
 
 
 class SPPF(nn.Module):
@@ -249,6 +280,15 @@ class Segment(nn.Module):
         return head, protos
 
 
+def _up_cat(a, b):
+    """Upsample(x2, nearest) + Concat of the neck (yaml layers 11-12, 14-15)."""
+    if a.is_cuda and a.dtype != torch.float32 and a.is_contiguous(memory_format=torch.channels_last) \
+            and b.is_contiguous(memory_format=torch.channels_last):
+        from . import ops
+        return ops.upsample2x_concat(a, b)
+    return torch.cat((F.interpolate(a, scale_factor=2.0, mode="nearest"), b), 1)
+
+
 class YOLO11sSeg(nn.Module):
     """yolo11-seg.yaml, scale s (depth 0.50, width 0.50, max_channels 1024)."""
 
@@ -280,8 +320,8 @@ class YOLO11sSeg(nn.Module):
         p3 = self.l4(self.l3(x))
         p4 = self.l6(self.l5(p3))
         p5 = self.l10(self.l9(self.l8(self.l7(p4))))
-        u4 = self.l13(torch.cat((F.interpolate(p5, scale_factor=2.0, mode="nearest"), p4), 1))
-        n3 = self.l16(torch.cat((F.interpolate(u4, scale_factor=2.0, mode="nearest"), p3), 1))
+        u4 = self.l13(_up_cat(p5, p4))
+        n3 = self.l16(_up_cat(u4, p3))
         n4 = self.l19(torch.cat((self.l17(n3), u4), 1))
         n5 = self.l22(torch.cat((self.l20(n4), p5), 1))
         return self.head((n3, n4, n5))

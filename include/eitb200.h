@@ -194,6 +194,18 @@ int eitb_codes_to_bgr(const uint8_t* code, uint8_t* bgr, int64_t n, eitb_stream_
 int eitb_bias_act_nhwc(void* x, int dtype, long long n_pixels, int C, const float* bias, int act,
                        eitb_stream_t stream);
 
+/* General form: y = act(src + bias [+ residual]); y is written to `out` (may alias src; NULL to skip)
+ * and/or into channels [out2_off, out2_off + C) of a wider channels-last tensor out2 [n_pixels, out2_C]
+ * (the concat buffer of a C3k2 / C3k block: no separate torch.cat, no separate residual add). */
+int eitb_conv_epilogue_nhwc(const void* src, int dtype, long long n_pixels, int C, const float* bias, int act,
+                            const void* residual, void* out, void* out2, int out2_C, int out2_off,
+                            eitb_stream_t stream);
+
+/* Upsample(x2, nearest) + Concat of the YOLO11 neck in one pass: a [B,h,w,Ca], b [B,2h,2w,Cb]
+ * -> out [B,2h,2w,Ca+Cb], all channels-last 16-bit. */
+int eitb_upsample2x_concat_nhwc(const void* a, const void* b, void* out, int dtype, int B, int h, int w, int Ca,
+                                int Cb, eitb_stream_t stream);
+
 /* ---- K8: per-triangle tissue labelling ----------------------------------------------------------
  * Replaces divide_triangles_into_groups / process_triangle / the CLASS vector of
  * export_mesh_for_femm (mesh_tools/femm_generator.py:12-85,118-184,187-265) with the

@@ -136,3 +136,43 @@ def test_run_series_matches_chunked_segment(pipe):
     assert torch.equal(res.labels, code) and np.array_equal(out_host.numpy(), code.cpu().numpy())
     srt = vol[np.argsort(inst, kind="stable")]
     assert np.array_equal(res.front_u8.cpu().numpy(), O.front_slice_norm(srt))
+
+
+def test_cnn_fused_epilogues_match_plain_torch():
+    """BN folding + K9 epilogues (bias/SiLU/residual/concat-slice) + fused upsample-concat vs the plain
+    PyTorch module with the same weights (fp16 on both sides)."""
+    from eitsynthai_b200.yolo_seg import YOLO11sSeg, build_model
+    fused = build_model(4, "cuda:0", torch.float16, seed=5, fuse=True)
+    plain = build_model(4, "cuda:0", torch.float16, seed=5, fuse=False)
+    for mod in plain.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            assert float(mod.running_var.float().mean()) == 1.0
+    x = torch.rand(3, 3, 256, 256, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        h1, p1 = fused(x)
+        h0, p0 = plain(x)
+    for a, b in ((h1, h0), (p1, p0)):
+        err = (a.float() - b.float()).abs().max().item()
+        assert err <= 2e-2 * max(1.0, b.float().abs().max().item()), err
+
+
+def test_conv_epilogue_and_upsample_concat_kernels():
+    from eitsynthai_b200 import ops
+    torch.manual_seed(0)
+    cl = torch.channels_last
+    y = torch.randn(2, 32, 20, 24, device="cuda").half().contiguous(memory_format=cl)
+    res = torch.randn_like(y).contiguous(memory_format=cl)
+    bias = torch.randn(32, device="cuda")
+    buf = torch.zeros(2, 96, 20, 24, device="cuda", dtype=torch.half).contiguous(memory_format=cl)
+    want = (torch.nn.functional.silu(y.float() + bias.view(1, -1, 1, 1)) + res.float())
+    src = y.clone(memory_format=cl)
+    out = ops.conv_epilogue(src, bias, True, res, True, buf, 32)
+    assert torch.allclose(out.float(), want, atol=4e-3, rtol=2e-3)
+    assert torch.equal(buf[:, 32:64], out) and float(buf[:, :32].abs().max()) == 0 and float(buf[:, 64:].abs().max()) == 0
+    src2 = y.clone(memory_format=cl)
+    assert ops.conv_epilogue(src2, None, False, None, False, buf, 64) is None
+    assert torch.equal(buf[:, 64:], y) and torch.equal(src2, y)
+    a = torch.randn(2, 16, 5, 7, device="cuda").half().contiguous(memory_format=cl)
+    b = torch.randn(2, 24, 10, 14, device="cuda").half().contiguous(memory_format=cl)
+    got = ops.upsample2x_concat(a, b)
+    assert torch.equal(got, torch.cat((torch.nn.functional.interpolate(a, scale_factor=2.0, mode="nearest"), b), 1))
