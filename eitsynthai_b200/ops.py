@@ -267,6 +267,37 @@ def upsample2x_concat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------ K10
+def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int) -> torch.Tensor:
+    """Lists of the 3 per-level branch outputs (channels-last fp16 [B,64|nc|nm,h,w]) -> head [B,4+nc+nm,A]."""
+    import ctypes as C
+    cl = torch.channels_last
+    B = box[0].shape[0]
+    for t in list(box) + list(cls) + list(mc):
+        if not (t.is_cuda and t.dtype == torch.float16 and (t.is_contiguous(memory_format=cl) or t.shape[1] == 1)):
+            raise ValueError("branch outputs must be channels-last fp16 CUDA tensors")
+    hs = (C.c_int * 3)(*[t.shape[2] for t in box])
+    ws = (C.c_int * 3)(*[t.shape[3] for t in box])
+    st = (C.c_int * 3)(*strides)
+    arr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
+    A = sum(t.shape[2] * t.shape[3] for t in box)
+    head = torch.empty((B, 4 + nc + nm, A), dtype=torch.float16, device=box[0].device)
+    with torch.cuda.device(head.device):
+        cabi.call("eitb_yolo_head_decode", arr(box), arr(cls), arr(mc), hs, ws, st, B, nc, nm, head.data_ptr(), _stream(head))
+    return head
+
+
+def sppf_pool_concat(x: torch.Tensor) -> torch.Tensor:
+    """x [B,C,h,w] channels-last fp16 -> [B,4C,h,w]: x | maxpool5 | maxpool9 | maxpool13."""
+    if not (x.is_cuda and x.dtype == torch.float16 and x.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("x must be a channels-last fp16 CUDA tensor")
+    B, Cc, h, w = x.shape
+    out = torch.empty((B, 4 * Cc, h, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        cabi.call("eitb_sppf_pool_concat", x.data_ptr(), B, h, w, Cc, out.data_ptr(), _stream(x))
+    return out
+
+
 # ------------------------------------------------------------------------------------ K8
 def tri_label(nodes_xy: torch.Tensor, tri: torch.Tensor, poly_xy: torch.Tensor, poly_off: torch.Tensor,
               poly_cls: torch.Tensor, outer_cls: int = 4) -> torch.Tensor:

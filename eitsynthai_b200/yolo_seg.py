@@ -155,7 +155,12 @@ class SPPF(nn.Module):
         self.m = nn.MaxPool2d(k, 1, k // 2)
 
     def forward(self, x):
-        y = [self.cv1(x)]
+        y0 = self.cv1(x)
+        if getattr(self, "fused_tails", False) and y0.is_cuda and y0.dtype == torch.float16 and y0.is_contiguous(memory_format=torch.channels_last) \
+                and y0.shape[1] % 8 == 0 and y0.shape[2] * y0.shape[3] <= 2048 and self.m.kernel_size == 5:
+            from . import ops
+            return self.cv2(ops.sppf_pool_concat(y0))
+        y = [y0]
         y.extend(self.m(y[-1]) for _ in range(3))
         return self.cv2(torch.cat(y, 1))
 
@@ -266,10 +271,15 @@ class Segment(nn.Module):
         box, cls, mc, shapes = [], [], [], []
         for i, x in enumerate(feats):
             shapes.append(x.shape[2:])
-            box.append(self.cv2[i](x).flatten(2))
-            cls.append(self.cv3[i](x).flatten(2))
-            mc.append(self.cv4[i](x).flatten(2))
-        box, cls, mc = torch.cat(box, 2), torch.cat(cls, 2), torch.cat(mc, 2)
+            box.append(self.cv2[i](x))
+            cls.append(self.cv3[i](x))
+            mc.append(self.cv4[i](x))
+        cl = torch.channels_last
+        if getattr(self, "fused_tails", False) and box[0].is_cuda and box[0].dtype == torch.float16 and all(
+                t.is_contiguous(memory_format=cl) or t.shape[1] == 1 for t in box + cls + mc):
+            from . import ops
+            return ops.yolo_head_decode(box, cls, mc, self.stride, self.nc, self.nm), protos
+        box, cls, mc = (torch.cat([t.flatten(2) for t in ts], 2) for ts in (box, cls, mc))
         A = box.shape[2]
         anchors, strides = self._grid(shapes, box.device, box.dtype)
         dist = (box.view(B, 4, self.reg_max, A).softmax(2) * self.bins.to(box.dtype)).sum(2)       # DFL
@@ -353,6 +363,8 @@ def build_model(nc: int, device, dtype=torch.float16, seed: int = 0, fuse: bool 
         for mod in list(m.modules()):
             if isinstance(mod, (C3k2, C2PSA)):
                 mod.split_cv1()
+            if isinstance(mod, (SPPF, Segment)):
+                mod.fused_tails = True                          # K10: one-pass SPPF pooling and head decode
     m = m.to(device=device, dtype=dtype).to(memory_format=torch.channels_last)
     for p in m.parameters():
         p.requires_grad_(False)

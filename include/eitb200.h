@@ -206,6 +206,17 @@ int eitb_conv_epilogue_nhwc(const void* src, int dtype, long long n_pixels, int 
 int eitb_upsample2x_concat_nhwc(const void* a, const void* b, void* out, int dtype, int B, int h, int w, int Ca,
                                 int Cb, eitb_stream_t stream);
 
+/* ---- K10: non-convolution tails of the network, fp16 channels-last ------------------------------------
+ * Detect/Segment inference tail: box[l] [B,h_l,w_l,64] DFL logits, cls[l]
+ * [B,h_l,w_l,nc] class logits, mc[l] [B,h_l,w_l,nm] for the 3 levels (host arrays of device pointers,
+ * sizes and strides) -> head [B,4+nc+nm,A] fp16: xywh in input pixels, sigmoid scores, coefficients. */
+int eitb_yolo_head_decode(const void* const* box, const void* const* cls, const void* const* mc, const int* hs,
+                          const int* ws, const int* strides, int B, int nc, int nm, void* head,
+                          eitb_stream_t stream);
+
+/* SPPF (yaml layer 9): x [B,h,w,C] -> out [B,h,w,4C] = x | maxpool5 | maxpool9 | maxpool13 (-inf padding). */
+int eitb_sppf_pool_concat(const void* x, int B, int h, int w, int C, void* out, eitb_stream_t stream);
+
 /* ---- K8: per-triangle tissue labelling ----------------------------------------------------------
  * Replaces divide_triangles_into_groups / process_triangle / the CLASS vector of
  * export_mesh_for_femm (mesh_tools/femm_generator.py:12-85,118-184,187-265) with the
