@@ -226,25 +226,30 @@ def run_b200(args):
     launches = {"n": 0}
     profiling = {"on": False}
 
-    def rib_stage(px):
-        """coronal rows of the local shard -> exchange -> rib model on the owned series -> indices."""
+    mine = [s for s in range(S) if sharded.owner_of_series(s, world) == rank]
+    mine_idx = torch.tensor(mine, dtype=torch.int64, device=dev)
+    rib_static = {"rows": torch.zeros((S, nslices, SIZE), dtype=torch.int16, device=dev),
+                  "mm": torch.zeros((S, 2), dtype=torch.int32, device=dev), "graph": None, "sel": None}
+
+    def rib_rows(px, src_row=None):
+        """K3: coronal rows + min/max of the local shard of every series.  ``px`` is [S,nl,H,W], or
+        [S,nl,1,W] when only the coronal row of every slice was shipped (``src_row`` = 0)."""
         with timer("K3_front_rows"):
             rows = torch.empty((S, nl, SIZE), dtype=torch.int16, device=dev)
             mm = torch.empty((S, 2), dtype=torch.int32, device=dev)
             mm[:, 0] = 2 ** 31 - 1; mm[:, 1] = -2 ** 31
             for s in range(S):
-                r, _ = ops.front_rows(px[s], orders[s], nl, row, fx, fz, mm[s])
+                r, _ = ops.front_rows(px[s], orders[s], nl, row if src_row is None else src_row, fx, fz, mm[s])
                 rows[s] = r
-            launches["n"] += S
-        with timer("C1_exchange"):
-            rows_all, mm_all = sharded.gather_rows(rows, mm, nslices)
+        return rows, mm
+
+    def rib_decide(rows_all, mm_all):
+        """MINMAX normalise -> letterbox -> rib network -> NMS -> scale_boxes -> arg-select, for the owned series."""
         sel = torch.zeros((S, 4), dtype=torch.int32, device=dev)
-        mine = [s for s in range(S) if sharded.owner_of_series(s, world) == rank]
         if mine:
             with timer("K3_minmax_letterbox"):
                 front = torch.stack([ops.minmax_u8(rows_all[s], mm_all[s]) for s in mine])
                 x, (gain, pad_x, pad_y, w0, h0) = pipe._rib_input(front)
-                launches["n"] += len(mine) + 1
             with timer("CNN_ribs"):
                 head, _ = pipe.ribs_model(x)
                 head = head.contiguous()
@@ -252,8 +257,20 @@ def run_b200(args):
                 dets, _, k = ops.nms(head, 1, CONF, IOU, MAX_DET, want_idx=False)
             with timer("K4_rib_select"):
                 boxes = ops.scale_boxes(dets, k, gain, pad_x, pad_y, w0, h0)
-                sel[mine] = ops.rib_select(boxes, k, 512.0)
-            launches["n"] += 3
+                sel.index_copy_(0, mine_idx, ops.rib_select(boxes, k, 512.0))
+        return sel
+
+    def rib_stage(px, graphed=False, src_row=None):
+        """coronal rows of the local shard -> exchange -> rib model on the owned series -> indices."""
+        rows, mm = rib_rows(px, src_row)
+        with timer("C1_exchange"):
+            rows_all, mm_all = sharded.gather_rows(rows, mm, nslices)
+        if graphed and rib_static["graph"] is not None:
+            rib_static["rows"].copy_(rows_all); rib_static["mm"].copy_(mm_all)
+            rib_static["graph"].replay()
+            sel = rib_static["sel"].clone()
+        else:
+            sel = rib_decide(rows_all, mm_all)
         with timer("C1_exchange"):
             sel = sharded.share_selected(sel)
         return sel
@@ -272,7 +289,6 @@ def run_b200(args):
             code, _, _ = ops.mask_decode(dets, n, protos, 0)
         with timer("K7_label_cleanup"):
             ops.label_cleanup(code, body)
-        launches["n"] += 11 + 1 + 1 + 1 + 18
         return code, n
 
     flat_dev = px_dev.view(S * nl, SIZE, SIZE)                     # the HBM-resident batch
@@ -300,6 +316,12 @@ def run_b200(args):
                 o = slice_stage(flat_dev[c0:c0 + args.chunk])
             graphs.append(g); outs.append(o)
 
+    if not args.no_graphs:                                          # the per-series decision as one more graph
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
+            rib_static["sel"] = rib_decide(rib_static["rows"], rib_static["mm"])
+        rib_static["graph"] = g
+
     def run_chunk(ci):
         if graphs:
             graphs[ci].replay()
@@ -307,10 +329,13 @@ def run_b200(args):
         return slice_stage(flat_dev[chunks[ci]:chunks[ci] + args.chunk])
 
     def step_device():
-        sel = rib_stage(px_dev)
+        sel = rib_stage(px_dev, graphed=True)
         for ci in range(len(chunks)):
             run_chunk(ci)
         return sel
+
+    rows_pin = torch.empty((S, nl, 1, SIZE), dtype=torch.int16).pin_memory()
+    rows_dev = torch.empty((S, nl, 1, SIZE), dtype=torch.int16, device=dev)
 
     def step_e2e():
         """Same pass from pinned host memory: H2D of the pixels, D2H of the label maps and indices."""
@@ -318,9 +343,16 @@ def run_b200(args):
         copy_in.wait_stream(main)
         evs = []
         with torch.cuda.stream(copy_in):
+            # the coronal scan needs one row per slice: ship those 1 KiB rows first, so the per-series
+            # decision runs while the first chunk of full slices is still on the wire
+            rows_pin.copy_(px_host[:, :, row:row + 1, :])
+            rows_dev.copy_(rows_pin, non_blocking=True)
+            ev_rows = torch.cuda.Event(); ev_rows.record(copy_in)
             for c0 in range(0, S * nl, args.chunk):
                 stage_buf[c0:c0 + args.chunk].copy_(flat_host[c0:c0 + args.chunk], non_blocking=True)
                 e = torch.cuda.Event(); e.record(copy_in); evs.append(e)
+        main.wait_event(ev_rows)
+        sel = rib_stage(rows_dev, graphed=True, src_row=0)
         for ci, c0 in enumerate(chunks):
             main.wait_event(evs[ci])
             code, n = run_chunk(ci)
@@ -329,7 +361,6 @@ def run_b200(args):
             with torch.cuda.stream(copy_out):
                 flat_labels_host[c0:c0 + args.chunk].copy_(code, non_blocking=True)
             code.record_stream(copy_out)
-        sel = rib_stage(stage_buf.view(S, nl, SIZE, SIZE))
         main.wait_stream(copy_out)
         return sel.cpu()                                          # result read on the host
 
@@ -383,7 +414,7 @@ def run_b200(args):
     if not args.no_e2e:
         ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
         e2e = {"value": total_slices / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(px_host.numel() * 2), "d2h_bytes_per_step": int(labels_host.numel() + S * 16)}
+               "h2d_bytes_per_step": int(px_host.numel() * 2 + rows_pin.numel() * 2), "d2h_bytes_per_step": int(labels_host.numel() + S * 16)}
 
     # ---------------------------------------------------------------- roofline of the dominant own kernel
     peaks = {}
