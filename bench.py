@@ -37,7 +37,7 @@ UNIT = "slices/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=160, help="slices per CNN batch / CUDA graph")
@@ -194,7 +194,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from eitsynthai_b200 import cabi, host, ops, sharded, synth
-    from eitsynthai_b200.pipeline import CONF, IOU, MAX_DET, ImagingPipeline, SeriesMeta
+    from eitsynthai_b200.pipeline import CONF, IOU, MAX_DET, ImagingPipeline, SeriesBatchRunner, SeriesMeta
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,152 +217,23 @@ def run_b200(args):
         vols.append(v); insts.append(i)
     px_host = torch.from_numpy(np.stack(vols)).pin_memory()        # [S, nl, H, W]
     labels_host = torch.empty((S, nl, SIZE, SIZE), dtype=torch.uint8).pin_memory()
-    px_dev = px_host.to(dev)
     metas = [SeriesMeta(insts[s]) for s in range(S)]
-    orders = [torch.from_numpy(host.instance_order(m.instance_numbers)).to(dev) for m in metas]
-    row, fx, fz = host.front_geometry(SIZE)
     timer = StageTimer(torch)
-    copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     launches = {"n": 0}
     profiling = {"on": False}
-
-    mine = [s for s in range(S) if sharded.owner_of_series(s, world) == rank]
-    mine_idx = torch.tensor(mine, dtype=torch.int64, device=dev)
-    rib_static = {"rows": torch.zeros((S, nslices, SIZE), dtype=torch.int16, device=dev),
-                  "mm": torch.zeros((S, 2), dtype=torch.int32, device=dev), "graph": None, "sel": None}
-
-    def rib_rows(px, src_row=None):
-        """K3: coronal rows + min/max of the local shard of every series.  ``px`` is [S,nl,H,W], or
-        [S,nl,1,W] when only the coronal row of every slice was shipped (``src_row`` = 0)."""
-        with timer("K3_front_rows"):
-            rows = torch.empty((S, nl, SIZE), dtype=torch.int16, device=dev)
-            mm = torch.empty((S, 2), dtype=torch.int32, device=dev)
-            mm[:, 0] = 2 ** 31 - 1; mm[:, 1] = -2 ** 31
-            for s in range(S):
-                r, _ = ops.front_rows(px[s], orders[s], nl, row if src_row is None else src_row, fx, fz, mm[s])
-                rows[s] = r
-        return rows, mm
-
-    def rib_decide(rows_all, mm_all):
-        """MINMAX normalise -> letterbox -> rib network -> NMS -> scale_boxes -> arg-select, for the owned series."""
-        sel = torch.zeros((S, 4), dtype=torch.int32, device=dev)
-        if mine:
-            with timer("K3_minmax_letterbox"):
-                front = torch.stack([ops.minmax_u8(rows_all[s], mm_all[s]) for s in mine])
-                x, (gain, pad_x, pad_y, w0, h0) = pipe._rib_input(front)
-            with timer("CNN_ribs"):
-                head, _ = pipe.ribs_model(x)
-                head = head.contiguous()
-            with timer("K5_nms_ribs"):
-                dets, _, k = ops.nms(head, 1, CONF, IOU, MAX_DET, want_idx=False)
-            with timer("K4_rib_select"):
-                boxes = ops.scale_boxes(dets, k, gain, pad_x, pad_y, w0, h0)
-                sel.index_copy_(0, mine_idx, ops.rib_select(boxes, k, 512.0))
-        return sel
-
-    def rib_stage(px, graphed=False, src_row=None):
-        """coronal rows of the local shard -> exchange -> rib model on the owned series -> indices."""
-        rows, mm = rib_rows(px, src_row)
-        with timer("C1_exchange"):
-            rows_all, mm_all = sharded.gather_rows(rows, mm, nslices)
-        if graphed and rib_static["graph"] is not None:
-            rib_static["rows"].copy_(rows_all); rib_static["mm"].copy_(mm_all)
-            rib_static["graph"].replay()
-            sel = rib_static["sel"].clone()
-        else:
-            sel = rib_decide(rows_all, mm_all)
-        with timer("C1_exchange"):
-            sel = sharded.share_selected(sel)
-        return sel
-
-    def slice_stage(px_chunk):
-        with timer("K2_body_mask"):
-            body = ops.body_mask(px_chunk, 1, -1024, True)
-        with timer("K1_hu_window_nchw"):
-            _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=torch.float16, channels_last=True)
-        with timer("CNN_axial"):
-            head, protos = pipe.axial_model_512(x)
-            head = head.contiguous()
-        with timer("K5_nms"):
-            dets, _, n = ops.nms(head, 4, CONF, IOU, MAX_DET, want_idx=False)
-        with timer("K6_mask_decode"):
-            code, _, _ = ops.mask_decode(dets, n, protos, 0)
-        with timer("K7_label_cleanup"):
-            ops.label_cleanup(code, body)
-        return code, n
-
-    flat_dev = px_dev.view(S * nl, SIZE, SIZE)                     # the HBM-resident batch
-    flat_host = px_host.view(S * nl, SIZE, SIZE)
-    flat_labels_host = labels_host.view(S * nl, SIZE, SIZE)
-    stage_buf = flat_dev                                          # e2e copies the host pixels over it, chunk by chunk
-    chunks = list(range(0, S * nl, args.chunk))
-
-    def step_eager():
-        sel = rib_stage(px_dev)
-        for c0 in chunks:
-            slice_stage(flat_dev[c0:c0 + args.chunk])
-        return sel
-
-    # ---- CUDA graphs: one per chunk of the per-slice path (fixed addresses inside the resident batch)
-    for _ in range(2):                                            # cuDNN autotune + lazy module loading, eagerly
-        step_eager()
-    torch.cuda.synchronize(dev)
-    graphs, outs = [], []
-    if not args.no_graphs:
-        pool = torch.cuda.graph_pool_handle()
-        for c0 in chunks:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                o = slice_stage(flat_dev[c0:c0 + args.chunk])
-            graphs.append(g); outs.append(o)
-
-    if not args.no_graphs:                                          # the per-series decision as one more graph
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=pool):
-            rib_static["sel"] = rib_decide(rib_static["rows"], rib_static["mm"])
-        rib_static["graph"] = g
-
-    def run_chunk(ci):
-        if graphs:
-            graphs[ci].replay()
-            return outs[ci]
-        return slice_stage(flat_dev[chunks[ci]:chunks[ci] + args.chunk])
-
-    def step_device():
-        sel = rib_stage(px_dev, graphed=True)
-        for ci in range(len(chunks)):
-            run_chunk(ci)
-        return sel
-
-    rows_pin = torch.empty((S, nl, 1, SIZE), dtype=torch.int16).pin_memory()
-    rows_dev = torch.empty((S, nl, 1, SIZE), dtype=torch.int16, device=dev)
+    # the public throughput engine of the package; bench.py only times it
+    runner = SeriesBatchRunner(pipe, metas, nslices, SIZE, args.chunk, use_graphs=not args.no_graphs, timer=timer)
+    runner.load(px_host)
+    runner.capture()
+    graphs, outs = runner.graphs, runner.outs
+    step_eager, step_device = runner.step_eager, runner.step_device
 
     def step_e2e():
-        """Same pass from pinned host memory: H2D of the pixels, D2H of the label maps and indices."""
-        main = torch.cuda.current_stream(dev)
-        copy_in.wait_stream(main)
-        evs = []
-        with torch.cuda.stream(copy_in):
-            # the coronal scan needs one row per slice: ship those 1 KiB rows first, so the per-series
-            # decision runs while the first chunk of full slices is still on the wire
-            rows_pin.copy_(px_host[:, :, row:row + 1, :])
-            rows_dev.copy_(rows_pin, non_blocking=True)
-            ev_rows = torch.cuda.Event(); ev_rows.record(copy_in)
-            for c0 in range(0, S * nl, args.chunk):
-                stage_buf[c0:c0 + args.chunk].copy_(flat_host[c0:c0 + args.chunk], non_blocking=True)
-                e = torch.cuda.Event(); e.record(copy_in); evs.append(e)
-        main.wait_event(ev_rows)
-        sel = rib_stage(rows_dev, graphed=True, src_row=0)
-        for ci, c0 in enumerate(chunks):
-            main.wait_event(evs[ci])
-            code, n = run_chunk(ci)
-            e = torch.cuda.Event(); e.record(main)
-            copy_out.wait_event(e)
-            with torch.cuda.stream(copy_out):
-                flat_labels_host[c0:c0 + args.chunk].copy_(code, non_blocking=True)
-            code.record_stream(copy_out)
-        main.wait_stream(copy_out)
-        return sel.cpu()                                          # result read on the host
+        """Same pass through the public API from pinned host memory: H2D of the pixels, D2H of the label
+        maps and of the selected indices inside the step."""
+        return runner.step_host(px_host, labels_host)
+
+    rows_pin = runner.rows_pin
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -488,7 +359,7 @@ def run_b200(args):
                 "config": dict(config(world), chunk=args.chunk, class_bias_shift=pipe.bias_shift,
                                mean_detections_per_slice=ndet_mean, cuda_graphs=bool(graphs)),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roof, "cpu_baseline": cpu,
-                "eager_ms_per_step": ms_eager,
+                "eager_profiled_ms_per_step": ms_eager,
                 "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stages.items())},
                 "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1][1])},
                 "kernel_gbs": {k: round(per_slice_bytes[k] * min(args.chunk, S * nl) * v[0] / (v[1] / 1e3) / 1e9, 1)

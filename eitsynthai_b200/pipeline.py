@@ -201,3 +201,198 @@ class ImagingPipeline:
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         return ops.tri_label(t(np.asarray(nodes_xy, np.float64)), t(np.asarray(triangles, np.int64)), t(xy), t(off),
                              t(cls), outer_class)
+
+
+class _NullTimer:
+    def __call__(self, name):
+        return self
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class SeriesBatchRunner:
+    """Throughput engine for a batch of series, slice-sharded over the ranks of ``torch.distributed``
+    (SURVEY §8(e)): this rank owns a contiguous z-range of every series.
+
+    * ``step_device()``  -- one pass with the pixels already in HBM;
+    * ``step_host(px_host, labels_host)`` -- the same pass from pinned host memory: the 1 KiB coronal
+      rows travel first (the per-series decision runs while the first chunk of slices is on the
+      wire), slices go host->device and label maps device->host chunk by chunk on two copy streams.
+
+    The per-slice path of every chunk (K2, K1, CNN, K5, K6, K7; ~1,000 launches) and the per-series
+    decision (K3 normalise, letterbox, rib CNN, K5, K4) are captured once as CUDA graphs over fixed
+    buffers and replayed; the NCCL exchange between them stays eager.
+    """
+
+    def __init__(self, pipe: ImagingPipeline, metas, n_slices: int, size: int = 512, chunk: int = 160,
+                 use_graphs: bool = True, timer=None):
+        from . import sharded
+        self.pipe, self.sharded = pipe, sharded
+        self.dev = pipe.device
+        self.rank, self.world = sharded.world()
+        self.S, self.n_slices, self.size, self.chunk = len(metas), n_slices, size, chunk
+        z0, z1 = sharded.shard_range(n_slices, self.world, self.rank)
+        self.nl = z1 - z0
+        self.metas = metas
+        dev = self.dev
+        self.orders = [torch.from_numpy(host.instance_order(m.instance_numbers)).to(dev) for m in metas]
+        m0 = metas[0]
+        self.row, self.fx, self.fz = host.front_geometry(size, m0.patient_position, m0.image_orientation, m0.patient_orientation)
+        self.timer = timer or _NullTimer()
+        self.px = torch.empty((self.S, self.nl, size, size), dtype=torch.int16, device=dev)      # the resident batch
+        self.flat = self.px.view(self.S * self.nl, size, size)
+        self.chunks = list(range(0, self.S * self.nl, chunk))
+        self.mine = [s for s in range(self.S) if sharded.owner_of_series(s, self.world) == self.rank]
+        self.mine_idx = torch.tensor(self.mine, dtype=torch.int64, device=dev)
+        self.rows_static = torch.zeros((self.S, n_slices, size), dtype=torch.int16, device=dev)
+        self.mm_static = torch.zeros((self.S, 2), dtype=torch.int32, device=dev)
+        self.rows_pin = torch.empty((self.S, self.nl, 1, size), dtype=torch.int16).pin_memory()
+        self.rows_dev = torch.empty((self.S, self.nl, 1, size), dtype=torch.int16, device=dev)
+        self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.graphs, self.outs, self.rib_graph, self.sel_static = [], [], None, None
+        self.use_graphs = use_graphs
+
+    # ---------------------------------------------------------------- stages
+    @torch.no_grad()
+    def slice_stage(self, px_chunk):
+        t, pipe = self.timer, self.pipe
+        m = self.metas[0]
+        with t("K2_body_mask"):
+            body = ops.body_mask(px_chunk, m.rescale_slope, m.rescale_intercept, True)
+        with t("K1_hu_window_nchw"):
+            _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=pipe.dtype, channels_last=True)
+        with t("CNN_axial"):
+            head, protos = (pipe.axial_model_256 if self.size == 256 else pipe.axial_model_512)(x)
+            head = head.contiguous()
+        with t("K5_nms"):
+            dets, _, n = ops.nms(head, 4, CONF, IOU, MAX_DET, want_idx=False)
+        with t("K6_mask_decode"):
+            code, _, _ = ops.mask_decode(dets, n, protos, pipe.mask_variant)
+        with t("K7_label_cleanup"):
+            ops.label_cleanup(code, body)
+        return code, n
+
+    def rib_rows(self, px, src_row=None):
+        with self.timer("K3_front_rows"):
+            rows = torch.empty((self.S, self.nl, self.size), dtype=torch.int16, device=self.dev)
+            mm = torch.empty((self.S, 2), dtype=torch.int32, device=self.dev)
+            mm[:, 0] = 2 ** 31 - 1
+            mm[:, 1] = -2 ** 31
+            for s in range(self.S):
+                r, _ = ops.front_rows(px[s], self.orders[s], self.nl, self.row if src_row is None else src_row,
+                                      self.fx, self.fz, mm[s])
+                rows[s] = r
+        return rows, mm
+
+    @torch.no_grad()
+    def rib_decide(self, rows_all, mm_all):
+        t, pipe = self.timer, self.pipe
+        sel = torch.zeros((self.S, 4), dtype=torch.int32, device=self.dev)
+        if self.mine:
+            with t("K3_minmax_letterbox"):
+                front = torch.stack([ops.minmax_u8(rows_all[s], mm_all[s]) for s in self.mine])
+                x, (gain, pad_x, pad_y, w0, h0) = pipe._rib_input(front)
+            with t("CNN_ribs"):
+                head, _ = pipe.ribs_model(x)
+                head = head.contiguous()
+            with t("K5_nms_ribs"):
+                dets, _, k = ops.nms(head, 1, CONF, IOU, MAX_DET, want_idx=False)
+            with t("K4_rib_select"):
+                boxes = ops.scale_boxes(dets, k, gain, pad_x, pad_y, w0, h0)
+                sel.index_copy_(0, self.mine_idx, ops.rib_select(boxes, k, 512.0))
+        return sel
+
+    def rib_stage(self, px, graphed=False, src_row=None):
+        rows, mm = self.rib_rows(px, src_row)
+        with self.timer("C1_exchange"):
+            rows_all, mm_all = self.sharded.gather_rows(rows, mm, self.n_slices)
+        if graphed and self.rib_graph is not None:
+            self.rows_static.copy_(rows_all)
+            self.mm_static.copy_(mm_all)
+            self.rib_graph.replay()
+            sel = self.sel_static.clone()
+        else:
+            sel = self.rib_decide(rows_all, mm_all)
+        with self.timer("C1_exchange"):
+            sel = self.sharded.share_selected(sel)
+        return sel
+
+    # ---------------------------------------------------------------- steps
+    def load(self, px_host: torch.Tensor):
+        """Place a batch [S, n_local, H, W] in the resident buffer (outside any timed region)."""
+        self.px.copy_(px_host)
+        torch.cuda.synchronize(self.dev)
+
+    def step_eager(self):
+        sel = self.rib_stage(self.px)
+        for c0 in self.chunks:
+            self.slice_stage(self.flat[c0:c0 + self.chunk])
+        return sel
+
+    def capture(self, warm: int = 2):
+        """cuDNN autotune / lazy loading eagerly, then one CUDA graph per chunk and one for the rib decision."""
+        for _ in range(warm):
+            self.step_eager()
+        torch.cuda.synchronize(self.dev)
+        if not self.use_graphs:
+            return
+        pool = torch.cuda.graph_pool_handle()
+        for c0 in self.chunks:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                o = self.slice_stage(self.flat[c0:c0 + self.chunk])
+            self.graphs.append(g)
+            self.outs.append(o)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
+            self.sel_static = self.rib_decide(self.rows_static, self.mm_static)
+        self.rib_graph = g
+
+    def run_chunk(self, ci):
+        if self.graphs:
+            self.graphs[ci].replay()
+            return self.outs[ci]
+        c0 = self.chunks[ci]
+        return self.slice_stage(self.flat[c0:c0 + self.chunk])
+
+    def step_device(self):
+        sel = self.rib_stage(self.px, graphed=True)
+        for ci in range(len(self.chunks)):
+            self.run_chunk(ci)
+        return sel
+
+    def step_host(self, px_host: torch.Tensor, labels_host: torch.Tensor):
+        """px_host [S, n_local, H, W] int16 pinned, labels_host [S, n_local, H, W] u8 pinned (file order).
+        Returns the selected-slice table [S, 4] on the host (the one synchronisation of the step)."""
+        main = torch.cuda.current_stream(self.dev)
+        flat_host = px_host.view(self.S * self.nl, self.size, self.size)
+        flat_out = labels_host.view(self.S * self.nl, self.size, self.size)
+        self.copy_in.wait_stream(main)
+        evs = []
+        with torch.cuda.stream(self.copy_in):
+            self.rows_pin.copy_(px_host[:, :, self.row:self.row + 1, :])
+            self.rows_dev.copy_(self.rows_pin, non_blocking=True)
+            ev_rows = torch.cuda.Event()
+            ev_rows.record(self.copy_in)
+            for c0 in self.chunks:
+                self.flat[c0:c0 + self.chunk].copy_(flat_host[c0:c0 + self.chunk], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self.copy_in)
+                evs.append(e)
+        main.wait_event(ev_rows)
+        sel = self.rib_stage(self.rows_dev, graphed=True, src_row=0)
+        for ci, c0 in enumerate(self.chunks):
+            main.wait_event(evs[ci])
+            code, _ = self.run_chunk(ci)
+            e = torch.cuda.Event()
+            e.record(main)
+            self.copy_out.wait_event(e)
+            with torch.cuda.stream(self.copy_out):
+                flat_out[c0:c0 + self.chunk].copy_(code, non_blocking=True)
+            code.record_stream(self.copy_out)
+        main.wait_stream(self.copy_out)
+        return sel.cpu()

@@ -176,3 +176,26 @@ def test_conv_epilogue_and_upsample_concat_kernels():
     b = torch.randn(2, 24, 10, 14, device="cuda").half().contiguous(memory_format=cl)
     got = ops.upsample2x_concat(a, b)
     assert torch.equal(got, torch.cat((torch.nn.functional.interpolate(a, scale_factor=2.0, mode="nearest"), b), 1))
+
+
+def test_series_batch_runner_graphs_match_eager(pipe):
+    """Public throughput engine: CUDA-graph replay and the host path give the same label maps as the
+    plain per-chunk calls, and the same coronal decision as ImagingPipeline.rib_select."""
+    from eitsynthai_b200.pipeline import SeriesBatchRunner, SeriesMeta
+    vol, inst = synth.phantom_series(48, seed=21)
+    px_host = torch.from_numpy(vol[None]).pin_memory()
+    out_host = torch.zeros((1, 48, 512, 512), dtype=torch.uint8).pin_memory()
+    r = SeriesBatchRunner(pipe, [SeriesMeta(inst)], 48, 512, chunk=32)
+    r.load(px_host)
+    r.capture(warm=1)
+    sel_dev = r.step_device().cpu()
+    want, _, _ = pipe.segment(torch.from_numpy(vol).cuda())
+    got = torch.cat([o[0] for o in r.outs])
+    assert torch.equal(got, want)
+    sel_host = r.step_host(px_host, out_host)
+    torch.cuda.synchronize()
+    assert torch.equal(sel_host, sel_dev)
+    assert np.array_equal(out_host[0].numpy(), want.cpu().numpy())
+    front = pipe.coronal(torch.from_numpy(vol).cuda(), SeriesMeta(inst))
+    sel_ref, _, _ = pipe.rib_select(front[None])
+    assert torch.equal(sel_ref.cpu(), sel_dev)
