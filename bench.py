@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--slices", type=int, default=N_SLICES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mesh", action="store_true", help="skip the configs[4] mesh element classification measurement")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
@@ -347,6 +348,41 @@ def run_b200(args):
                 "algorithmic_bytes_per_slice": per_slice_bytes[top],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                 "how": "CUDA events around every launch of the kernel (libeitb200 launch profiler) over an eager pass of the same steps"}
+    # ---------------------------------------------------------------- configs[4]: mesh element classification (K8)
+    mesh = None
+    if rank == 0 and not args.no_mesh:
+        from eitsynthai_b200.kt_service.ai_tools import utils as kt_utils
+        hd, pr = synth.teacher_heads(seed=0)
+        dets_m, _, n_m = ops.nms(torch.from_numpy(hd[None]).to(dev), 4, want_idx=False)
+        code_m, _, _ = ops.mask_decode(dets_m, n_m, torch.from_numpy(pr[None]).to(dev))
+        body_m = ops.body_mask(torch.from_numpy(synth.phantom_slice(0)[None]).to(dev), 1, -1024, True)
+        ops.label_cleanup(code_m, body_m)
+        polys = kt_utils.codes_to_polygons(code_m[0].cpu().numpy(), [0.753906, 0.753906], body_m[0].cpu().numpy())[2:]
+        xy, off, pcls = host.prepare_polygons(host.parse_contours(polys, host.find_outer_index(polys)))
+        nodes, tris = synth.delaunay_mesh((20, 40, 490, 470), 1.43, seed=0)
+        dm = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (nodes, tris, xy, off, pcls)]
+        for _ in range(3):
+            cls_gpu = ops.tri_label(*dm)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            cls_gpu = ops.tri_label(*dm)
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms_mesh = a.elapsed_time(b) / 10
+        mesh = {"triangles": int(len(tris)), "polygons": int(len(pcls)), "polygon_vertices": int(len(xy)),
+                "ms": ms_mesh, "elements_per_sec": len(tris) / (ms_mesh / 1e3),
+                "class_histogram": torch.bincount(cls_gpu, minlength=5).tolist()}
+        if not args.no_cpu_baseline:
+            from oracle import tri_label as TL                      # CPU baseline leg: the C restatement, one core
+            nb = min(20000, len(tris))
+            t0 = time.perf_counter()
+            ref = TL.label_triangles(nodes, tris[:nb], xy, off, pcls)
+            dt = time.perf_counter() - t0
+            mesh["cpu_elements_per_sec"] = nb / dt
+            mesh["cpu_sample"] = f"first {nb} triangles, oracle/tri_label.c, 1 core"
+            mesh["labels_match_cpu"] = bool(np.array_equal(ref, cls_gpu[:nb].cpu().numpy()))
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -364,7 +400,7 @@ def run_b200(args):
                 "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1][1])},
                 "kernel_gbs": {k: round(per_slice_bytes[k] * min(args.chunk, S * nl) * v[0] / (v[1] / 1e3) / 1e9, 1)
                                for k, v in kernels.items() if k in per_slice_bytes and v[1] > 0 and k != "bias_act_kernel"},
-                "selected_slices": sel.cpu().tolist()}
+                "selected_slices": sel.cpu().tolist(), "mesh_labelling": mesh}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
