@@ -67,21 +67,32 @@ class DICOMabc(abc.ABC):
             return list(zip_buffer), 0
         if isinstance(zip_buffer, dict):
             return list(zip_buffer["slices"]), int(zip_buffer.get("custom_number_slise", 0))
-        import pydicom                                             # not installed here: explicit seam
-        from pydicom.filebase import DicomBytesIO
-        series, custom = {}, 0
+        from . import dicom_io
+        if isinstance(zip_buffer, (bytes, bytearray)):
+            import io
+            zip_buffer = io.BytesIO(zip_buffer)
         with zipfile.ZipFile(zip_buffer, "r") as zf:
-            for name in zf.namelist():
-                if name.endswith(".txt"):
-                    if name.endswith("custom_input.txt"):
-                        custom = int(zf.read(name).decode().strip() or 0)
-                    continue
-                ds = pydicom.dcmread(DicomBytesIO(zf.read(name)))
-                series.setdefault(ds.SeriesInstanceUID, []).append(ds)
-        return max(series.values(), key=len), custom
+            try:                                                   # uncompressed little-endian files: built-in reader
+                return dicom_io.create_dicom_dict(zf)
+            except dicom_io.UnsupportedTransferSyntax:
+                import pydicom                                     # compressed syntaxes need pydicom (+ pylibjpeg)
+                from pydicom.filebase import DicomBytesIO
+                series, custom = {}, 0
+                for name in zf.namelist():
+                    if name.endswith(".txt"):
+                        if name.endswith("custom_input.txt"):
+                            custom = int(zf.read(name).decode().strip() or 0)
+                        continue
+                    ds = pydicom.dcmread(DicomBytesIO(zf.read(name)))
+                    series.setdefault(ds.SeriesInstanceUID, []).append(ds)
+                return max(series.values(), key=len), custom
 
     def _series_arrays(self, i_slices):
-        px = np.stack([np.asarray(s.pixel_array, np.int16) for s in i_slices])
+        from . import dicom_io
+        if i_slices and isinstance(i_slices[0], dicom_io.Dataset):
+            px = dicom_io.series_to_pinned(i_slices)[0].numpy()   # one copy, file buffer -> pinned memory
+        else:
+            px = np.stack([np.asarray(s.pixel_array, np.int16) for s in i_slices])
         s0 = i_slices[0]
         meta = SeriesMeta(np.asarray([int(s.InstanceNumber) for s in i_slices]),
                           _tag(s0, (0x0018, 0x5100), "HFS"), _tag(s0, (0x0020, 0x0037), (1, 0, 0, 0, 1, 0)),
@@ -135,7 +146,7 @@ class DICOMabc(abc.ABC):
         (labels code image (S,S) u8, body mask or None, n_detections, segmentation_time)."""
         t1 = time.time()
         if ds is not None:
-            px = torch.from_numpy(np.ascontiguousarray(ds.pixel_array, np.int16)[None]).to(self.device)
+            px = torch.from_numpy(np.array(ds.pixel_array, np.int16)[None]).to(self.device)
             code, body, n = self.pipeline.segment(px, int(_tag(ds, (0x0028, 0x1053), 1)), int(_tag(ds, (0x0028, 0x1052), -1024)))
             body = body[0].cpu().numpy()
         else:

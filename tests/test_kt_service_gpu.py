@@ -199,3 +199,20 @@ def test_series_batch_runner_graphs_match_eager(pipe):
     front = pipe.coronal(torch.from_numpy(vol).cuda(), SeriesMeta(inst))
     sel_ref, _, _ = pipe.rib_select(front[None])
     assert torch.equal(sel_ref.cpu(), sel_dev)
+
+
+def test_zip_of_dicom_files_end_to_end(pipe):
+    """Real wire format: a zip of (uncompressed) DICOM files through the reference-named entry points."""
+    from eitsynthai_b200.kt_service.ai_tools import ai_tools as A
+    from eitsynthai_b200.kt_service.ai_tools import dicom_io as D
+    vol, inst = synth.phantom_series(40, seed=4)
+    z = D.zip_series(vol, inst, custom=1)
+    frame = A.DICOMToMask().get_coordinate_slice_from_dicom_frame(z)
+    assert frame["status"] == "success"
+    code, _, _ = pipe.segment(torch.from_numpy(vol[-1:].copy()).cuda())       # the last dataset of the archive
+    assert np.array_equal(frame["label_codes"], code[0].cpu().numpy())
+    obj = A.DICOMSequencesToMaskCustom()
+    front, px, i_slices, custom = obj._search_front_slise(D.zip_series(vol, inst, custom=1))
+    assert custom == 1 and np.array_equal(px, vol)
+    assert [int(s.InstanceNumber) for s in i_slices] == sorted(int(i) for i in inst)
+    assert np.array_equal(front, O.front_slice_norm(vol[np.argsort(inst, kind="stable")]))
