@@ -25,7 +25,6 @@ constexpr int MROW = 128;                    // MMA M: instances per pass
 constexpr int KDIM = 64;                     // 32 coefficients, hi | lo
 constexpr int LSTRIDE = 253;                 // odd row stride of the parked logits: conflict-free
 constexpr int kThreads = 256;
-constexpr int kMaxDet = 1024;
 
 constexpr int OFF_B = 0;                                   // 256 x 128 B
 constexpr int OFF_A = OFF_B + NCOL * 128;                  // 128 x 128 B

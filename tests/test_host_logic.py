@@ -1,0 +1,62 @@
+"""Host-side rules of the product (eitsynthai_b200/host.py) against the oracle's statements, CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from eitsynthai_b200 import host
+from oracle import imaging as O
+from oracle import tri_label as TL
+from oracle import yolo_post as Y
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("h,w,imgsz", [(320, 512, 640), (512, 512, 512), (256, 256, 256), (40, 512, 640), (301, 512, 640),
+                                       (700, 512, 640), (512, 300, 640)])
+def test_letterbox_and_scale_boxes_geometry(h, w, imgsz):
+    assert host.letterbox_geometry(h, w, imgsz) == Y.letterbox_geometry(h, w, imgsz)
+    nh, nw, top, bottom, left, right = host.letterbox_geometry(h, w, imgsz)
+    gain, px, py = host.scale_boxes_params((nh + top + bottom, nw + left + right), (h, w))
+    import torch
+    b = torch.tensor([[10.0, 20.0, 200.0, 300.0]])
+    want = Y.scale_boxes((nh + top + bottom, nw + left + right), b, (h, w))
+    got = ((b - torch.tensor([px, py, px, py])) / gain)
+    got[:, [0, 2]] = got[:, [0, 2]].clamp(0, w)
+    got[:, [1, 3]] = got[:, [1, 3]].clamp(0, h)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("pp,iop,po", [("HFS", [1, 0, 0, 0, 1, 0], None), ("FFS", [1, 0, 0, 0, 1, 0], None),
+                                       ("FFS", [-1, 0, 0, 0, -1, 0], ["L", "P"]), ("HFP", [1, 0, 0, 0, -1, 0], ["L", "A"]),
+                                       ("HFS", [-1, 0, 0, 0, 1, 0], ["L", "P"])])
+def test_front_geometry_equals_oracle_rows(pp, iop, po):
+    rng = np.random.default_rng(0)
+    vol = rng.integers(-1000, 1000, (9, 16, 24)).astype(np.int16)
+    row, fx, fz = host.front_geometry(16, pp, iop, po)
+    rows = vol[:, row, :]
+    rows = rows[:, ::-1] if fx else rows
+    rows = rows[::-1] if fz else rows
+    assert np.array_equal(rows, O.front_rows(vol, pp, iop, po))
+
+
+def test_instance_order_is_stable():
+    inst = np.array([3, 1, 2, 1, 3, 2])
+    assert host.instance_order(inst).tolist() == [1, 3, 2, 5, 0, 4]
+
+
+def test_polygon_preparation_matches_oracle():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_polygons.json")) as f:
+        polys = json.load(f)
+    for tag, lst in polys.items():
+        strs = lst[2:]
+        outer = host.find_outer_index(strs)
+        assert outer == next((i for i, s in enumerate(strs) if isinstance(s, str) and s[:1] == "4"), None)
+        a = host.prepare_polygons(host.parse_contours(strs, outer))
+        b = TL.prepare_polygons(TL.parse_contours(strs, outer))
+        for x, y in zip(a, b[:3]):
+            assert np.array_equal(x, y), tag
+    xy, off, cls = host.prepare_polygons([[1, 0, 0, 1, 1], [2.0, 0, 0, 4, 0, 4, 4, 0, 4]])     # first is too short
+    assert off.tolist() == [0, 5] and cls.tolist() == [2] and np.array_equal(xy[0], xy[-1])
+    assert host.prepare_polygons([])[1].tolist() == [0]
