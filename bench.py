@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=160, help="slices per CNN batch / CUDA graph")
     ap.add_argument("--slices", type=int, default=N_SLICES)
+    ap.add_argument("--series", type=int, default=0, help="series per step (default: one per GPU = weak scaling; "
+                    "64 with --gpus 8 is BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mesh", action="store_true", help="skip the configs[4] mesh element classification measurement")
@@ -49,10 +51,11 @@ def parse():
     return ap.parse_args()
 
 
-def config(world):
+def config(world, series=0):
     return {"workload": "configs[2]: synthetic 320-slice 512x512 int16 series, dicom_sequences_auto "
-                        "(rib-slice selection + every slice segmented and labelled)",
-            "series_per_step": world, "slices_per_series": N_SLICES, "slice": [SIZE, SIZE],
+                        "(rib-slice selection + every slice segmented and labelled)" if not series or series == world else
+                        f"configs[3]: batch of {series} synthetic 320-slice series sharded by slice across {world} GPUs",
+            "series_per_step": series or world, "slices_per_series": N_SLICES, "slice": [SIZE, SIZE],
             "sharding": "z-range per GPU, all-gather of coronal rows" if world > 1 else "single GPU",
             "l2": "inputs (168 MB/GPU) larger than L2, no flush", "weights": "random-init YOLO11s-seg x3, class bias shifted"}
 
@@ -207,14 +210,18 @@ def run_b200(args):
     torch.backends.cudnn.benchmark = True
 
     pipe = ImagingPipeline(dev, torch.float16, seed=0)
-    S = world                                                     # series per step (weak scaling)
+    S = args.series or world                                      # series per step (default: weak scaling, one per GPU)
     nslices = args.slices
     z0, z1 = sharded.shard_range(nslices, world, rank)
     nl = z1 - z0
     # this rank's shard of every series, file order shuffled inside the shard
     vols, insts = [], []
+    distinct = min(S, max(world, 2))                              # more series than that reuse the generated pixels
     for s in range(S):
-        v, i = synth.phantom_series(nslices, seed=s, shuffle_seed=17 + s, z_range=(z0, z1))
+        if s < distinct:
+            v, i = synth.phantom_series(nslices, seed=s, shuffle_seed=17 + s, z_range=(z0, z1))
+        else:
+            v, i = vols[s % distinct], insts[s % distinct]
         vols.append(v); insts.append(i)
     px_host = torch.from_numpy(np.stack(vols)).pin_memory()        # [S, nl, H, W]
     labels_host = torch.empty((S, nl, SIZE, SIZE), dtype=torch.uint8).pin_memory()
@@ -390,7 +397,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 (CNN) / int16,u8,f32 (kernels)", "data": "synthetic",
-                "config": dict(config(world), chunk=args.chunk, class_bias_shift=pipe.bias_shift,
+                "config": dict(config(world, S), chunk=args.chunk, class_bias_shift=pipe.bias_shift,
                                mean_detections_per_slice=ndet_mean, cuda_graphs=bool(graphs)),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roof, "cpu_baseline": cpu,
                 "eager_profiled_ms_per_step": ms_eager,

@@ -488,3 +488,31 @@ def test_label_cleanup_full_size_pipeline(ops):
         body = O.body_mask(synth.phantom_slice(seed, -1024), -1024, 1)
         got = ops.label_cleanup(dev(code[None].copy()), dev(body[None]))[0].cpu().numpy()
         assert np.array_equal(got, O.create_color_codes(O.class_union_masks(masks, cls, 512), body))
+
+
+def _real_set(k):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(root, "tests", "golden", "reference_polygon_sets.npz"))
+    xy, off, cls = z[f"set{k}_xy"], z[f"set{k}_off"], z[f"set{k}_cls"]
+    return [[float(cls[p])] + xy[off[p]:off[p + 1]].reshape(-1).tolist() for p in range(len(cls))]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+def test_tri_label_reference_real_polygon_sets(ops, k):
+    """The six real-data polygon lists of the reference's mesh_service_trials.py (inputs only): rings
+    that touch / retrace themselves, mm units and a class-4 body contour in set 6."""
+    from eitsynthai_b200 import host
+    from oracle import tri_label as TL
+    contours = _real_set(k)
+    outer = next((i for i, c in enumerate(contours) if int(c[0]) == 4), None)
+    inner = [c for i, c in enumerate(contours) if i != outer]
+    xy, off, cls, _ = TL.prepare_polygons([list(c) for c in inner])
+    hx, hoff, hcls = host.prepare_polygons([list(c) for c in inner])
+    assert np.array_equal(hx, xy) and np.array_equal(hoff, off) and np.array_equal(hcls, cls)
+    lo, hi = xy.min(0), xy.max(0)
+    pitch = float(max(hi - lo)) / 220.0
+    nodes, tri = synth.delaunay_mesh((lo[0] - 2 * pitch, lo[1] - 2 * pitch, hi[0] + 2 * pitch, hi[1] + 2 * pitch), pitch, seed=k)
+    want = TL.label_triangles(nodes, tri, xy, off, cls)
+    got = ops.tri_label(dev(nodes), dev(tri), dev(xy), dev(off), dev(cls)).cpu().numpy()
+    assert np.array_equal(got, want), (k, int((got != want).sum()), len(tri))
+    assert len(np.unique(want)) >= 3

@@ -60,3 +60,14 @@ def test_polygon_preparation_matches_oracle():
     xy, off, cls = host.prepare_polygons([[1, 0, 0, 1, 1], [2.0, 0, 0, 4, 0, 4, 4, 0, 4]])     # first is too short
     assert off.tolist() == [0, 5] and cls.tolist() == [2] and np.array_equal(xy[0], xy[-1])
     assert host.prepare_polygons([])[1].tolist() == [0]
+
+
+def test_tri_label_oracle_c_vs_python_on_a_real_polygon_set():
+    """The C restatement of process_triangle against the independent pure-Python one, on real polygons."""
+    from eitsynthai_b200 import synth
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_polygon_sets.npz"))
+    xy, off, cls = z["set1_xy"], z["set1_off"], z["set1_cls"]
+    contours = [[float(cls[p])] + xy[off[p]:off[p + 1]].reshape(-1).tolist() for p in range(len(cls))]
+    pxy, poff, pcls, _ = TL.prepare_polygons(contours)
+    nodes, tri = synth.delaunay_mesh((40, 60, 470, 440), 22.0, seed=2)
+    assert np.array_equal(TL.label_triangles(nodes, tri, pxy, poff, pcls), TL.label_triangles_py(nodes, tri, pxy, poff, pcls))
