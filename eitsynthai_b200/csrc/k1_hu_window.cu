@@ -115,8 +115,9 @@ hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int 
                    uint16_t* __restrict__ out_all, int bf16) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int d = hi - lo;
-    uint16_t* lutT = reinterpret_cast<uint16_t*>(smem);
-    uint8_t* lut8 = smem + (size_t)(d + 1) * 2;
+    int4* stage = reinterpret_cast<int4*>(smem);                  // [8 warps][96] store staging (NHWC)
+    uint16_t* lutT = reinterpret_cast<uint16_t*>(smem + (kThreads / 32) * 96 * sizeof(int4));
+    uint8_t* lut8 = reinterpret_cast<uint8_t*>(lutT) + (size_t)(d + 1) * 2;
     for (int v = threadIdx.x; v <= d; v += kThreads) {
         const int u = (v * 255) / d;
         lutT[v] = unit16_bits(u, bf16);
@@ -128,8 +129,25 @@ hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int 
     const int16_t* px = px_all + b * hw;
     const uint8_t* mask = mask_all ? mask_all + b * hw : nullptr;
     const unsigned lo2 = ((unsigned)lo & 0xffffu) | ((unsigned)lo << 16), hi2 = ((unsigned)hi & 0xffffu) | ((unsigned)hi << 16);
-    for (int o = blockIdx.x * kThreads + threadIdx.x; o < units_per_slice; o += gridDim.x * kThreads) {
-        const int4 raw = ld_stream_int4(reinterpret_cast<const int4*>(px + (rot180 ? hw - 8 - o * 8 : o * 8)));
+    // two 8-pixel units per trip: both loads (and both mask loads) are issued before any arithmetic
+    const int step = gridDim.x * kThreads;
+    for (int o0 = blockIdx.x * kThreads + threadIdx.x; o0 < units_per_slice; o0 += 2 * step) {
+        int4 raws[2];
+        uint2 mks[2];
+        const int nu = o0 + step < units_per_slice ? 2 : 1;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u < nu) {
+                const int o = o0 + u * step;
+                raws[u] = ld_stream_int4(reinterpret_cast<const int4*>(px + (rot180 ? hw - 8 - o * 8 : o * 8)));
+                if (mask) mks[u] = ld_stream_uint2(reinterpret_cast<const uint2*>(mask + o * 8));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u >= nu) break;
+            const int o = o0 + u * step;
+            const int4 raw = raws[u];
         unsigned w[4];
         if (rot180) {
             w[0] = __byte_perm(raw.w, 0, 0x1032); w[1] = __byte_perm(raw.z, 0, 0x1032);
@@ -138,10 +156,7 @@ hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int 
             w[0] = raw.x; w[1] = raw.y; w[2] = raw.z; w[3] = raw.w;
         }
         uint2 mb = make_uint2(0xffffffffu, 0xffffffffu);
-        if (mask) {
-            const uint2 mk = ld_stream_uint2(reinterpret_cast<const uint2*>(mask + o * 8));
-            mb.x = __vcmpne4(mk.x, 0u); mb.y = __vcmpne4(mk.y, 0u);
-        }
+        if (mask) { mb.x = __vcmpne4(mks[u].x, 0u); mb.y = __vcmpne4(mks[u].y, 0u); }
         unsigned v[4], u8lo = 0, u8hi = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -164,10 +179,26 @@ hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int 
                 for (int k = 0; k < 4; ++k) {
                     t[3 * k] = __byte_perm(v[k], 0, 0x1010); t[3 * k + 1] = v[k]; t[3 * k + 2] = __byte_perm(v[k], 0, 0x3232);
                 }
-                int4* dst = reinterpret_cast<int4*>(out_all + (b * hw + (long long)o * 8) * 3);
-                st_stream_int4(dst, make_int4(t[0], t[1], t[2], t[3]));
-                st_stream_int4(dst + 1, make_int4(t[4], t[5], t[6], t[7]));
-                st_stream_int4(dst + 2, make_int4(t[8], t[9], t[10], t[11]));
+                if ((units_per_slice & 31) == 0) {
+                    // the warp's 32 x 48 B are one contiguous 1536 B block: exchange through shared memory so
+                    // that every store instruction writes 512 contiguous bytes (whole sectors, no partial writes)
+                    const int lane = threadIdx.x & 31;
+                    int4* stg = stage + (threadIdx.x >> 5) * 96;
+                    stg[lane * 3] = make_int4(t[0], t[1], t[2], t[3]);
+                    stg[lane * 3 + 1] = make_int4(t[4], t[5], t[6], t[7]);
+                    stg[lane * 3 + 2] = make_int4(t[8], t[9], t[10], t[11]);
+                    __syncwarp();
+                    int4* dst = reinterpret_cast<int4*>(out_all + (b * hw + (long long)(o - lane) * 8) * 3);
+                    st_stream_int4(dst + lane, stg[lane]);
+                    st_stream_int4(dst + 32 + lane, stg[32 + lane]);
+                    st_stream_int4(dst + 64 + lane, stg[64 + lane]);
+                    __syncwarp();
+                } else {                                            // ragged rows: plain 48-byte-strided stores
+                    int4* dst = reinterpret_cast<int4*>(out_all + (b * hw + (long long)o * 8) * 3);
+                    st_stream_int4(dst, make_int4(t[0], t[1], t[2], t[3]));
+                    st_stream_int4(dst + 1, make_int4(t[4], t[5], t[6], t[7]));
+                    st_stream_int4(dst + 2, make_int4(t[8], t[9], t[10], t[11]));
+                }
             } else {
                 uint16_t* base = out_all + b * 3 * hw + o * 8;
                 const int4 q = make_int4(v[0], v[1], v[2], v[3]);
@@ -175,6 +206,7 @@ hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int 
                 st_stream_int4(reinterpret_cast<int4*>(base + hw), q);
                 st_stream_int4(reinterpret_cast<int4*>(base + 2 * hw), q);
             }
+        }
         }
     }
 }
@@ -185,7 +217,7 @@ int launch_hu16(const int16_t* px, int B, int H, int W, int lo, int hi, int rot1
     const int d = hi - lo;
     if (B > 65535) return EITB_ERR_UNSUPPORTED;
     const dim3 grid(eitb_grid_per_image(ups, kThreads, B), B);
-    const size_t smem = (size_t)(d + 1) * 3 + 16;
+    const size_t smem = (size_t)(d + 1) * 3 + 16 + (kThreads / 32) * 96 * sizeof(int4);
     eitb_prof_begin("hu_window_kernel", s);
     if (nhwc) {
         if (out_u8) hu_window16_kernel<true, true><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);

@@ -64,6 +64,18 @@ def test_hu_window_other_windows_and_no_rotation(ops):
         assert np.array_equal(u8.cpu().numpy(), want)
 
 
+def test_hu_window_channels_last_ragged_shapes(ops):
+    rng = np.random.default_rng(4)
+    for shape in ((3, 40, 72), (2, 8, 8), (5, 256, 256), (1, 24, 104)):
+        px = rng.integers(-400, 500, shape).astype(np.int16)
+        m = (rng.random(shape) > 0.4).astype(np.uint8) * 255
+        for dt in (torch.float16, torch.bfloat16):
+            _, a = ops.hu_window(dev(px), body_mask=dev(m), want_u8=False, nchw_dtype=dt, channels_last=True)
+            u8, b = ops.hu_window(dev(px), body_mask=dev(m), want_u8=True, nchw_dtype=dt, channels_last=False)
+            assert torch.equal(a, b)
+            assert np.array_equal(u8.cpu().numpy(), O.apply_mask(O.classic_norm(px), m))
+
+
 def test_u8_to_nchw(ops):
     g = np.arange(256, dtype=np.uint8).repeat(64).reshape(1, 128, 128)
     for dt in (torch.float32, torch.float16, torch.bfloat16):
