@@ -66,3 +66,30 @@ def test_ops_refuse_cpu_tensors():
     from eitsynthai_b200 import ops
     with pytest.raises(ValueError):
         ops.hu_window(torch.zeros((1, 8, 8), dtype=torch.int16))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without libeitb200.so the binding raises instead of computing elsewhere."""
+    from eitsynthai_b200 import cabi
+    monkeypatch.setattr(cabi, "_lib", None)
+    monkeypatch.setattr(cabi, "LIB_PATH", str(tmp_path / "libeitb200.so"))
+    with pytest.raises(cabi.EitbLibraryError):
+        cabi.load()
+    with pytest.raises(cabi.EitbLibraryError):
+        cabi.call("eitb_version")
+
+
+def test_product_package_never_imports_the_oracle():
+    import ast
+    pkg = os.path.join(ROOT, "eitsynthai_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                tree = ast.parse(open(os.path.join(dirpath, f)).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom) and node.module:
+                        names = [node.module]
+                    assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (f, names)

@@ -216,3 +216,36 @@ def test_zip_of_dicom_files_end_to_end(pipe):
     assert custom == 1 and np.array_equal(px, vol)
     assert [int(s.InstanceNumber) for s in i_slices] == sorted(int(i) for i in inst)
     assert np.array_equal(front, O.front_slice_norm(vol[np.argsort(inst, kind="stable")]))
+
+
+def test_full_size_series_invariants(pipe):
+    """BASELINE configs[2] at full size (320 slices): properties that need no CPU run of the whole series --
+    the coronal image equals the (cheap) oracle, label maps do not depend on how the series is chunked or
+    batched, body masks are per-slice functions, and a z-split of the series gives the same coronal rows."""
+    from eitsynthai_b200 import ops
+    from eitsynthai_b200.pipeline import SeriesBatchRunner, SeriesMeta
+    vol, inst = synth.phantom_series(320, seed=0, shuffle_seed=17)
+    meta = SeriesMeta(inst)
+    dev_px = torch.from_numpy(vol).cuda()
+    srt = vol[np.argsort(inst, kind="stable")]
+    assert np.array_equal(pipe.coronal(dev_px, meta).cpu().numpy(), O.front_slice_norm(srt))
+    r = SeriesBatchRunner(pipe, [meta], 320, 512, chunk=160)
+    r.load(torch.from_numpy(vol[None]))
+    r.capture(warm=1)
+    sel = r.step_device().cpu()
+    big = torch.cat([o[0] for o in r.outs])
+    small = torch.cat([pipe.segment(dev_px[c:c + 64])[0] for c in range(0, 320, 64)])
+    assert torch.equal(big, small)                                   # chunk / graph invariance of 84 M label pixels
+    for k in (0, 131, 319):                                          # single-slice calls agree with the batch
+        assert torch.equal(pipe.segment(dev_px[k:k + 1])[0][0], big[k])
+        assert np.array_equal(ops.body_mask(dev_px[k:k + 1])[0].cpu().numpy(), O.body_mask(vol[k], -1024, 1))
+    order = np.argsort(inst, kind="stable").astype(np.int32)
+    lo, hi = order[:160], order[160:]                                # the two shards a 2-GPU run would hold
+    rows = []
+    for part in (lo, hi):
+        sub = dev_px[torch.from_numpy(np.sort(part)).cuda().long()]
+        sub_inst = inst[np.sort(part)]
+        rr, mm = pipe.coronal(sub, SeriesMeta(sub_inst), return_rows=True)
+        rows.append(rr)
+    assert np.array_equal(torch.cat(rows).cpu().numpy(), O.front_rows(srt))
+    assert sel.shape == (1, 4)
