@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=160, help="slices per CNN batch / CUDA graph")
+    ap.add_argument("--first-chunk", type=int, default=0, help="size of a smaller first chunk (0: all chunks equal)")
     ap.add_argument("--slices", type=int, default=N_SLICES)
     ap.add_argument("--series", type=int, default=0, help="series per step (default: one per GPU = weak scaling; "
                     "64 with --gpus 8 is BASELINE configs[3])")
@@ -229,7 +230,8 @@ def run_b200(args):
     timer = StageTimer(torch)
     profiling = {"on": False}
     # the public throughput engine of the package; bench.py only times it
-    runner = SeriesBatchRunner(pipe, metas, nslices, SIZE, args.chunk, use_graphs=not args.no_graphs, timer=timer)
+    runner = SeriesBatchRunner(pipe, metas, nslices, SIZE, args.chunk, use_graphs=not args.no_graphs, timer=timer,
+                               first_chunk=args.first_chunk)
     runner.load(px_host)
     runner.capture()
     graphs, outs = runner.graphs, runner.outs

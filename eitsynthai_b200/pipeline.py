@@ -229,7 +229,7 @@ class SeriesBatchRunner:
     """
 
     def __init__(self, pipe: ImagingPipeline, metas, n_slices: int, size: int = 512, chunk: int = 160,
-                 use_graphs: bool = True, timer=None):
+                 use_graphs: bool = True, timer=None, first_chunk: int = 0):
         from . import sharded
         self.pipe, self.sharded = pipe, sharded
         self.dev = pipe.device
@@ -245,7 +245,11 @@ class SeriesBatchRunner:
         self.timer = timer or _NullTimer()
         self.px = torch.empty((self.S, self.nl, size, size), dtype=torch.int16, device=dev)      # the resident batch
         self.flat = self.px.view(self.S * self.nl, size, size)
-        self.chunks = list(range(0, self.S * self.nl, chunk))
+        total = self.S * self.nl
+        # (start, stop) of every chunk; a smaller first chunk lets compute start sooner on the host path
+        starts = list(range(0, total, chunk)) if not first_chunk else [0] + list(range(first_chunk, total, chunk))
+        self.bounds = [(a, min(b, total)) for a, b in zip(starts, starts[1:] + [total])]
+        self.chunks = [a for a, _ in self.bounds]
         self.mine = [s for s in range(self.S) if sharded.owner_of_series(s, self.world) == self.rank]
         self.mine_idx = torch.tensor(self.mine, dtype=torch.int64, device=dev)
         self.rows_static = torch.zeros((self.S, n_slices, size), dtype=torch.int16, device=dev)
@@ -253,6 +257,7 @@ class SeriesBatchRunner:
         self.rows_pin = torch.empty((self.S, self.nl, 1, size), dtype=torch.int16).pin_memory()
         self.rows_dev = torch.empty((self.S, self.nl, 1, size), dtype=torch.int16, device=dev)
         self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.side = torch.cuda.Stream(dev)                      # the per-series decision runs beside the slice chunks
         self.graphs, self.outs, self.rib_graph, self.sel_static = [], [], None, None
         self.use_graphs = use_graphs
 
@@ -329,8 +334,8 @@ class SeriesBatchRunner:
 
     def step_eager(self):
         sel = self.rib_stage(self.px)
-        for c0 in self.chunks:
-            self.slice_stage(self.flat[c0:c0 + self.chunk])
+        for a, b in self.bounds:
+            self.slice_stage(self.flat[a:b])
         return sel
 
     def capture(self, warm: int = 2):
@@ -341,14 +346,14 @@ class SeriesBatchRunner:
         if not self.use_graphs:
             return
         pool = torch.cuda.graph_pool_handle()
-        for c0 in self.chunks:
+        for a, b in self.bounds:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
-                o = self.slice_stage(self.flat[c0:c0 + self.chunk])
+                o = self.slice_stage(self.flat[a:b])
             self.graphs.append(g)
             self.outs.append(o)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=pool):
+        with torch.cuda.graph(g):                                 # own memory pool: it replays beside the chunk graphs
             self.sel_static = self.rib_decide(self.rows_static, self.mm_static)
         self.rib_graph = g
 
@@ -356,13 +361,25 @@ class SeriesBatchRunner:
         if self.graphs:
             self.graphs[ci].replay()
             return self.outs[ci]
-        c0 = self.chunks[ci]
-        return self.slice_stage(self.flat[c0:c0 + self.chunk])
+        a, b = self.bounds[ci]
+        return self.slice_stage(self.flat[a:b])
+
+    def _rib_on_side(self, px, src_row=None):
+        """The coronal decision is independent of the per-slice path and tiny (one image per series): run it
+        on a side stream so its ~300 small launches hide under the chunk graphs."""
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            sel = self.rib_stage(px, graphed=True, src_row=src_row)
+        sel.record_stream(main)
+        return sel
 
     def step_device(self):
-        sel = self.rib_stage(self.px, graphed=True)
+        main = torch.cuda.current_stream(self.dev)
+        sel = self._rib_on_side(self.px)
         for ci in range(len(self.chunks)):
             self.run_chunk(ci)
+        main.wait_stream(self.side)
         return sel
 
     def step_host(self, px_host: torch.Tensor, labels_host: torch.Tensor):
@@ -378,21 +395,22 @@ class SeriesBatchRunner:
             self.rows_dev.copy_(self.rows_pin, non_blocking=True)
             ev_rows = torch.cuda.Event()
             ev_rows.record(self.copy_in)
-            for c0 in self.chunks:
-                self.flat[c0:c0 + self.chunk].copy_(flat_host[c0:c0 + self.chunk], non_blocking=True)
+            for a, b in self.bounds:
+                self.flat[a:b].copy_(flat_host[a:b], non_blocking=True)
                 e = torch.cuda.Event()
                 e.record(self.copy_in)
                 evs.append(e)
         main.wait_event(ev_rows)
-        sel = self.rib_stage(self.rows_dev, graphed=True, src_row=0)
-        for ci, c0 in enumerate(self.chunks):
+        sel = self._rib_on_side(self.rows_dev, src_row=0)
+        for ci, (a, b) in enumerate(self.bounds):
             main.wait_event(evs[ci])
             code, _ = self.run_chunk(ci)
             e = torch.cuda.Event()
             e.record(main)
             self.copy_out.wait_event(e)
             with torch.cuda.stream(self.copy_out):
-                flat_out[c0:c0 + self.chunk].copy_(code, non_blocking=True)
+                flat_out[a:b].copy_(code, non_blocking=True)
             code.record_stream(self.copy_out)
         main.wait_stream(self.copy_out)
+        main.wait_stream(self.side)
         return sel.cpu()
