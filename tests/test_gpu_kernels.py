@@ -287,6 +287,29 @@ def test_mask_decode_tensor_core_path(ops, case, variant):
         assert (want != tc[b].cpu().numpy()).mean() <= 1e-4
 
 
+def test_mask_decode_tensor_core_small_size_ragged_batch(ops):
+    """tcgen05 path at the 256-pixel size (64x64 prototypes: partial tiles), images with 0 / few / >128
+    instances in one batch, and max_det smaller than the candidate count."""
+    heads, protos = [], []
+    for n_c, seed in ((0, 1), (7, 2), (300, 3)):
+        h, p = synth.random_heads(1, n_c, seed=seed, size=256)
+        heads.append(h[0]); protos.append(p[0])
+    head, ph = np.stack(heads), torch.from_numpy(np.stack(protos)).half()
+    for max_det in (300, 40):
+        dets, idx, n = ops.nms(dev(head), 4, max_det=max_det)
+        assert n.cpu().tolist()[0] == 0 and int(n[2]) <= max_det
+        tc, a1, b1 = ops.mask_decode(dets, n, ph.to(DEV), 0, want_area=True, want_bits=True)
+        cc, a2, b2 = ops.mask_decode(dets, n, ph.to(DEV), 0x10, want_area=True, want_bits=True)
+        assert (tc != cc).float().mean().item() <= 1e-4
+        assert int((np.unpackbits(b1.cpu().numpy()) != np.unpackbits(b2.cpu().numpy())).sum()) <= 1e-5 * b1.numel() * 8
+        assert float((tc[0] != 0).sum()) == 0
+        for b in range(3):
+            r = Y.postprocess(torch.from_numpy(head[b]), ph[b].float(), 4, (256, 256), (256, 256), drop_empty=False)
+            m, c = r["masks"].numpy()[:max_det], r["cls"].numpy().astype(int)[:max_det]
+            want = O.overlay_codes(O.class_union_masks(m, c, 256))
+            assert (want != tc[b].cpu().numpy()).mean() <= 1e-4
+
+
 def test_codes_to_bgr(ops):
     code = np.random.default_rng(0).choice([0, 1, 3, 6, 7], (3, 64, 64)).astype(np.uint8)
     assert np.array_equal(ops.codes_to_bgr(dev(code)).cpu().numpy(), O.code_to_bgr(code))

@@ -249,3 +249,24 @@ def test_full_size_series_invariants(pipe):
         rows.append(rr)
     assert np.array_equal(torch.cat(rows).cpu().numpy(), O.front_rows(srt))
     assert sel.shape == (1, 4)
+
+
+def test_post_cnn_chain_matches_oracle_256(pipe):
+    """The 256-pixel route (ai_tools.py:138-146 picks the 256 model): every stage at the other supported size."""
+    from eitsynthai_b200 import ops
+    px = np.stack([synth.phantom_slice(s, size=256) for s in (21, 22)])
+    pxd = torch.from_numpy(px).cuda()
+    body = ops.body_mask(pxd, 1, -1024, True)
+    _, x = ops.hu_window(pxd, body_mask=body, want_u8=False, nchw_dtype=pipe.dtype, channels_last=True)
+    with torch.no_grad():
+        head, protos = pipe.axial_model_256(x)
+    assert head.shape == (2, 40, 1344) and protos.shape == (2, 32, 64, 64)
+    code, body2, n = pipe.segment(pxd)
+    for b in range(2):
+        wbody = O.body_mask(px[b], -1024, 1)
+        assert np.array_equal(body2[b].cpu().numpy(), wbody)
+        r = Y.postprocess(head[b].float().cpu(), protos[b].float().cpu(), 4, (256, 256), (256, 256))
+        union = O.class_union_masks(r["masks"].numpy(), r["cls"].numpy().astype(int), 256)
+        want = O.create_color_codes(union, wbody)
+        got = code[b].cpu().numpy()
+        assert (got != want).mean() <= 1e-4, (b, int((got != want).sum()))
