@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk", type=int, default=160, help="slices per CNN batch / CUDA graph")
     ap.add_argument("--first-chunk", type=int, default=0, help="size of a smaller first chunk (0: all chunks equal)")
+    ap.add_argument("--chunks", default="", help="explicit comma-separated chunk sizes (must add up to the local slice count)")
     ap.add_argument("--slices", type=int, default=N_SLICES)
     ap.add_argument("--series", type=int, default=0, help="series per step (default: one per GPU = weak scaling; "
                     "64 with --gpus 8 is BASELINE configs[3])")
@@ -231,7 +232,8 @@ def run_b200(args):
     profiling = {"on": False}
     # the public throughput engine of the package; bench.py only times it
     runner = SeriesBatchRunner(pipe, metas, nslices, SIZE, args.chunk, use_graphs=not args.no_graphs, timer=timer,
-                               first_chunk=args.first_chunk)
+                               first_chunk=args.first_chunk,
+                               chunk_sizes=[int(c) for c in args.chunks.split(",")] if args.chunks else None)
     runner.load(px_host)
     runner.capture()
     graphs, outs = runner.graphs, runner.outs
@@ -380,6 +382,16 @@ def run_b200(args):
         mesh = {"triangles": int(len(tris)), "polygons": int(len(pcls)), "polygon_vertices": int(len(xy)),
                 "ms": ms_mesh, "elements_per_sec": len(tris) / (ms_mesh / 1e3),
                 "class_histogram": torch.bincount(cls_gpu, minlength=5).tolist()}
+        # the raster look-up the north star also names (centroid pixel of the label map), against the
+        # reference's polygon semantics on the same mesh
+        cls_raster = ops.tri_label_raster(dm[0], dm[1], code_m[0].contiguous())
+        a.record()
+        for _ in range(10):
+            ops.tri_label_raster(dm[0], dm[1], code_m[0].contiguous())
+        b.record()
+        torch.cuda.synchronize(dev)
+        mesh["raster_mode"] = {"ms": a.elapsed_time(b) / 10, "elements_per_sec": len(tris) / (a.elapsed_time(b) / 10 / 1e3),
+                               "disagreement_vs_polygon_mode": float((cls_raster != cls_gpu).float().mean())}
         if not args.no_cpu_baseline:
             from oracle import tri_label as TL                      # CPU baseline leg: the C restatement, one core
             nb = min(20000, len(tris))

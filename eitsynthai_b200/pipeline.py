@@ -229,7 +229,7 @@ class SeriesBatchRunner:
     """
 
     def __init__(self, pipe: ImagingPipeline, metas, n_slices: int, size: int = 512, chunk: int = 160,
-                 use_graphs: bool = True, timer=None, first_chunk: int = 0):
+                 use_graphs: bool = True, timer=None, first_chunk: int = 0, chunk_sizes=None):
         from . import sharded
         self.pipe, self.sharded = pipe, sharded
         self.dev = pipe.device
@@ -249,6 +249,12 @@ class SeriesBatchRunner:
         # (start, stop) of every chunk; a smaller first chunk lets compute start sooner on the host path
         starts = list(range(0, total, chunk)) if not first_chunk else [0] + list(range(first_chunk, total, chunk))
         self.bounds = [(a, min(b, total)) for a, b in zip(starts, starts[1:] + [total])]
+        if chunk_sizes:                                         # explicit list, e.g. small head and tail chunks for the host path
+            assert sum(chunk_sizes) == total, "chunk_sizes must add up to the local slice count"
+            edges = [0]
+            for c in chunk_sizes:
+                edges.append(edges[-1] + c)
+            self.bounds = list(zip(edges[:-1], edges[1:]))
         self.chunks = [a for a, _ in self.bounds]
         self.mine = [s for s in range(self.S) if sharded.owner_of_series(s, self.world) == self.rank]
         self.mine_idx = torch.tensor(self.mine, dtype=torch.int64, device=dev)
