@@ -54,7 +54,7 @@ SIGNATURES = {
     "eitb_bias_act_nhwc": (_i, [_p, _i, C.c_longlong, _i, _p, _i, _p]),
     "eitb_conv_epilogue_nhwc": (_i, [_p, _i, C.c_longlong, _i, _p, _i, _p, _p, _p, _i, _i, _p]),
     "eitb_upsample2x_concat_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "eitb_yolo_head_decode": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "eitb_yolo_head_decode": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "eitb_sppf_pool_concat": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "eitb_tri_label_workspace_bytes": (_sz, [_i]),
     "eitb_tri_label": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _p, _p, _sz, _p]),

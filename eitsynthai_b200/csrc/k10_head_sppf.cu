@@ -18,6 +18,9 @@ struct HeadLevel {
     const __half* cls;   // [B,h,w,nc]
     const __half* mc;    // [B,h,w,nm]
     int h, w, stride, a0;   // a0: first anchor index of the level
+    const float* bbox;   // [64] bias of the last box conv, or NULL
+    const float* bcls;   // [nc]
+    const float* bmc;    // [nm]
 };
 struct HeadArgs { HeadLevel lv[3]; };
 
@@ -45,6 +48,10 @@ head_decode_kernel(HeadArgs args, int B, int nc, int nm, int A, __half* __restri
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h2[k]); v[q * 8 + 2 * k] = f.x; v[q * 8 + 2 * k + 1] = f.y; }
             }
+            if (L.bbox) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] += __ldg(L.bbox + s * 16 + k);
+            }
             float m = v[0];
 #pragma unroll
             for (int k = 1; k < 16; ++k) m = fmaxf(m, v[k]);
@@ -62,11 +69,15 @@ head_decode_kernel(HeadArgs args, int B, int nc, int nm, int A, __half* __restri
         o[(long long)3 * A] = __float2half_rn((y2 - y1) * st);
         const __half* cp = L.cls + pix * nc;
         for (int c = 0; c < nc; ++c) {
-            const float z = __half2float(__ldg(cp + c));
+            const float z = __half2float(__ldg(cp + c)) + (L.bcls ? __ldg(L.bcls + c) : 0.f);
             o[(long long)(4 + c) * A] = __float2half_rn(1.f / (1.f + __expf(-z)));
         }
         const __half* mp = L.mc + pix * nm;
-        for (int c = 0; c < nm; ++c) o[(long long)(4 + nc + c) * A] = __ldg(mp + c);
+        if (L.bmc) {
+            for (int c = 0; c < nm; ++c) o[(long long)(4 + nc + c) * A] = __float2half_rn(__half2float(__ldg(mp + c)) + __ldg(L.bmc + c));
+        } else {
+            for (int c = 0; c < nm; ++c) o[(long long)(4 + nc + c) * A] = __ldg(mp + c);
+        }
     }
 }
 
@@ -120,8 +131,9 @@ sppf_kernel(const __half* __restrict__ x, int h, int w, int C, __half* __restric
 
 }  // namespace
 
-extern "C" int eitb_yolo_head_decode(const void* const* box, const void* const* cls, const void* const* mc, const int* hs,
-                                     const int* ws, const int* strides, int B, int nc, int nm, void* head,
+extern "C" int eitb_yolo_head_decode(const void* const* box, const void* const* cls, const void* const* mc,
+                                     const float* const* box_bias, const float* const* cls_bias, const float* const* mc_bias,
+                                     const int* hs, const int* ws, const int* strides, int B, int nc, int nm, void* head,
                                      eitb_stream_t stream) {
     if (!box || !cls || !mc || !hs || !ws || !strides || !head || B < 0 || nc <= 0 || nm < 0) return EITB_ERR_BAD_ARG;
     if (nm % 8) return EITB_ERR_UNSUPPORTED;
@@ -130,7 +142,8 @@ extern "C" int eitb_yolo_head_decode(const void* const* box, const void* const* 
     for (int l = 0; l < 3; ++l) {
         if (!box[l] || !cls[l] || (nm && !mc[l]) || hs[l] <= 0 || ws[l] <= 0) return EITB_ERR_BAD_ARG;
         if (reinterpret_cast<uintptr_t>(box[l]) & 15) return EITB_ERR_UNSUPPORTED;
-        a.lv[l] = HeadLevel{(const __half*)box[l], (const __half*)cls[l], (const __half*)mc[l], hs[l], ws[l], strides[l], A};
+        a.lv[l] = HeadLevel{(const __half*)box[l], (const __half*)cls[l], (const __half*)mc[l], hs[l], ws[l], strides[l], A,
+                            box_bias ? box_bias[l] : nullptr, cls_bias ? cls_bias[l] : nullptr, mc_bias ? mc_bias[l] : nullptr};
         A += hs[l] * ws[l];
     }
     if (B == 0) return EITB_OK;

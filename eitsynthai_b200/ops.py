@@ -268,8 +268,9 @@ def upsample2x_concat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------ K10
-def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int) -> torch.Tensor:
-    """Lists of the 3 per-level branch outputs (channels-last fp16 [B,64|nc|nm,h,w]) -> head [B,4+nc+nm,A]."""
+def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int, biases=None) -> torch.Tensor:
+    """Lists of the 3 per-level branch outputs (channels-last fp16 [B,64|nc|nm,h,w]) -> head [B,4+nc+nm,A].
+    ``biases`` = (box, cls, mc) lists of per-level float32 bias vectors folded into the decode."""
     import ctypes as C
     cl = torch.channels_last
     B = box[0].shape[0]
@@ -282,8 +283,15 @@ def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int) -> torch.Tensor:
     arr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
     A = sum(t.shape[2] * t.shape[3] for t in box)
     head = torch.empty((B, 4 + nc + nm, A), dtype=torch.float16, device=box[0].device)
+    bb = cb = mb = None
+    if biases is not None:
+        for group in biases:
+            for t in group:
+                _chk(t, torch.float32, "bias")
+        bb, cb, mb = (arr(g) for g in biases)
     with torch.cuda.device(head.device):
-        cabi.call("eitb_yolo_head_decode", arr(box), arr(cls), arr(mc), hs, ws, st, B, nc, nm, head.data_ptr(), _stream(head))
+        cabi.call("eitb_yolo_head_decode", arr(box), arr(cls), arr(mc), bb, cb, mb, hs, ws, st, B, nc, nm, head.data_ptr(),
+                  _stream(head))
     return head
 
 

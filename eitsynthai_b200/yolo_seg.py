@@ -224,8 +224,27 @@ class Proto(nn.Module):
         self.cv2 = Conv(c_, c_, 3)
         self.cv3 = Conv(c_, c2, 1)
 
+    def strip_bias(self):
+        """Serve the transposed convolution's bias through K9 instead of PyTorch's broadcast add."""
+        self.up_bias = self.upsample.bias.detach().float().clone()
+        self.upsample.bias = None
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        if getattr(self, "up_bias", None) is not None:
+            self.up_bias = fn(self.up_bias).float()
+        return self
+
     def forward(self, x):
-        return self.cv3(self.cv2(self.upsample(self.cv1(x))))
+        y = self.upsample(self.cv1(x))
+        ub = getattr(self, "up_bias", None)
+        if ub is not None:
+            if y.is_cuda and y.dtype != torch.float32 and y.is_contiguous(memory_format=torch.channels_last):
+                from . import ops
+                ops.bias_act_(y, ub, False)
+            else:
+                y = y + ub.to(y.dtype).view(1, -1, 1, 1)
+        return self.cv3(self.cv2(y))
 
 
 class Segment(nn.Module):
@@ -253,6 +272,30 @@ class Segment(nn.Module):
             a[-1].bias.data[:] = 1.0
             b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / s) ** 2)
 
+    def strip_bias(self):
+        """The last convolution of every branch runs bias-free; the biases are added inside the K10 decode
+        (PyTorch would run nine broadcast adds per forward for them)."""
+        self.head_bias = tuple([br[i][-1].bias.detach().float().clone() for i in range(self.nl)]
+                               for br in (self.cv2, self.cv3, self.cv4))
+        for br in (self.cv2, self.cv3, self.cv4):
+            for i in range(self.nl):
+                br[i][-1].bias = None
+        self.proto.strip_bias()
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        if getattr(self, "head_bias", None) is not None:
+            self.head_bias = tuple([fn(t).float() for t in g] for g in self.head_bias)
+        return self
+
+    def shift_cls_bias(self, shift: float):
+        if getattr(self, "head_bias", None) is not None:
+            for t in self.head_bias[1]:
+                t += shift
+        else:
+            for b in self.cv3:
+                b[-1].bias.data += shift
+
     def _grid(self, shapes, device, dtype):
         key = (tuple(shapes), str(device), dtype)
         if key not in self._anchors:
@@ -278,7 +321,11 @@ class Segment(nn.Module):
         if getattr(self, "fused_tails", False) and box[0].is_cuda and box[0].dtype == torch.float16 and all(
                 t.is_contiguous(memory_format=cl) or t.shape[1] == 1 for t in box + cls + mc):
             from . import ops
-            return ops.yolo_head_decode(box, cls, mc, self.stride, self.nc, self.nm), protos
+            return ops.yolo_head_decode(box, cls, mc, self.stride, self.nc, self.nm, getattr(self, "head_bias", None)), protos
+        hb = getattr(self, "head_bias", None)
+        if hb is not None:                                        # biases were stripped from the convolutions
+            box, cls, mc = ([t + g[i].to(t.dtype).view(1, -1, 1, 1) for i, t in enumerate(ts)]
+                            for ts, g in ((box, hb[0]), (cls, hb[1]), (mc, hb[2])))
         box, cls, mc = (torch.cat([t.flatten(2) for t in ts], 2) for ts in (box, cls, mc))
         A = box.shape[2]
         anchors, strides = self._grid(shapes, box.device, box.dtype)
@@ -346,8 +393,7 @@ class YOLO11sSeg(nn.Module):
         logit = torch.log(s) - torch.log1p(-s)
         q = torch.quantile(logit[torch.randperm(logit.numel(), device=logit.device)[:1_000_000]], 1.0 - frac)
         shift = float(math.log(conf / (1 - conf)) - q)
-        for b in self.head.cv3:
-            b[-1].bias.data += shift
+        self.head.shift_cls_bias(shift)
         return shift
 
 
@@ -365,6 +411,8 @@ def build_model(nc: int, device, dtype=torch.float16, seed: int = 0, fuse: bool 
                 mod.split_cv1()
             if isinstance(mod, (SPPF, Segment)):
                 mod.fused_tails = True                          # K10: one-pass SPPF pooling and head decode
+            if isinstance(mod, Segment):
+                mod.strip_bias()
     m = m.to(device=device, dtype=dtype).to(memory_format=torch.channels_last)
     for p in m.parameters():
         p.requires_grad_(False)

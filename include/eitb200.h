@@ -209,9 +209,12 @@ int eitb_upsample2x_concat_nhwc(const void* a, const void* b, void* out, int dty
 /* ---- K10: non-convolution tails of the network, fp16 channels-last ------------------------------------
  * Detect/Segment inference tail: box[l] [B,h_l,w_l,64] DFL logits, cls[l]
  * [B,h_l,w_l,nc] class logits, mc[l] [B,h_l,w_l,nm] for the 3 levels (host arrays of device pointers,
- * sizes and strides) -> head [B,4+nc+nm,A] fp16: xywh in input pixels, sigmoid scores, coefficients. */
-int eitb_yolo_head_decode(const void* const* box, const void* const* cls, const void* const* mc, const int* hs,
-                          const int* ws, const int* strides, int B, int nc, int nm, void* head,
+ * sizes and strides) -> head [B,4+nc+nm,A] fp16: xywh in input pixels, sigmoid scores, coefficients.
+ * box_bias / cls_bias / mc_bias: per-level device float32 bias vectors of the last convolution of each
+ * branch, added on the fly (host arrays of 3 pointers, or NULL when the convolutions carry their bias). */
+int eitb_yolo_head_decode(const void* const* box, const void* const* cls, const void* const* mc,
+                          const float* const* box_bias, const float* const* cls_bias, const float* const* mc_bias,
+                          const int* hs, const int* ws, const int* strides, int B, int nc, int nm, void* head,
                           eitb_stream_t stream);
 
 /* SPPF (yaml layer 9): x [B,h,w,C] -> out [B,h,w,4C] = x | maxpool5 | maxpool9 | maxpool13 (-inf padding). */
