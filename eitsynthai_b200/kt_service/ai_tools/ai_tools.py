@@ -227,13 +227,21 @@ class ImageToMask(DICOMSequencesToMask):
 
 class NIIToMask(DICOMSequencesToMask):
     def get_coordinate_slice_from_nii(self, zip_buffer, answer=None, mesh=None):
-        """ai_tools.py:408-450: the middle slice of the volume as an HU image.  ``zip_buffer`` may be a
-        dict(hu=(H,W) int16, pixel_spacing=[..]) -- the NIfTI decode (utils.py:1062-1119, nibabel) is a seam.
+        """ai_tools.py:408-450: the middle slice of the volume as an HU image.  ``zip_buffer`` is the uploaded
+        zip (first ``.nii.gz`` member, nifti_io.get_nii_mean_slice) or a dict(hu=(H,W) int16, pixel_spacing=[..]).
         classic_norm rotates by 180 and the caller rotates back (ai_tools.py:430-431): net no rotation."""
         answer = []
         try:
-            hu = np.asarray(zip_buffer["hu"], np.int16)
-            spacing = list(zip_buffer.get("pixel_spacing", [0.662, 0.662]))
+            if isinstance(zip_buffer, dict):
+                hu = np.asarray(zip_buffer["hu"], np.int16)
+                spacing = list(zip_buffer.get("pixel_spacing", [0.662, 0.662]))
+            else:                                                  # a zip with a .nii.gz member, like the reference
+                from . import nifti_io
+                if isinstance(zip_buffer, (bytes, bytearray)):
+                    import io
+                    zip_buffer = io.BytesIO(zip_buffer)
+                with zipfile.ZipFile(zip_buffer, "r") as zf:
+                    hu, spacing = nifti_io.get_nii_mean_slice(zf)
             px = torch.from_numpy(hu[None].copy()).to(self.device)
             t1 = time.time()
             from ... import ops

@@ -24,8 +24,8 @@ def _get(name):
 
 
 def _pack(answer):
-    if not answer:
-        return JSONResponse(status_code=500, content={"status": "error", "message": "processing failed"})
+    if not answer:                                                  # the pipelines' failure sentinel, returned as is (ai_tools.py:203,229-231)
+        return JSONResponse(content=[])
     return JSONResponse(content={"status": answer["status"], "message": answer["message"],
                                  "segmentation_time": answer["segmentation_time"], "text_data": answer["text_data"],
                                  "label_shape": list(answer["label_codes"].shape), "polygons": answer["polygons"],
@@ -35,6 +35,9 @@ def _pack(answer):
 async def _run(file: UploadFile, cls_name: str, method: str):
     try:
         buf = io.BytesIO(await file.read())
+        if not zipfile.is_zipfile(buf):                             # main_kt_service.py:42-44
+            raise zipfile.BadZipFile
+        buf.seek(0)
         return _pack(getattr(_get(cls_name), method)(buf))
     except zipfile.BadZipFile:
         return JSONResponse(status_code=400, content={"status": "error", "message": "bad zip file"})
@@ -72,5 +75,4 @@ async def upload_image(file: UploadFile = File(...)):
 
 @app.post("/uploadNII")
 async def upload_nii(file: UploadFile = File(...)):
-    return JSONResponse(status_code=501, content={"status": "error", "message": "NIfTI decode (nibabel) is outside the hot path; "
-                                                  "call NIIToMask.get_coordinate_slice_from_nii with a decoded HU slice"})
+    return await _run(file, "NIIToMask", "get_coordinate_slice_from_nii")

@@ -62,3 +62,29 @@ def test_zip_series_largest_series_custom_input_and_pinned_copy():
     with zipfile.ZipFile(z) as zf:
         s2, c2 = D.create_dicom_dict(zf)
     assert c2 == 0 and len(s2) == 12
+
+
+def test_nifti_mid_slice_matches_the_reference_recipe():
+    """get_nii_mean_slice restated (utils.py:1062-1119): data[:, :, Z//2] rotated 90 degrees clockwise, int16."""
+    import cv2
+    from eitsynthai_b200.kt_service.ai_tools import nifti_io as N
+    rng = np.random.default_rng(0)
+    vol = rng.integers(-1000, 2000, (48, 40, 7)).astype(np.int16)          # [i, j, k]
+    for gz in (True, False):
+        sl, spacing = N.read_nifti_mid_slice(N.write_nifti(vol, pixdim=(0.68, 0.71, 2.5), gz=gz))
+        assert np.array_equal(sl, cv2.rotate(vol[:, :, int(7 / 2)], cv2.ROTATE_90_CLOCKWISE)) and sl.dtype == np.int16
+        assert spacing == [pytest.approx(0.68), pytest.approx(0.71)]
+    f32 = (vol.astype(np.float32) / 3.0)
+    sl, _ = N.read_nifti_mid_slice(N.write_nifti(f32, slope=2.0, inter=-5.0))
+    want = (f32[:, :, 3].astype(np.float64) * 2.0 - 5.0).astype(np.int16)
+    assert np.array_equal(sl, cv2.rotate(want, cv2.ROTATE_90_CLOCKWISE))
+    sl, spacing = N.read_nifti_mid_slice(N.write_nifti(vol, pixdim=(0.0, 0.7, 1.0)))
+    assert spacing == [0.662, 0.662]                                       # the reference's default
+    buf = io.BytesIO()
+    with zipfile.ZipFile(buf, "w") as zf:
+        zf.writestr("custom_input.txt", "")
+        zf.writestr("scan/volume.nii.gz", N.write_nifti(vol))
+    buf.seek(0)
+    with zipfile.ZipFile(buf) as zf:
+        s2, _ = N.get_nii_mean_slice(zf)
+    assert np.array_equal(s2, cv2.rotate(vol[:, :, 3], cv2.ROTATE_90_CLOCKWISE))

@@ -270,3 +270,53 @@ def test_post_cnn_chain_matches_oracle_256(pipe):
         want = O.create_color_codes(union, wbody)
         got = code[b].cpu().numpy()
         assert (got != want).mean() <= 1e-4, (b, int((got != want).sum()))
+
+
+def test_nii_zip_upload_end_to_end(pipe):
+    import io
+    import zipfile
+    from eitsynthai_b200.kt_service.ai_tools import ai_tools as A
+    from eitsynthai_b200.kt_service.ai_tools import nifti_io as N
+    hu = np.stack([synth.phantom_hu(s).astype(np.int16) for s in range(3)], axis=-1)      # [i, j, k]
+    buf = io.BytesIO()
+    with zipfile.ZipFile(buf, "w") as zf:
+        zf.writestr("vol.nii.gz", N.write_nifti(hu, pixdim=(0.7, 0.7, 1.0)))
+    buf.seek(0)
+    ans = A.NIIToMask().get_coordinate_slice_from_nii(buf)
+    assert ans["status"] == "success" and ans["polygons"][0] == str(np.float32(0.7).item())
+    want = A.NIIToMask().get_coordinate_slice_from_nii({"hu": np.ascontiguousarray(np.rot90(hu[:, :, 1], k=-1)),
+                                                        "pixel_spacing": [0.7, 0.7]})
+    assert np.array_equal(ans["label_codes"], want["label_codes"])
+
+
+def test_fastapi_routes(pipe):
+    """The five POST routes of main_kt_service.py (:33,50,69,88,127) over the GPU pipelines."""
+    import io
+    import zipfile
+    from fastapi.testclient import TestClient
+    from PIL import Image
+    from eitsynthai_b200.kt_service import main_kt_service as M
+    from eitsynthai_b200.kt_service.ai_tools import dicom_io as D
+    from eitsynthai_b200.kt_service.ai_tools import nifti_io as N
+    c = TestClient(M.app)
+    vol, inst = synth.phantom_series(16, seed=8)
+    z = D.zip_series(vol, inst).getvalue()
+    r = c.post("/uploadDicomFrame", files={"file": ("s.zip", z, "application/zip")})
+    assert r.status_code == 200 and r.json()["status"] == "success" and r.json()["label_shape"] == [512, 512]
+    assert c.post("/uploadDicomFrame", files={"file": ("s.zip", b"junk", "application/zip")}).status_code == 400
+    r = c.post("/uploadDicomSequence", files={"file": ("s.zip", z, "application/zip")})
+    assert r.status_code == 200                   # random-init rib model: < 7 right-side ribs -> the reference's [] sentinel
+    assert r.json() == [] or r.json()["status"] == "success"
+    img = O.apply_mask(O.classic_norm(vol[0]), O.body_mask(vol[0], -1024, 1))
+    buf, png = io.BytesIO(), io.BytesIO()
+    Image.fromarray(img).save(png, format="PNG")
+    with zipfile.ZipFile(buf, "w") as zf:
+        zf.writestr("slice.png", png.getvalue())
+    r = c.post("/uploadImageAxialSlice", files={"file": ("i.zip", buf.getvalue(), "application/zip")})
+    assert r.status_code == 200 and r.json()["mesh_classes"] == []
+    hu = np.stack([synth.phantom_hu(s).astype(np.int16) for s in range(3)], axis=-1)
+    buf = io.BytesIO()
+    with zipfile.ZipFile(buf, "w") as zf:
+        zf.writestr("vol.nii.gz", N.write_nifti(hu))
+    r = c.post("/uploadNII", files={"file": ("n.zip", buf.getvalue(), "application/zip")})
+    assert r.status_code == 200 and len(r.json()["mesh_classes"]) > 100
