@@ -359,7 +359,7 @@ def run_b200(args):
                 "how": "CUDA events around every launch of the kernel (libeitb200 launch profiler) over an eager pass of the same steps"}
     # ---------------------------------------------------------------- configs[4]: mesh element classification (K8)
     mesh = None
-    if rank == 0 and not args.no_mesh:
+    if not args.no_mesh:                                          # every rank labels its contiguous block of the elements
         from eitsynthai_b200.kt_service.ai_tools import utils as kt_utils
         hd, pr = synth.teacher_heads(seed=0)
         dets_m, _, n_m = ops.nms(torch.from_numpy(hd[None]).to(dev), 4, want_idx=False)
@@ -368,8 +368,12 @@ def run_b200(args):
         ops.label_cleanup(code_m, body_m)
         polys = kt_utils.codes_to_polygons(code_m[0].cpu().numpy(), [0.753906, 0.753906], body_m[0].cpu().numpy())[2:]
         xy, off, pcls = host.prepare_polygons(host.parse_contours(polys, host.find_outer_index(polys)))
-        nodes, tris = synth.delaunay_mesh((20, 40, 490, 470), 1.43, seed=0)
+        nodes, tris_all = synth.delaunay_mesh((20, 40, 490, 470), 1.43, seed=0)
+        t0_, t1_ = sharded.shard_range(len(tris_all), world, rank)   # polygon table replicated, no collective on the data path
+        tris = tris_all[t0_:t1_]
         dm = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (nodes, tris, xy, off, pcls)]
+        if world > 1:
+            dist.barrier()
         for _ in range(3):
             cls_gpu = ops.tri_label(*dm)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -379,8 +383,12 @@ def run_b200(args):
         b.record()
         torch.cuda.synchronize(dev)
         ms_mesh = a.elapsed_time(b) / 10
-        mesh = {"triangles": int(len(tris)), "polygons": int(len(pcls)), "polygon_vertices": int(len(xy)),
-                "ms": ms_mesh, "elements_per_sec": len(tris) / (ms_mesh / 1e3),
+        if world > 1:
+            tm = torch.tensor([ms_mesh], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms_mesh = float(tm)
+        mesh = {"triangles": int(len(tris_all)), "triangles_per_gpu": int(len(tris)), "polygons": int(len(pcls)),
+                "polygon_vertices": int(len(xy)), "ms": ms_mesh, "elements_per_sec": len(tris_all) / (ms_mesh / 1e3),
                 "class_histogram": torch.bincount(cls_gpu, minlength=5).tolist()}
         # the raster look-up the north star also names (centroid pixel of the label map), against the
         # reference's polygon semantics on the same mesh
@@ -390,9 +398,9 @@ def run_b200(args):
             ops.tri_label_raster(dm[0], dm[1], code_m[0].contiguous())
         b.record()
         torch.cuda.synchronize(dev)
-        mesh["raster_mode"] = {"ms": a.elapsed_time(b) / 10, "elements_per_sec": len(tris) / (a.elapsed_time(b) / 10 / 1e3),
+        mesh["raster_mode"] = {"ms": a.elapsed_time(b) / 10, "elements_per_sec_per_gpu": len(tris) / (a.elapsed_time(b) / 10 / 1e3),
                                "disagreement_vs_polygon_mode": float((cls_raster != cls_gpu).float().mean())}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and rank == 0:
             from oracle import tri_label as TL                      # CPU baseline leg: the C restatement, one core
             nb = min(20000, len(tris))
             t0 = time.perf_counter()
