@@ -71,3 +71,15 @@ def test_tri_label_oracle_c_vs_python_on_a_real_polygon_set():
     pxy, poff, pcls, _ = TL.prepare_polygons(contours)
     nodes, tri = synth.delaunay_mesh((40, 60, 470, 440), 22.0, seed=2)
     assert np.array_equal(TL.label_triangles(nodes, tri, pxy, poff, pcls), TL.label_triangles_py(nodes, tri, pxy, poff, pcls))
+
+
+def test_config_surface_keeps_the_reference_names():
+    """kt_service_config.py:1-13 and ai_fsi_config.toml:1-9 of the reference: same attribute / key names."""
+    from eitsynthai_b200.kt_service import config, kt_service_config as c
+    for name in ("ribs_segm_model", "axial_slice_segm_model_256", "axial_slice_segm_model_512"):
+        assert getattr(c, name).endswith("_best.pt")
+    assert c.service_version == "1.0" and c.save_log_path == ["ai_logs"] and c.device == ""
+    cfg = config.load()
+    assert set(cfg["main_settings"]) >= {"service_version", "save_log_path"}
+    assert set(cfg["ai_settings"]) >= {"device", "weights_ribs", "weights_segmentation"}
+    assert config.device() == "cuda:0"
