@@ -154,7 +154,8 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rate, sample, ms = cpu_path_rate(120.0, threads, max(args.steps, 1), min(args.warmup, 1))
+    budget = float(os.environ.get("EITB_REF_BUDGET_S", "120"))    # whole run, all steps; bounded so the arm ends in minutes
+    rate, sample, ms = cpu_path_rate(budget, threads, max(args.steps, 1), min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
