@@ -116,8 +116,17 @@ def get_axial_slice_body_mask_nii(hu_img):
 
 
 def apply_body_mask(norm_u8, body_mask):
-    """cv2.bitwise_and(x, x, mask=m) of ai_tools.py:212 (fused into K1 on the batched path)."""
-    return np.where(np.asarray(body_mask) != 0, norm_u8, 0).astype(np.uint8)
+    """cv2.bitwise_and(x, x, mask=m) of ai_tools.py:212 (fused into K1 on the batched path); on the device."""
+    try:
+        img, m = _to_dev(norm_u8, np.uint8), _to_dev(body_mask, np.uint8)
+        return _masked(img, m).cpu().numpy()
+    except Exception as e:
+        logger.error(f"apply_body_mask failed: {e}")
+        return []
+
+
+def _masked(img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    return torch.where(mask != 0, img, torch.zeros_like(img))
 
 
 # ---------------------------------------------------------------------------- a2 / a3
@@ -200,11 +209,15 @@ def create_segmentations_masks(results, img_size=512):
         return {}
 
 
-def _codes_from_class_images(d):
-    code = np.zeros(next(iter(d.values())).shape[:2], np.uint8)
-    for name, val in (("bone", 7), ("muscles", 1), ("lung", 6), ("adipose", 3)):       # saturating add == OR of codes
+def _codes_from_class_images(d, device) -> torch.Tensor:
+    """overlay_segmentation_masks (utils.py:395-434) on the device: the saturating colour adds of the four
+    class images are the OR of their 3-bit colour codes.  Returns the (S, S) u8 code image."""
+    code = None
+    for name, val in (("bone", 7), ("muscles", 1), ("lung", 6), ("adipose", 3)):
         if name in d:
-            code[np.any(d[name] > 0, axis=2)] |= val
+            img = torch.from_numpy(np.ascontiguousarray(d[name])).to(device)
+            hit = (img > 0).any(dim=2).to(torch.uint8) * val
+            code = hit if code is None else torch.bitwise_or(code, hit)
     return code
 
 
@@ -214,7 +227,7 @@ def create_color_output(segmentation_masks_image, only_body_mask=None):
     try:
         if segmentation_masks_image is None or len(segmentation_masks_image) == 0:
             return None
-        code = _to_dev(_codes_from_class_images(segmentation_masks_image)[None], np.uint8)
+        code = _codes_from_class_images(segmentation_masks_image, _dev())[None].contiguous()
         body = None if only_body_mask is None else _to_dev(np.asarray(only_body_mask)[None], np.uint8)
         ops.label_cleanup(code, body)
         return ops.codes_to_bgr(code)[0].cpu().numpy()
