@@ -245,7 +245,7 @@ def run_b200(args):
         maps and of the selected indices inside the step."""
         return runner.step_host(px_host, labels_host)
 
-    rows_pin = runner.rows_pin
+    rows_bytes = runner.rows_dev.numel() * 2
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -296,7 +296,7 @@ def run_b200(args):
     if not args.no_e2e:
         ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
         e2e = {"value": total_slices / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(px_host.numel() * 2 + rows_pin.numel() * 2), "d2h_bytes_per_step": int(labels_host.numel() + S * 16)}
+               "h2d_bytes_per_step": int(px_host.numel() * 2 + rows_bytes), "d2h_bytes_per_step": int(labels_host.numel() + S * 16)}
 
     # ---------------------------------------------------------------- roofline of the dominant own kernel
     peaks = {}

@@ -40,6 +40,8 @@ SIGNATURES = {
     "eitb_body_mask": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "eitb_cc_label": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "eitb_front_rows": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "eitb_front_rows_batch": (_i, [_p, C.c_longlong, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "eitb_rows_h2d": (_i, [_p, C.c_longlong, _i, _i, _i, _p, _p]),
     "eitb_minmax_u8": (_i, [_p, _i64, _p, _p, _p]),
     "eitb_letterbox_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "eitb_rib_select": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),
@@ -54,8 +56,13 @@ SIGNATURES = {
     "eitb_bias_act_nhwc": (_i, [_p, _i, C.c_longlong, _i, _p, _i, _p]),
     "eitb_conv_epilogue_nhwc": (_i, [_p, _i, C.c_longlong, _i, _p, _i, _p, _p, _p, _i, _i, _p]),
     "eitb_upsample2x_concat_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "eitb_yolo_head_decode": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "eitb_yolo_head_decode": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "eitb_sppf_pool_concat": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "eitb_conv2d_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "eitb_conv2d_tuning": (_i, [_i, _i, _i]),
+    "eitb_conv2d_debug": (_i, [_i]),
+    "eitb_stem_conv3x3s2_nhwc": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _i, _p]),
+    "eitb_dwconv3x3_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p]),
     "eitb_tri_label_workspace_bytes": (_sz, [_i]),
     "eitb_tri_label": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _p, _p, _sz, _p]),
     "eitb_tri_label_raster": (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _p, _p]),

@@ -121,3 +121,16 @@ extern "C" int eitb_codes_to_bgr(const uint8_t* code, uint8_t* bgr, int64_t n, e
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Host path of K3: the coronal image needs one row of every slice.  Ship exactly those rows
+// from the pinned host series with one strided DMA (no CPU gather, no staging copy): row `row` of each of
+// n_slices [H,W] int16 slices -> dev_rows [n_slices, W].
+extern "C" int eitb_rows_h2d(const int16_t* host_px, long long n_slices, int H, int W, int row, int16_t* dev_rows,
+                             eitb_stream_t stream) {
+    if (!host_px || !dev_rows || n_slices < 0 || H <= 0 || W <= 0 || row < 0 || row >= H) return EITB_ERR_BAD_ARG;
+    if (n_slices == 0) return EITB_OK;
+    const cudaError_t e = cudaMemcpy2DAsync(dev_rows, (size_t)W * 2, host_px + (size_t)row * W, (size_t)H * W * 2, (size_t)W * 2,
+                                            (size_t)n_slices, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? EITB_OK : EITB_ERR_LAUNCH;
+}

@@ -25,7 +25,7 @@ struct HeadLevel {
 struct HeadArgs { HeadLevel lv[3]; };
 
 __global__ void __launch_bounds__(128)
-head_decode_kernel(HeadArgs args, int B, int nc, int nm, int A, __half* __restrict__ head) {
+head_decode_kernel(HeadArgs args, int B, int nc, int nm, int A, int cls_cstride, __half* __restrict__ head) {
     const int C = 4 + nc + nm;
     const long long total = (long long)B * A;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -67,7 +67,7 @@ head_decode_kernel(HeadArgs args, int B, int nc, int nm, int A, __half* __restri
         o[(long long)A] = __float2half_rn((y1 + y2) * 0.5f * st);
         o[(long long)2 * A] = __float2half_rn((x2 - x1) * st);
         o[(long long)3 * A] = __float2half_rn((y2 - y1) * st);
-        const __half* cp = L.cls + pix * nc;
+        const __half* cp = L.cls + pix * cls_cstride;
         for (int c = 0; c < nc; ++c) {
             const float z = __half2float(__ldg(cp + c)) + (L.bcls ? __ldg(L.bcls + c) : 0.f);
             o[(long long)(4 + c) * A] = __float2half_rn(1.f / (1.f + __expf(-z)));
@@ -133,10 +133,11 @@ sppf_kernel(const __half* __restrict__ x, int h, int w, int C, __half* __restric
 
 extern "C" int eitb_yolo_head_decode(const void* const* box, const void* const* cls, const void* const* mc,
                                      const float* const* box_bias, const float* const* cls_bias, const float* const* mc_bias,
-                                     const int* hs, const int* ws, const int* strides, int B, int nc, int nm, void* head,
-                                     eitb_stream_t stream) {
+                                     const int* hs, const int* ws, const int* strides, int B, int nc, int nm, int cls_cstride,
+                                     void* head, eitb_stream_t stream) {
     if (!box || !cls || !mc || !hs || !ws || !strides || !head || B < 0 || nc <= 0 || nm < 0) return EITB_ERR_BAD_ARG;
-    if (nm % 8) return EITB_ERR_UNSUPPORTED;
+    if (nm % 8 || (cls_cstride && cls_cstride < nc)) return EITB_ERR_UNSUPPORTED;
+    if (!cls_cstride) cls_cstride = nc;
     HeadArgs a;
     int A = 0;
     for (int l = 0; l < 3; ++l) {
@@ -149,7 +150,7 @@ extern "C" int eitb_yolo_head_decode(const void* const* box, const void* const* 
     if (B == 0) return EITB_OK;
     cudaStream_t s = (cudaStream_t)stream;
     eitb_prof_begin("head_decode_kernel", s);
-    head_decode_kernel<<<eitb_grid((long long)B * A, 128, 12), 128, 0, s>>>(a, B, nc, nm, A, (__half*)head);
+    head_decode_kernel<<<eitb_grid((long long)B * A, 128, 12), 128, 0, s>>>(a, B, nc, nm, A, cls_cstride, (__half*)head);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

@@ -1,0 +1,536 @@
+// K11: the convolutions of the YOLO11s-seg networks (reference: the models loaded at
+// kt_service/ai_tools/ai_tools.py:69-71 and called at :121-122,153) as an implicit GEMM on the
+// 5th-generation tensor cores, with the whole Conv epilogue (folded-BatchNorm bias, SiLU, Bottleneck
+// residual, write into a channel slice of a concat buffer) fused.  NHWC fp16 in, fp32 accumulate
+// in TMEM, fp16 out.  Replaces cuDNN's convolution + the separate K9 read-modify-write pass.
+//
+//   M = 128 output pixels per tile: a (tn images) x (th rows) x (tw columns) box of one feature map
+//   N = up to 256 output channels per tile (one tcgen05.mma N)
+//   K = taps x Cin, walked as (tap, chunk of Kc <= 64 channels): every step is
+//         A  [128 px][Kc]  TMA box of the input, shifted by the tap offset; out-of-range
+//                          coordinates (the zero padding, and tiles that overhang the map) are
+//                          zero-filled by the TMA unit; stride-2 layers use the box traversal stride
+//         B  [N ch][Kc]    TMA box of the pre-packed weights  [tap][Cout][Cin]
+//       both land in shared memory in the K-major swizzled layout tcgen05.mma reads directly.
+//
+// Warp roles (persistent CTA, one per SM):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2..9 = epilogue (TMEM -> registers -> bias/SiLU/residual -> fp16 -> swizzled staging
+// tile -> TMA store).  Two accumulator stages in TMEM let the MMAs of tile i+1 run under the
+// epilogue of tile i; the shared-memory ring is 3..8 stages deep.
+#include "common.cuh"
+#include <cuda.h>        // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
+#include <mutex>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kMaxHalo = 4;
+
+struct ConvArgs {
+    int taps, ksize, stride, kchunks, Kc;
+    int ntile, n_tiles, slabC, slabs;
+    int tw, th, tn, tiles_x, tiles_y, tiles_b;
+    int total_tiles;
+    int Cout, act, has_res, stages;
+    int a_bytes, b_bytes, stage_bytes, slab_bytes;
+    int swz_ab, swz_out;               // 16-byte-chunk xor masks: 7 (128B rows), 3 (64B), 1 (32B)
+    int tmem_cols;
+    int dbg;                           // experiments: 1 no TMA store, 2 no staging writes, 8 halo descriptors carry base_offset = tap column
+    int halo, WB, HB, halo_bytes, halo_tx, halo_stages;   // halo mode (3x3, stride 1): input tile + 1-pixel frame staged once per K chunk
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major operand tile in shared memory: rows of `row_bytes` (one swizzle span), 8-row groups back to back
+// `group_bytes`: distance between consecutive 8-row groups (8 * row_bytes when the tile is dense)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int row_bytes, int group_bytes, int base_offset) {
+    const uint64_t layout = row_bytes == 128 ? 2 : row_bytes == 64 ? 4 : 6;     // SWIZZLE_128B / 64B / 32B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;                                   // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)((group_bytes >> 4) & 0x3fff) << 32;       // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+    d |= (uint64_t)(base_offset & 7) << 49;
+    d |= layout << 61;
+    return d;
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v);
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+// CT = output channels per epilogue thread and half slab (slabC / 2): 8, 16 or 32.
+// EW = epilogue warps: 8 ("heavy": one CTA per SM, N up to 256, deep ring) or 4 ("light": two CTAs per SM for
+// layers with <= 128 output channels, which are bandwidth-bound: twice the loads in flight and two
+// independent epilogues per SM).
+template <int CT, int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, EW == 8 ? 1 : 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
+               const float* __restrict__ bias, const ConvArgs p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // dynamic shared memory is only 16-byte aligned by contract: align the operand buffers by hand
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* halo = smem;                                            // halo_stages x input halo tile (halo mode)
+    unsigned char* ring = halo + (size_t)p.halo_stages * p.halo_bytes;     // stages x (A | B)   [halo mode: B only]
+    unsigned char* staging = ring + (size_t)p.stages * p.stage_bytes;      // 2 x slab
+    float* sbias = reinterpret_cast<float*>(staging + 2 * (size_t)p.slab_bytes);       // [n_tiles * ntile]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.n_tiles * p.ntile);
+    // bars: full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | res_full[2] | halo_full[4] | halo_empty[4]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kMaxStages, bar_tempty = bar_tfull + 16, bar_res = bar_tempty + 16;
+    const uint32_t bar_hfull = bar_res + 16, bar_hempty = bar_hfull + 8 * kMaxHalo;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6 + 2 * kMaxHalo);
+
+    constexpr int kThreads = (2 + EW) * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < p.halo_stages; ++s) { mbar_init(bar_hfull + 8 * s, 1); mbar_init(bar_hempty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EW); mbar_init(bar_res + 8 * a, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = threadIdx.x; i < p.n_tiles * p.ntile; i += kThreads) sbias[i] = (bias && i < p.Cout) ? bias[i] : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot;
+    const int row_bytes = p.Kc * 2;
+
+    if (warp == 0) {
+        // ================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int hs = 0; uint32_t hphase = 0;
+            const int pad = p.ksize >> 1;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+                const int bx = mt % p.tiles_x, by = (mt / p.tiles_x) % p.tiles_y, bb = mt / (p.tiles_x * p.tiles_y);
+                if (p.halo) {
+                    // one halo tile per K chunk feeds all nine taps; only the weights stream through the ring
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(bar_hempty + 8 * hs, hphase ^ 1);
+                        mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)p.halo_tx);
+                        tma_load_4d(smem_u32(halo + (size_t)hs * p.halo_bytes), &map_x, kc * p.Kc, bx * p.tw - 1, by * p.th - 1, bb,
+                                    bar_hfull + 8 * hs);
+                        if (++hs == p.halo_stages) { hs = 0; hphase ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)p.b_bytes);
+                            tma_load_3d(smem_u32(ring + (size_t)stage * p.stage_bytes), &map_w, kc * p.Kc, nt * p.ntile, tap,
+                                        bar_full + 8 * stage);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int r = tap / p.ksize, s = tap - r * p.ksize;
+                    const int cx = bx * p.tw * p.stride - pad + s, cy = by * p.th * p.stride - pad + r;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t a_dst = smem_u32(ring + (size_t)stage * p.stage_bytes);
+                        mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.a_bytes + p.b_bytes));
+                        tma_load_4d(a_dst, &map_x, kc * p.Kc, cx, cy, bb * p.tn, bar_full + 8 * stage);
+                        tma_load_3d(a_dst + p.a_bytes, &map_w, kc * p.Kc, nt * p.ntile, tap, bar_full + 8 * stage);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int hs = 0; uint32_t hphase = 0;
+            // instruction descriptor: D fp32, A/B fp16, both K-major, N = ntile, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const int iters = p.taps * p.kchunks;
+            int local = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
+                const int acc = local & 1;
+                mbar_wait(bar_tempty + 8 * acc, (uint32_t)((local >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t d_tmem = tmem + (uint32_t)(acc * p.ntile);
+                if (p.halo) {
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(bar_hfull + 8 * hs, hphase);
+                        const uint32_t h_addr = smem_u32(halo + (size_t)hs * p.halo_bytes);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int r = tap / 3, s = tap - r * 3;
+                            mbar_wait(bar_full + 8 * stage, phase);
+                            asm volatile("tcgen05.fence::after_thread_sync;");
+                            // tile row y = 8 consecutive halo pixels starting at (y + r, s): 8-row groups WB pixels apart
+                            const uint64_t da = make_desc(h_addr + (uint32_t)((r * p.WB + s) * row_bytes), row_bytes, p.WB * row_bytes,
+                                                          (p.dbg & 8) ? s : 0);
+                            const uint64_t db = make_desc(smem_u32(ring + (size_t)stage * p.stage_bytes), row_bytes, 8 * row_bytes, 0);
+                            for (int k = 0; k < p.Kc / 16; ++k) {
+                                const uint32_t accum = (kc | tap | k) != 0;
+                                asm volatile(
+                                    "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
+                                    ::"r"(d_tmem), "l"(da + (uint64_t)(k * 2)), "l"(db + (uint64_t)(k * 2)), "r"(idesc), "r"(accum));
+                            }
+                            umma_commit(bar_empty + 8 * stage);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit(bar_hempty + 8 * hs);                  // halo tile free when its 9 x Kc/16 MMAs retire
+                        if (++hs == p.halo_stages) { hs = 0; hphase ^= 1; }
+                    }
+                } else {
+                    for (int it = 0; it < iters; ++it) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        const uint32_t a_addr = smem_u32(ring + (size_t)stage * p.stage_bytes);
+                        const uint64_t da = make_desc(a_addr, row_bytes, 8 * row_bytes, 0);
+                        const uint64_t db = make_desc(a_addr + p.a_bytes, row_bytes, 8 * row_bytes, 0);
+                        for (int k = 0; k < p.Kc / 16; ++k) {
+                            const uint32_t accum = (it | k) != 0;
+                            asm volatile(
+                                "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
+                                ::"r"(d_tmem), "l"(da + (uint64_t)(k * 2)), "l"(db + (uint64_t)(k * 2)), "r"(idesc), "r"(accum));
+                        }
+                        umma_commit(bar_empty + 8 * stage);                // frees the ring slot when these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit(bar_tfull + 8 * acc);                          // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ================================================================== epilogue (EW warps)
+        const int ew = warp - 2;
+        const int q = warp & 3;                                            // TMEM lane quadrant this warp may read
+        const int half0 = EW == 8 ? ew >> 2 : 0;                           // 8 warps: each takes one half of a slab's channels
+        constexpr int kHalfStep = EW == 8 ? 2 : 1;                         // 4 warps: both halves, one after the other
+        const int row = q * 32 + lane;                                     // pixel row of the tile = TMEM lane
+        const bool leader = threadIdx.x == 64;
+        int local = 0;
+        uint32_t slab_count = 0;                                           // staging buffers used so far (parity of res_full)
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+            const int bx = mt % p.tiles_x, by = (mt / p.tiles_x) % p.tiles_y, bb = mt / (p.tiles_x * p.tiles_y);
+            mbar_wait(bar_tfull + 8 * acc, (uint32_t)((local >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int sl = 0; sl < p.slabs; ++sl, ++slab_count) {
+                const int buf = slab_count & 1;
+                unsigned char* stg = staging + (size_t)buf * p.slab_bytes;
+                const int c_slab = nt * p.ntile + sl * p.slabC;            // first output channel of this slab
+                if (c_slab >= p.Cout) break;                               // padded channels of the last tile (warp-uniform)
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read `buf` is done
+                asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+                if (p.has_res) {
+                    if (leader) {
+                        mbar_expect_tx(bar_res + 8 * buf, (uint32_t)p.slab_bytes);
+                        tma_load_4d(smem_u32(stg), &map_r, c_slab, bx * p.tw, by * p.th, bb * p.tn, bar_res + 8 * buf);
+                    }
+                    mbar_wait(bar_res + 8 * buf, (slab_count >> 1) & 1);
+                }
+#pragma unroll 1
+                for (int half = half0; half < 2; half += kHalfStep) {
+                uint32_t v[CT];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.ntile + sl * p.slabC + half * CT);
+                tmem_ld<CT>(taddr, v);
+                // this thread's CT/8 16-byte chunks of a staging row, swizzled like the TMA store expects
+                uint32_t soff[CT / 8];
+#pragma unroll
+                for (int j = 0; j < CT / 8; ++j) {
+                    const uint32_t byte = (uint32_t)(row * (p.slabC * 2) + (half * CT + j * 8) * 2);
+                    soff[j] = byte ^ (((byte >> 7) & (uint32_t)p.swz_out) << 4);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float x[CT];
+                const float4* bs = reinterpret_cast<const float4*>(sbias + c_slab + half * CT);
+#pragma unroll
+                for (int i = 0; i < CT / 4; ++i) {
+                    const float4 b4 = bs[i];                               // same address in every lane: broadcast
+                    x[4 * i] = __uint_as_float(v[4 * i]) + b4.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+                    x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+                }
+                if (p.act) {
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) {                         // SiLU: x * 1/(1 + 2^(-x log2 e)), 32 independent chains
+                        float e;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x[i] * -1.4426950408889634f));
+                        float rcp;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(1.f + e));
+                        x[i] *= rcp;
+                    }
+                }
+                if (p.has_res) {
+#pragma unroll
+                    for (int j = 0; j < CT / 8; ++j) {
+                        const int4 rv = *reinterpret_cast<const int4*>(stg + soff[j]);
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 rf = __half22float2(rh[e]);
+                            x[8 * j + 2 * e] += rf.x; x[8 * j + 2 * e + 1] += rf.y;
+                        }
+                    }
+                }
+                if (!(p.dbg & 2)) {
+#pragma unroll
+                    for (int j = 0; j < CT / 8; ++j) {
+                        int4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(x[8 * j + 2 * e], x[8 * j + 2 * e + 1]);
+                        *reinterpret_cast<int4*>(stg + soff[j]) = o;
+                    }
+                }
+                }                                                          // half
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA store reads
+                asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+                if (leader && !(p.dbg & 1)) {
+                    tma_store_4d(&map_y, smem_u32(stg), c_slab, bx * p.tw, by * p.th, bb * p.tn);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);              // this warp has drained the accumulator
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols));
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int row_bytes) {
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// NHWC fp16 view {C, W, H, N} of `c` channels starting at `base`; pixel stride `ctot` channels;
+// (sx, sy) place the W/H axes on every sx-th / sy-th pixel of a (Wfull x Hfull) map (transposed convolution)
+bool encode_act(CUtensorMap* m, const void* base, int c, int W, int H, int N, int ctot, long long row_stride_px,
+                long long img_stride_px, int px_stride, int box_c, int box_w, int box_h, int box_n, int estride) {
+    const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)px_stride * ctot * 2, (cuuint64_t)row_stride_px * ctot * 2,
+                                   (cuuint64_t)img_stride_px * ctot * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), (cuuint32_t)box_n};
+    const cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    return encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_ntile_max = 256, g_stage_cap = kMaxStages, g_grid_cap = EITB_NUM_SMS, g_dbg = 0, g_halo = 1, g_light = 1;
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+// bit 4 (16) turns halo mode off, bit 5 (32) the two-CTAs-per-SM configuration; the others are ConvArgs::dbg
+extern "C" int eitb_conv2d_debug(int flags) { g_dbg = flags & ~48; g_halo = !(flags & 16); g_light = !(flags & 32); return EITB_OK; }
+
+extern "C" int eitb_conv2d_tuning(int ntile_max, int stage_cap, int grid_cap) {
+    if (ntile_max >= 16) g_ntile_max = ntile_max;
+    if (stage_cap >= 2) g_stage_cap = stage_cap < kMaxStages ? stage_cap : kMaxStages;
+    if (grid_cap >= 1) g_grid_cap = grid_cap;
+    return EITB_OK;
+}
+
+extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_coff, int Cin,
+                                const void* w_packed, const float* bias, int Cout, int ksize, int stride, int act,
+                                const void* res, int res_ctot, int res_coff,
+                                void* y, int y_ctot, int y_coff, int y_up, int y_dy, int y_dx, eitb_stream_t stream) {
+    if (!x || !w_packed || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return EITB_ERR_BAD_ARG;
+    if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) || Cin % 16 || x_ctot % 8 || x_coff % 8 || y_ctot % 8 ||
+        y_coff % 8 || (res && (res_ctot % 8 || res_coff % 8)) || y_up < 1 || y_up > 2)
+        return EITB_ERR_UNSUPPORTED;
+    if (!encoder()) return EITB_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int pad = ksize / 2;
+    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+    const int cout_pad = (Cout + 15) / 16 * 16;
+
+    ConvArgs p{};
+    p.ksize = ksize; p.taps = ksize * ksize; p.stride = stride;
+    p.Kc = Cin % 64 == 0 ? 64 : Cin % 32 == 0 ? 32 : 16;
+    p.kchunks = Cin / p.Kc;
+    p.ntile = cout_pad < g_ntile_max ? cout_pad : g_ntile_max;
+    if (p.ntile > 64 && p.ntile % 64) p.ntile = p.ntile / 64 * 64;        // slabs of 64 channels
+    p.n_tiles = (cout_pad + p.ntile - 1) / p.ntile;
+    p.slabC = p.ntile < 64 ? p.ntile : 64;
+    if (p.slabC != 16 && p.slabC != 32 && p.slabC != 64) return EITB_ERR_UNSUPPORTED;
+    p.slabs = p.ntile / p.slabC;
+    p.tw = Wo >= 16 ? 16 : pow2_ceil(Wo);
+    p.th = pow2_ceil(Ho) < BM / p.tw ? pow2_ceil(Ho) : BM / p.tw;
+    p.tn = BM / (p.tw * p.th);
+    // halo mode: 3x3 stride-1 layers stage a (16+2) x (8+2 -> 16) pixel tile once per K chunk and take all nine taps
+    // from it (row y of the 16 x 8 output tile = 8 consecutive halo pixels = one 8-row group of the A operand)
+    p.halo = (g_halo && ksize == 3 && stride == 1 && Ho >= 9) ? 1 : 0;
+    if (p.halo) { p.tw = 8; p.th = 16; p.tn = 1; p.WB = 10; p.HB = 18; }
+    const bool light = g_light && p.ntile <= 128;                          // two CTAs per SM
+    p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th; p.tiles_b = (N + p.tn - 1) / p.tn;
+    const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+    if (total > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
+    p.total_tiles = (int)total;
+    p.Cout = Cout; p.act = act; p.has_res = res != nullptr; p.dbg = g_dbg;
+    p.a_bytes = BM * p.Kc * 2;
+    p.b_bytes = p.ntile * p.Kc * 2;
+    p.stage_bytes = ((p.halo ? 0 : p.a_bytes) + p.b_bytes + 1023) / 1024 * 1024;
+    p.halo_bytes = p.halo ? (p.WB * p.HB * p.Kc * 2 + 1023) / 1024 * 1024 : 0;
+    p.halo_tx = p.WB * p.HB * p.Kc * 2;
+    p.slab_bytes = BM * p.slabC * 2;
+    p.swz_ab = p.Kc == 64 ? 7 : p.Kc == 32 ? 3 : 1;
+    p.swz_out = p.slabC == 64 ? 7 : p.slabC == 32 ? 3 : 1;
+    p.tmem_cols = pow2_ceil(2 * p.ntile) < 32 ? 32 : pow2_ceil(2 * p.ntile);
+    const int fixed = 1024 /*alignment slack*/ + 2 * p.slab_bytes + p.n_tiles * p.ntile * 4 /*bias*/ + 512 /*barriers*/;
+    int avail = (light ? 113 : 227) * 1024 - fixed;
+    if (p.halo) {
+        // weights: one ring slot per tap in flight is plenty (they are L2 hits); the rest goes to halo tiles
+        p.stages = 4;
+        p.halo_stages = (avail - p.stages * p.stage_bytes) / p.halo_bytes;
+        if (p.halo_stages > kMaxHalo) p.halo_stages = kMaxHalo;
+        if (p.halo_stages < 1) return EITB_ERR_UNSUPPORTED;
+        avail -= p.halo_stages * p.halo_bytes;
+    }
+    p.stages = avail / p.stage_bytes;
+    if (p.stages > g_stage_cap) p.stages = g_stage_cap;
+    if (p.stages < 2) return EITB_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes + (size_t)p.halo_stages * p.halo_bytes;
+
+    alignas(64) CUtensorMap mx, mw, my, mr;
+    const char* xb = static_cast<const char*>(x) + (size_t)x_coff * 2;
+    if (p.halo) {
+        if (!encode_act(&mx, xb, Cin, W, H, N, x_ctot, W, (long long)H * W, 1, p.Kc, p.WB, p.HB, 1, 1)) return EITB_ERR_BAD_ARG;
+    } else if (!encode_act(&mx, xb, Cin, W, H, N, x_ctot, W, (long long)H * W, 1, p.Kc, p.tw, p.th, p.tn, stride)) {
+        return EITB_ERR_BAD_ARG;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)cout_pad, (cuuint64_t)p.taps};
+        const cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)cout_pad * Cin * 2};
+        const cuuint32_t box[3] = {(cuuint32_t)p.Kc, (cuuint32_t)p.ntile, 1};
+        const cuuint32_t es[3] = {1, 1, 1};
+        if (encoder()(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(w_packed), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.Kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return EITB_ERR_BAD_ARG;
+    }
+    {
+        // the output map sees (Wo x Ho) pixels placed on every y_up-th pixel of a (Wo*y_up x Ho*y_up) map, offset (dy, dx)
+        const int Wy = Wo * y_up, Hy = Ho * y_up;
+        char* yb = static_cast<char*>(y) + ((size_t)(y_dy * Wy + y_dx) * y_ctot + y_coff) * 2;
+        const int cvis = Cout < y_ctot - y_coff ? Cout : y_ctot - y_coff;
+        if (!encode_act(&my, yb, cvis, Wo, Ho, N, y_ctot, (long long)Wy * y_up, (long long)Hy * Wy, y_up, p.slabC, p.tw, p.th, p.tn, 1))
+            return EITB_ERR_BAD_ARG;
+    }
+    if (res) {
+        const char* rb = static_cast<const char*>(res) + (size_t)res_coff * 2;
+        if (!encode_act(&mr, rb, Cout, Wo, Ho, N, res_ctot, Wo, (long long)Ho * Wo, 1, p.slabC, p.tw, p.th, p.tn, 1)) return EITB_ERR_BAD_ARG;
+    } else {
+        mr = my;
+    }
+    const int cap = g_grid_cap * (light ? 2 : 1);
+    const int grid = p.total_tiles < cap ? p.total_tiles : cap;
+    auto launch = [&](auto kernel, int threads) -> int {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EITB_ERR_LAUNCH;
+        eitb_prof_begin("conv_tc_kernel", s);
+        kernel<<<grid, threads, smem, s>>>(mx, mw, my, mr, bias, p);
+        EITB_CHECK_LAUNCH();
+        return EITB_OK;
+    };
+    if (light) {
+        switch (p.slabC) {
+            case 64: return launch(conv_tc_kernel<32, 4>, 192);
+            case 32: return launch(conv_tc_kernel<16, 4>, 192);
+            default: return launch(conv_tc_kernel<8, 4>, 192);
+        }
+    }
+    switch (p.slabC) {
+        case 64: return launch(conv_tc_kernel<32, 8>, 320);
+        case 32: return launch(conv_tc_kernel<16, 8>, 320);
+        default: return launch(conv_tc_kernel<8, 8>, 320);
+    }
+}

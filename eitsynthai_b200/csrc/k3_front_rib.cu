@@ -12,7 +12,16 @@ namespace {
 // ---------------------------------------------------------------- front rows
 __global__ void __launch_bounds__(256)
 front_rows_kernel(const int16_t* __restrict__ px, const int32_t* __restrict__ order, int n, int H, int W,
-                  int row, int flip_x, int flip_z, int16_t* __restrict__ rows, int32_t* __restrict__ minmax) {
+                  int row, int flip_x, int flip_z, int16_t* __restrict__ rows, int32_t* __restrict__ minmax,
+                  const int32_t* __restrict__ geom, long long series_stride) {
+    if (geom) {                                          // batched form: blockIdx.y = series, per-series geometry
+        const int s = blockIdx.y;
+        row = geom[3 * s]; flip_x = geom[3 * s + 1]; flip_z = geom[3 * s + 2];
+        px += (long long)s * series_stride;
+        if (order) order += (long long)s * n;
+        rows += (long long)s * n * W;
+        minmax += 2 * s;
+    }
     const int upr = W / 8;                               // 16-byte units per row
     const long long n_units = (long long)n * upr;
     int mn = INT_MAX, mx = INT_MIN;
@@ -218,7 +227,22 @@ extern "C" int eitb_front_rows(const int16_t* px, const int32_t* order, int n, i
     if (n == 0) return EITB_OK;
     const long long units = (long long)n * (W / 8);
     eitb_prof_begin("front_rows_kernel", (cudaStream_t)stream);
-    front_rows_kernel<<<eitb_grid(units, 256, 4), 256, 0, (cudaStream_t)stream>>>(px, order, n, H, W, row, flip_x, flip_z, rows, minmax);
+    front_rows_kernel<<<eitb_grid(units, 256, 4), 256, 0, (cudaStream_t)stream>>>(px, order, n, H, W, row, flip_x, flip_z, rows, minmax,
+                                                                                  nullptr, 0);
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
+}
+
+extern "C" int eitb_front_rows_batch(const int16_t* px, long long series_stride, const int32_t* order, const int32_t* geom,
+                                     int S, int n, int H, int W, int16_t* rows, int32_t* minmax, eitb_stream_t stream) {
+    if (!px || !geom || !rows || !minmax || S < 0 || n < 0 || H <= 0 || W <= 0) return EITB_ERR_BAD_ARG;
+    if (W % 8 || S > 65535) return EITB_ERR_UNSUPPORTED;
+    if (n == 0 || S == 0) return EITB_OK;
+    const long long units = (long long)n * (W / 8);
+    int gx = eitb_grid(units, 256, 4);
+    if (gx > 8 && S >= 8) gx = 8;                        // many series: a few CTAs each already fill the chip
+    eitb_prof_begin("front_rows_kernel", (cudaStream_t)stream);
+    front_rows_kernel<<<dim3(gx, S), 256, 0, (cudaStream_t)stream>>>(px, order, n, H, W, 0, 0, 0, rows, minmax, geom, series_stride);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

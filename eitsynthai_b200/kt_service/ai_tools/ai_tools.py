@@ -32,12 +32,12 @@ logger = logging.getLogger(__name__)
 _PIPELINES = {}
 
 
-def _shared_pipeline(device) -> ImagingPipeline:
+def _shared_pipeline(device, ribs, axial256, axial512) -> ImagingPipeline:
     """The reference builds 5 pipeline objects x 3 models at import (main_kt_service.py:24-28);
-    one set of networks per device is enough."""
-    key = str(device)
+    one set of networks per (device, weight files) is enough."""
+    key = (str(device), ribs, axial256, axial512)
     if key not in _PIPELINES:
-        _PIPELINES[key] = ImagingPipeline(device)
+        _PIPELINES[key] = ImagingPipeline(device, weights={"ribs": ribs, "axial256": axial256, "axial512": axial512})
     return _PIPELINES[key]
 
 
@@ -50,12 +50,18 @@ def _tag(ds, t, default=None):
 
 class DICOMabc(abc.ABC):
     def __init__(self, ribs_model_path=None, axial_model_256_path=None, axial_model_512_path=None):
+        # a path passed explicitly must exist, as YOLO(path) would raise at ai_tools.py:69-71; the configured
+        # defaults fall back to seeded random-init networks with a warning when the files are not deployed
+        import os
+        for given in (ribs_model_path, axial_model_256_path, axial_model_512_path):
+            if given and not os.path.exists(given):
+                raise FileNotFoundError(f"model weights not found: {given}")
         self.ribs_model_path = ribs_model_path or kt_service_config.ribs_segm_model
         self.axial_model_256_path = axial_model_256_path or kt_service_config.axial_slice_segm_model_256
         self.axial_model_512_path = axial_model_512_path or kt_service_config.axial_slice_segm_model_512
         self.device = torch.device(config.device())
         utils.set_device(self.device)
-        self.pipeline = _shared_pipeline(self.device)
+        self.pipeline = _shared_pipeline(self.device, self.ribs_model_path, self.axial_model_256_path, self.axial_model_512_path)
         self.ribs_model = self.pipeline.ribs_model
         self.axial_model_256 = self.pipeline.axial_model_256
         self.axial_model_512 = self.pipeline.axial_model_512
@@ -74,18 +80,13 @@ class DICOMabc(abc.ABC):
         with zipfile.ZipFile(zip_buffer, "r") as zf:
             try:                                                   # uncompressed little-endian files: built-in reader
                 return dicom_io.create_dicom_dict(zf)
-            except dicom_io.UnsupportedTransferSyntax:
-                import pydicom                                     # compressed syntaxes need pydicom (+ pylibjpeg)
-                from pydicom.filebase import DicomBytesIO
-                series, custom = {}, 0
-                for name in zf.namelist():
-                    if name.endswith(".txt"):
-                        if name.endswith("custom_input.txt"):
-                            custom = int(zf.read(name).decode().strip() or 0)
-                        continue
-                    ds = pydicom.dcmread(DicomBytesIO(zf.read(name)))
-                    series.setdefault(ds.SeriesInstanceUID, []).append(ds)
-                return max(series.values(), key=len), custom
+            except dicom_io.UnsupportedTransferSyntax as e:
+                try:                                               # JPEG / JPEG-LS / J2K need pydicom (+ pylibjpeg)
+                    import pydicom
+                    from pydicom.filebase import DicomBytesIO
+                except ImportError:
+                    raise RuntimeError(f"transfer syntax {e} needs pydicom + pylibjpeg, which are not installed") from e
+                return dicom_io.create_dicom_dict(zf, reader=lambda b: pydicom.dcmread(DicomBytesIO(b)))
 
     def _series_arrays(self, i_slices):
         from . import dicom_io

@@ -221,20 +221,37 @@ def write_dicom(pixel_array: np.ndarray, instance_number: int = 1, series_uid: s
 
 
 # ------------------------------------------------------------------------------------------ series level
-def create_dicom_dict(zip_file: zipfile.ZipFile):
-    """utils.py:26-70: every member not ending in ``.txt`` is a DICOM file; group by SeriesInstanceUID;
-    return the largest series (file order) and ``int(custom_input.txt)`` (0 when absent)."""
+def create_dicom_dict(zip_file: zipfile.ZipFile, reader=None):
+    """utils.py:26-70: every member not ending in ``.txt`` is tried as a DICOM file; a member that does not
+    parse (DICOMDIR, ``__MACOSX/._*`` resource forks, stray json, truncated files) is logged and skipped, as the
+    reference's per-file try/except does (utils.py:52-60); group by SeriesInstanceUID; return the largest
+    series (file order) and ``int(custom_input.txt)`` (0 when absent; the member must be named exactly so,
+    utils.py:46).  Only a compressed transfer syntax aborts (``UnsupportedTransferSyntax``): the caller then
+    retries with a decoder that has the codecs (``reader``)."""
+    import logging
+    log = logging.getLogger(__name__)
+    reader = reader or read_dicom
     series, custom = {}, 0
     for name in zip_file.namelist():
         if name.endswith("/"):
             continue
         if name.endswith(".txt"):
-            if name.endswith("custom_input.txt"):
-                txt = zip_file.read(name).decode().strip()
-                custom = int(txt) if txt else 0
+            if name == "custom_input.txt":
+                try:
+                    txt = zip_file.read(name).decode().strip()
+                    custom = int(txt) if txt else 0
+                except Exception as e:
+                    log.error(f"custom_input.txt unreadable: {e}")
             continue
-        ds = read_dicom(zip_file.read(name))
-        series.setdefault(ds.SeriesInstanceUID, []).append(ds)
+        try:
+            ds = reader(zip_file.read(name))
+            uid = ds.SeriesInstanceUID
+        except UnsupportedTransferSyntax:
+            raise
+        except Exception as e:
+            log.error(f"skipping archive member {name}: {e}")
+            continue
+        series.setdefault(uid, []).append(ds)
     if not series:
         return [], custom
     return max(series.values(), key=len), custom

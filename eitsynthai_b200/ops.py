@@ -102,6 +102,36 @@ def front_rows(px: torch.Tensor, order: torch.Tensor | None, n: int, row: int, f
     return rows, minmax
 
 
+def front_rows_batch(px: torch.Tensor, order: torch.Tensor | None, geom: torch.Tensor, minmax: torch.Tensor | None = None):
+    """px [S,n,H,W] int16 (may be a view with its own series stride), order [S,n] int32, geom [S,3] int32
+    (row, flip_x, flip_z per series) -> rows [S,n,W] int16, minmax [S,2] int32: one launch for the batch."""
+    if not px.is_cuda or px.dtype != torch.int16 or px.dim() != 4 or not px[0].is_contiguous():
+        raise ValueError("px must be a CUDA int16 [S,n,H,W] tensor with contiguous series")
+    S, n, H, W = px.shape
+    _chk(geom, torch.int32, "geom")
+    if order is not None:
+        _chk(order, torch.int32, "order")
+    rows = torch.empty((S, n, W), dtype=torch.int16, device=px.device)
+    if minmax is None:
+        minmax = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=px.device).repeat(S, 1)
+    with torch.cuda.device(px.device):
+        cabi.call("eitb_front_rows_batch", px.data_ptr(), px.stride(0) if S > 1 else n * H * W, _ptr(order), geom.data_ptr(),
+                  S, n, H, W, rows.data_ptr(), minmax.data_ptr(), _stream(px))
+    return rows, minmax
+
+
+def rows_h2d(px_host: torch.Tensor, row: int, out: torch.Tensor) -> torch.Tensor:
+    """px_host [n,H,W] int16 pinned host tensor -> out [n,W] (device): row ``row`` of every slice, one strided DMA."""
+    if px_host.is_cuda or not px_host.is_pinned() or px_host.dtype != torch.int16 or not px_host.is_contiguous():
+        raise ValueError("px_host must be a contiguous pinned int16 host tensor")
+    n, H, W = px_host.shape
+    _chk(out, torch.int16, "out")
+    assert out.numel() == n * W
+    with torch.cuda.device(out.device):
+        cabi.call("eitb_rows_h2d", px_host.data_ptr(), n, H, W, row, out.data_ptr(), _stream(out))
+    return out
+
+
 def minmax_u8(rows: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
     _chk(rows, torch.int16, "rows")
     _chk(minmax, torch.int32, "minmax")
@@ -268,14 +298,14 @@ def upsample2x_concat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------ K10
-def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int, biases=None) -> torch.Tensor:
+def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int, biases=None, cls_cstride: int = 0) -> torch.Tensor:
     """Lists of the 3 per-level branch outputs (channels-last fp16 [B,64|nc|nm,h,w]) -> head [B,4+nc+nm,A].
     ``biases`` = (box, cls, mc) lists of per-level float32 bias vectors folded into the decode."""
     import ctypes as C
     cl = torch.channels_last
     B = box[0].shape[0]
     for t in list(box) + list(cls) + list(mc):
-        if not (t.is_cuda and t.dtype == torch.float16 and (t.is_contiguous(memory_format=cl) or t.shape[1] == 1)):
+        if not (t.is_cuda and t.dtype == torch.float16 and (cls_cstride or t.is_contiguous(memory_format=cl) or t.shape[1] == 1)):
             raise ValueError("branch outputs must be channels-last fp16 CUDA tensors")
     hs = (C.c_int * 3)(*[t.shape[2] for t in box])
     ws = (C.c_int * 3)(*[t.shape[3] for t in box])
@@ -290,7 +320,7 @@ def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int, biases=None) -> to
                 _chk(t, torch.float32, "bias")
         bb, cb, mb = (arr(g) for g in biases)
     with torch.cuda.device(head.device):
-        cabi.call("eitb_yolo_head_decode", arr(box), arr(cls), arr(mc), bb, cb, mb, hs, ws, st, B, nc, nm, head.data_ptr(),
+        cabi.call("eitb_yolo_head_decode", arr(box), arr(cls), arr(mc), bb, cb, mb, hs, ws, st, B, nc, nm, cls_cstride, head.data_ptr(),
                   _stream(head))
     return head
 

@@ -8,6 +8,8 @@ stream and the label maps come back the same way, chunk by chunk, so copies over
 """
 from __future__ import annotations
 
+import logging
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -15,6 +17,8 @@ import torch
 
 from . import host, ops
 from .yolo_seg import build_model
+
+logger = logging.getLogger(__name__)
 
 CONF = 0.3          # ai_tools.py:121,153
 IOU = 0.7           # ultralytics default
@@ -47,16 +51,44 @@ class ImagingPipeline:
     """Owns the three networks (rib, axial 256, axial 512 -- ai_tools.py:52,66-67) and scratch memory."""
 
     def __init__(self, device="cuda:0", dtype=torch.float16, seed: int = 0, calibrate: bool = True,
-                 mask_variant: int = 0):
+                 mask_variant: int = 0, weights: dict | None = None, engine: str = "eitb"):
+        """``weights``: {"ribs" | "axial256" | "axial512": checkpoint path} (ultralytics ``.pt`` or a state_dict
+        in its key layout, see ``weights.py``).  A network whose file exists is loaded with its real BatchNorm
+        statistics; the others are seeded random-init (the reference's files are not distributed) with the
+        class bias calibrated so that the post-process sees candidates.  ``engine``: "eitb" runs the networks
+        on libeitb200's own convolution kernels (K11/K12), "cudnn" through PyTorch/cuDNN + the K9 epilogue."""
         self.device = torch.device(device)
         self.dtype = dtype
         self.mask_variant = mask_variant
-        self.ribs_model = build_model(1, self.device, dtype, seed)
-        self.axial_model_512 = build_model(4, self.device, dtype, seed + 1)
-        self.axial_model_256 = build_model(4, self.device, dtype, seed + 2)
+        self.engine = engine
+        self.loaded = {}
+        weights = weights or {}
+
+        def make(key, nc, sd):
+            path = weights.get(key)
+            if path and os.path.exists(path):
+                from .weights import load_model
+                self.loaded[key] = path
+                return load_model(path, self.device, dtype, nc)
+            if path:
+                logger.warning("weights for %s not found at %s: seeded random-init network instead", key, path)
+            return build_model(nc, self.device, dtype, sd)
+
+        self.ribs_torch = make("ribs", 1, seed)
+        self.axial_512_torch = make("axial512", 4, seed + 1)
+        self.axial_256_torch = make("axial256", 4, seed + 2)
+        self._bind_engine()
         self.bias_shift = {}
         if calibrate:
             self._calibrate()
+
+    def _bind_engine(self):
+        if self.engine == "eitb" and self.dtype == torch.float16:
+            from .convnet import ConvNet
+            self.ribs_model, self.axial_model_512, self.axial_model_256 = (
+                ConvNet(self.ribs_torch), ConvNet(self.axial_512_torch), ConvNet(self.axial_256_torch))
+        else:
+            self.ribs_model, self.axial_model_512, self.axial_model_256 = self.ribs_torch, self.axial_512_torch, self.axial_256_torch
 
     # ------------------------------------------------------------------ random-init calibration
     @torch.no_grad()
@@ -64,16 +96,22 @@ class ImagingPipeline:
         """Random-init class heads score ~0: shift the class bias so ~1 % of the anchors
         of a phantom batch pass conf=0.3.  The shifts are reported by bench.py."""
         from . import synth
+        if len(self.loaded) == 3:
+            return
         px = torch.from_numpy(np.stack([synth.phantom_slice(s) for s in range(4)])).to(self.device)
         body = ops.body_mask(px, 1, -1024, True)
         _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype)
         x = x.contiguous(memory_format=torch.channels_last)
-        self.bias_shift["axial512"] = self.axial_model_512.shift_class_bias(x)
+        if "axial512" not in self.loaded:
+            self.bias_shift["axial512"] = self.axial_512_torch.shift_class_bias(x)
         x256 = torch.nn.functional.interpolate(x, size=(256, 256)).contiguous(memory_format=torch.channels_last)
-        self.bias_shift["axial256"] = self.axial_model_256.shift_class_bias(x256)
+        if "axial256" not in self.loaded:
+            self.bias_shift["axial256"] = self.axial_256_torch.shift_class_bias(x256)
+        if "ribs" in self.loaded:
+            return
         vol, inst = synth.phantom_series(64, seed=0)
         front = self.coronal(torch.from_numpy(vol).to(self.device), SeriesMeta(inst))
-        self.bias_shift["ribs"] = self.ribs_model.shift_class_bias(self._rib_input(front[None])[0], frac=0.004)
+        self.bias_shift["ribs"] = self.ribs_torch.shift_class_bias(self._rib_input(front[None])[0], frac=0.004)
 
     # ------------------------------------------------------------------ a2/a3: coronal image
     def coronal(self, px: torch.Tensor, meta: SeriesMeta, minmax: torch.Tensor | None = None,
@@ -239,9 +277,17 @@ class SeriesBatchRunner:
         self.nl = z1 - z0
         self.metas = metas
         dev = self.dev
-        self.orders = [torch.from_numpy(host.instance_order(m.instance_numbers)).to(dev) for m in metas]
-        m0 = metas[0]
-        self.row, self.fx, self.fz = host.front_geometry(size, m0.patient_position, m0.image_orientation, m0.patient_orientation)
+        self.orders = torch.from_numpy(np.stack([host.instance_order(m.instance_numbers) for m in metas])).to(dev)   # [S, nl]
+        # per-series geometry and rescale tags (a batch may mix orientations and scanners)
+        geo = [host.front_geometry(size, m.patient_position, m.image_orientation, m.patient_orientation) for m in metas]
+        # z is reversed AFTER the gather (a per-shard reversal would come out as [rev(shard0), rev(shard1), ...])
+        self.flip_z = [s for s, g in enumerate(geo) if g[2]]
+        self.geom = torch.tensor([[g[0], int(g[1]), 0] for g in geo], dtype=torch.int32, device=dev)
+        self.geom_row0 = self.geom.clone()
+        self.geom_row0[:, 0] = 0                                # host path ships only the coronal row of every slice
+        self.rows_of = [g[0] for g in geo]
+        self.rescale = [(m.rescale_slope, m.rescale_intercept) for m in metas]
+        self.uniform_rescale = len(set(self.rescale)) == 1
         self.timer = timer or _NullTimer()
         self.px = torch.empty((self.S, self.nl, size, size), dtype=torch.int16, device=dev)      # the resident batch
         self.flat = self.px.view(self.S * self.nl, size, size)
@@ -260,7 +306,6 @@ class SeriesBatchRunner:
         self.mine_idx = torch.tensor(self.mine, dtype=torch.int64, device=dev)
         self.rows_static = torch.zeros((self.S, n_slices, size), dtype=torch.int16, device=dev)
         self.mm_static = torch.zeros((self.S, 2), dtype=torch.int32, device=dev)
-        self.rows_pin = torch.empty((self.S, self.nl, 1, size), dtype=torch.int16).pin_memory()
         self.rows_dev = torch.empty((self.S, self.nl, 1, size), dtype=torch.int16, device=dev)
         self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.side = torch.cuda.Stream(dev)                      # the per-series decision runs beside the slice chunks
@@ -269,11 +314,20 @@ class SeriesBatchRunner:
 
     # ---------------------------------------------------------------- stages
     @torch.no_grad()
-    def slice_stage(self, px_chunk):
+    def slice_stage(self, px_chunk, a: int = 0, b: int | None = None):
+        """K2 .. K7 for the slices [a, b) of the flattened [S * n_local] batch."""
         t, pipe = self.timer, self.pipe
-        m = self.metas[0]
         with t("K2_body_mask"):
-            body = ops.body_mask(px_chunk, m.rescale_slope, m.rescale_intercept, True)
+            if self.uniform_rescale:
+                body = ops.body_mask(px_chunk, self.rescale[0][0], self.rescale[0][1], True)
+            else:                                               # per-series RescaleSlope / RescaleIntercept
+                body = torch.empty(px_chunk.shape, dtype=torch.uint8, device=self.dev)
+                b = a + px_chunk.shape[0] if b is None else b
+                s0 = a // self.nl
+                while s0 * self.nl < b:
+                    lo, hi = max(a, s0 * self.nl) - a, min(b, (s0 + 1) * self.nl) - a
+                    body[lo:hi] = ops.body_mask(px_chunk[lo:hi], self.rescale[s0][0], self.rescale[s0][1], True)
+                    s0 += 1
         with t("K1_hu_window_nchw"):
             _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=pipe.dtype, channels_last=True)
         with t("CNN_axial"):
@@ -287,16 +341,11 @@ class SeriesBatchRunner:
             ops.label_cleanup(code, body)
         return code, n
 
-    def rib_rows(self, px, src_row=None):
+    def rib_rows(self, px, row0: bool = False):
+        """One launch for the whole batch: the coronal row of every local slice of every series + per-series
+        (min, max).  ``row0``: ``px`` holds only that row of each slice ([S, n_local, 1, W], host path)."""
         with self.timer("K3_front_rows"):
-            rows = torch.empty((self.S, self.nl, self.size), dtype=torch.int16, device=self.dev)
-            mm = torch.empty((self.S, 2), dtype=torch.int32, device=self.dev)
-            mm[:, 0] = 2 ** 31 - 1
-            mm[:, 1] = -2 ** 31
-            for s in range(self.S):
-                r, _ = ops.front_rows(px[s], self.orders[s], self.nl, self.row if src_row is None else src_row,
-                                      self.fx, self.fz, mm[s])
-                rows[s] = r
+            rows, mm = ops.front_rows_batch(px, self.orders, self.geom_row0 if row0 else self.geom)
         return rows, mm
 
     @torch.no_grad()
@@ -317,10 +366,12 @@ class SeriesBatchRunner:
                 sel.index_copy_(0, self.mine_idx, ops.rib_select(boxes, k, 512.0))
         return sel
 
-    def rib_stage(self, px, graphed=False, src_row=None):
-        rows, mm = self.rib_rows(px, src_row)
+    def rib_stage(self, px, graphed=False, row0=False):
+        rows, mm = self.rib_rows(px, row0)
         with self.timer("C1_exchange"):
             rows_all, mm_all = self.sharded.gather_rows(rows, mm, self.n_slices)
+            for s_ in self.flip_z:                              # FFS / 'P' orientation: reverse the gathered z axis
+                rows_all[s_] = rows_all[s_].flip(0)
         if graphed and self.rib_graph is not None:
             self.rows_static.copy_(rows_all)
             self.mm_static.copy_(mm_all)
@@ -341,7 +392,7 @@ class SeriesBatchRunner:
     def step_eager(self):
         sel = self.rib_stage(self.px)
         for a, b in self.bounds:
-            self.slice_stage(self.flat[a:b])
+            self.slice_stage(self.flat[a:b], a, b)
         return sel
 
     def capture(self, warm: int = 2):
@@ -355,7 +406,7 @@ class SeriesBatchRunner:
         for a, b in self.bounds:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
-                o = self.slice_stage(self.flat[a:b])
+                o = self.slice_stage(self.flat[a:b], a, b)
             self.graphs.append(g)
             self.outs.append(o)
         g = torch.cuda.CUDAGraph()
@@ -368,15 +419,15 @@ class SeriesBatchRunner:
             self.graphs[ci].replay()
             return self.outs[ci]
         a, b = self.bounds[ci]
-        return self.slice_stage(self.flat[a:b])
+        return self.slice_stage(self.flat[a:b], a, b)
 
-    def _rib_on_side(self, px, src_row=None):
+    def _rib_on_side(self, px, row0=False):
         """The coronal decision is independent of the per-slice path and tiny (one image per series): run it
         on a side stream so its ~300 small launches hide under the chunk graphs."""
         main = torch.cuda.current_stream(self.dev)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            sel = self.rib_stage(px, graphed=True, src_row=src_row)
+            sel = self.rib_stage(px, graphed=True, row0=row0)
         sel.record_stream(main)
         return sel
 
@@ -397,8 +448,12 @@ class SeriesBatchRunner:
         self.copy_in.wait_stream(main)
         evs = []
         with torch.cuda.stream(self.copy_in):
-            self.rows_pin.copy_(px_host[:, :, self.row:self.row + 1, :])
-            self.rows_dev.copy_(self.rows_pin, non_blocking=True)
+            # strided DMA of the coronal rows straight from the pinned series: no CPU gather, no staging buffer
+            if len(set(self.rows_of)) == 1:
+                ops.rows_h2d(flat_host, self.rows_of[0], self.rows_dev.view(self.S * self.nl, self.size))
+            else:
+                for s_ in range(self.S):
+                    ops.rows_h2d(px_host[s_], self.rows_of[s_], self.rows_dev[s_].view(self.nl, self.size))
             ev_rows = torch.cuda.Event()
             ev_rows.record(self.copy_in)
             for a, b in self.bounds:
@@ -407,7 +462,7 @@ class SeriesBatchRunner:
                 e.record(self.copy_in)
                 evs.append(e)
         main.wait_event(ev_rows)
-        sel = self._rib_on_side(self.rows_dev, src_row=0)
+        sel = self._rib_on_side(self.rows_dev, row0=True)
         for ci, (a, b) in enumerate(self.bounds):
             main.wait_event(evs[ci])
             code, _ = self.run_chunk(ci)

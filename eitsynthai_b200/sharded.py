@@ -4,9 +4,9 @@ Every stage of the hot path is per-slice except the coronal image (one row per s
 global min/max), so a series is cut into contiguous z-ranges, one per rank, and
 the only exchange is
 
-  * all-gather of the per-slice coronal rows   (n_local x W int16 per series per rank)
-  * all-gather of the per-shard (min, max)     (2 int32 per series per rank)
-  * all-reduce of the selected slice indices   (4 int32 per series; series s is decided on rank s % world)
+  * one all-gather (``all_gather_into_tensor``) of the per-slice coronal rows (n_local x W int16 per series
+    per rank) together with the per-shard (min, max) (2 int32 per series per rank)
+  * one all-reduce of the selected slice indices (4 int32 per series; series s is decided on rank s % world)
 
 The plumbing below works on whatever ``torch.distributed`` backend is initialised (NCCL over
 NVLink on the box, gloo in the CPU tests) and on a single process without a process group.
@@ -35,26 +35,28 @@ def owner_of_series(s: int, world_size: int) -> int:
 
 
 def gather_rows(rows_local: torch.Tensor, minmax_local: torch.Tensor, n_slices: int):
-    """rows_local [S, n_local, W] int16 (this rank's z-range, sorted), minmax_local [S, 2] int32 ->
-    (rows [S, n_slices, W], minmax [S, 2]) identical on every rank."""
+    """rows_local [S, n_local, W] int16 (this rank's z-range, ascending z), minmax_local [S, 2] int32 ->
+    (rows [S, n_slices, W], minmax [S, 2]) identical on every rank.  ONE collective: rows and min/max travel
+    in the same byte buffer (neither NCCL nor gloo has a 16-bit integer type)."""
     rank, ws = world()
     if ws == 1:
         return rows_local, minmax_local
     S, nl, W = rows_local.shape
-    nmax = max(shard_range(n_slices, ws, r)[1] - shard_range(n_slices, ws, r)[0] for r in range(ws))
-    send = rows_local
-    if nl < nmax:                                      # ragged shards: pad to the largest
-        send = torch.zeros((S, nmax, W), dtype=rows_local.dtype, device=rows_local.device)
-        send[:, :nl] = rows_local
-    # neither NCCL nor gloo has a 16-bit integer type: ship the rows as bytes
-    send8 = send.contiguous().view(torch.uint8)
-    parts8 = [torch.empty_like(send8) for _ in range(ws)]
-    dist.all_gather(parts8, send8)
-    parts = [p.view(rows_local.dtype) for p in parts8]
-    mms = [torch.empty_like(minmax_local) for _ in range(ws)]
-    dist.all_gather(mms, minmax_local.contiguous())
-    rows = torch.cat([parts[r][:, :shard_range(n_slices, ws, r)[1] - shard_range(n_slices, ws, r)[0]] for r in range(ws)], 1)
-    mm = torch.stack(mms)                              # [ws, S, 2]
+    sizes = [shard_range(n_slices, ws, r)[1] - shard_range(n_slices, ws, r)[0] for r in range(ws)]
+    nmax = max(sizes)
+    row_bytes = S * nmax * W * 2
+    send = torch.zeros((row_bytes + S * 8,), dtype=torch.uint8, device=rows_local.device)
+    send[:row_bytes].view(torch.int16).view(S, nmax, W)[:, :nl] = rows_local          # ragged shards: padded to the largest
+    send[row_bytes:].view(torch.int32).view(S, 2).copy_(minmax_local)
+    recv = torch.empty((ws * (row_bytes + S * 8),), dtype=torch.uint8, device=rows_local.device)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.view(ws, row_bytes + S * 8)
+    parts = recv[:, :row_bytes].view(torch.int16).view(ws, S, nmax, W)
+    if all(sz == nmax for sz in sizes):
+        rows = parts.permute(1, 0, 2, 3).reshape(S, ws * nmax, W)
+    else:
+        rows = torch.cat([parts[r, :, :sizes[r]] for r in range(ws)], 1)
+    mm = recv[:, row_bytes:].view(torch.int32).view(ws, S, 2)
     minmax = torch.stack((mm[:, :, 0].min(0).values, mm[:, :, 1].max(0).values), 1).contiguous()
     return rows.contiguous(), minmax
 

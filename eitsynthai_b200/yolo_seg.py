@@ -397,11 +397,9 @@ class YOLO11sSeg(nn.Module):
         return shift
 
 
-def build_model(nc: int, device, dtype=torch.float16, seed: int = 0, fuse: bool = True) -> YOLO11sSeg:
-    g = torch.random.get_rng_state()
-    torch.manual_seed(seed)
-    m = YOLO11sSeg(nc).eval()
-    torch.random.set_rng_state(g)
+def finalize_model(m: YOLO11sSeg, device, dtype=torch.float16, fuse: bool = True) -> YOLO11sSeg:
+    """Fold BatchNorm, split/strip what the fused kernels take over, move to the device; inference only."""
+    m = m.eval()
     if fuse:
         for mod in m.modules():
             if isinstance(mod, Conv):
@@ -417,3 +415,12 @@ def build_model(nc: int, device, dtype=torch.float16, seed: int = 0, fuse: bool 
     for p in m.parameters():
         p.requires_grad_(False)
     return m
+
+
+def build_model(nc: int, device, dtype=torch.float16, seed: int = 0, fuse: bool = True) -> YOLO11sSeg:
+    """Seeded random-init network (the reference's weights are not distributed; see ``weights.load_model``)."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    m = YOLO11sSeg(nc).eval()
+    torch.random.set_rng_state(g)
+    return finalize_model(m, device, dtype, fuse)

@@ -113,6 +113,17 @@ int eitb_cc_label(const uint8_t* mask, int B, int H, int W, int connectivity, in
 int eitb_front_rows(const int16_t* px, const int32_t* order, int n, int H, int W, int row,
                     int flip_x, int flip_z, int16_t* rows, int32_t* minmax, eitb_stream_t stream);
 
+/* The same for S series in one launch (a batch of series, BASELINE configs[3]): series s starts at
+ * px + s*series_stride elements and has its own order row [S,n], geometry geom [S,3] int32 device
+ * (row, flip_x, flip_z), output rows [S,n,W] and minmax [S,2]. */
+int eitb_front_rows_batch(const int16_t* px, long long series_stride, const int32_t* order, const int32_t* geom,
+                          int S, int n, int H, int W, int16_t* rows, int32_t* minmax, eitb_stream_t stream);
+
+/* Host path: row `row` of each of n_slices [H,W] int16 slices in PINNED HOST memory -> dev_rows [n_slices,W],
+ * one strided DMA on `stream` (host_px is a host pointer). */
+int eitb_rows_h2d(const int16_t* host_px, long long n_slices, int H, int W, int row, int16_t* dev_rows,
+                  eitb_stream_t stream);
+
 /* cv2.normalize(front, None, 0, 255, NORM_MINMAX, CV_8U) (ai_tools.py:101) with OpenCV's
  * arithmetic: scale/shift in double, cast to float, one float FMA per pixel, round-half-even.
  *   minmax [2] int32 device pointer (from eitb_front_rows / an all-reduce). */
@@ -211,14 +222,45 @@ int eitb_upsample2x_concat_nhwc(const void* a, const void* b, void* out, int dty
  * [B,h_l,w_l,nc] class logits, mc[l] [B,h_l,w_l,nm] for the 3 levels (host arrays of device pointers,
  * sizes and strides) -> head [B,4+nc+nm,A] fp16: xywh in input pixels, sigmoid scores, coefficients.
  * box_bias / cls_bias / mc_bias: per-level device float32 bias vectors of the last convolution of each
- * branch, added on the fly (host arrays of 3 pointers, or NULL when the convolutions carry their bias). */
+ * branch, added on the fly (host arrays of 3 pointers, or NULL when the convolutions carry their bias).
+ * cls_cstride: halves per pixel of the cls buffers (0 = nc; K11 pads nc to a multiple of 8). */
 int eitb_yolo_head_decode(const void* const* box, const void* const* cls, const void* const* mc,
                           const float* const* box_bias, const float* const* cls_bias, const float* const* mc_bias,
-                          const int* hs, const int* ws, const int* strides, int B, int nc, int nm, void* head,
-                          eitb_stream_t stream);
+                          const int* hs, const int* ws, const int* strides, int B, int nc, int nm, int cls_cstride,
+                          void* head, eitb_stream_t stream);
 
 /* SPPF (yaml layer 9): x [B,h,w,C] -> out [B,h,w,4C] = x | maxpool5 | maxpool9 | maxpool13 (-inf padding). */
 int eitb_sppf_pool_concat(const void* x, int B, int h, int w, int C, void* out, eitb_stream_t stream);
+
+/* ---- K11 / K12: the convolutions of the networks -----------------------------------------------------
+ * Replace cuDNN + the K9 pass for the YOLO11s-seg models loaded at ai_tools.py:69-71 (called at
+ * ai_tools.py:121-122,153): implicit GEMM on tcgen05 tensor cores, operands moved by TMA, the Conv
+ * epilogue fused.  All activations are NHWC fp16; a tensor is addressed as (pointer, channels per pixel of
+ * the buffer `*_ctot`, first channel `*_coff`), so producers write and consumers read channel slices of
+ * concat buffers in place (ctot and coff multiples of 8).
+ *   y = act(conv(x, w) + bias) + res          (res added after the activation: Bottleneck shortcut)
+ *   x [N,H,W,x_ctot], channels [x_coff, x_coff+Cin), Cin % 16 == 0
+ *   w_packed [ksize*ksize][ceil16(Cout)][Cin] fp16 (tap-major, K contiguous; padded output rows zero)
+ *   bias [Cout] float32 or NULL; act 1 = SiLU, 0 = none; res NULL or [N,Ho,Wo,res_ctot] slice
+ *   ksize 1 or 3 (padding ksize/2), stride 1 or 2;  Ho = (H + 2*pad - ksize)/stride + 1
+ *   y_up 1: y [N,Ho,Wo,y_ctot].  y_up 2: y [N,2Ho,2Wo,y_ctot] and the result lands on pixels
+ *   (2*oy + y_dy, 2*ox + y_dx) -- one of the four phases of ConvTranspose2d(k=2, s=2). */
+int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_coff, int Cin,
+                     const void* w_packed, const float* bias, int Cout, int ksize, int stride, int act,
+                     const void* res, int res_ctot, int res_coff,
+                     void* y, int y_ctot, int y_coff, int y_up, int y_dy, int y_dx, eitb_stream_t stream);
+/* tile-shape experiments (host, process-wide): largest MMA N, deepest shared-memory ring, grid cap; <= 0 keeps a value */
+int eitb_conv2d_tuning(int ntile_max, int stage_cap, int grid_cap);
+/* kernel experiments (host, process-wide; 0 = production): 1 skip the TMA store, 2 skip the staging writes,
+ * 8 halo-mode descriptors carry base_offset, 16 halo mode off (nine shifted TMA loads per K chunk instead) */
+int eitb_conv2d_debug(int flags);
+
+/* Stem Conv(3 -> 32, k3, s2, pad 1): x [N,H,W,3] fp16, w27 [27][32] float32 ((r*3+s)*3+ci major). */
+int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, const float* w27, const float* bias, int Cout, int act,
+                             void* y, int y_ctot, int y_coff, eitb_stream_t stream);
+/* Depthwise Conv(C -> C, k3, s1, pad 1, groups C): w9 [9][C] fp16, C % 8 == 0. */
+int eitb_dwconv3x3_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_coff, int C, const void* w9, const float* bias,
+                        int act, void* y, int y_ctot, int y_coff, eitb_stream_t stream);
 
 /* ---- K8: per-triangle tissue labelling ----------------------------------------------------------
  * Replaces divide_triangles_into_groups / process_triangle / the CLASS vector of
