@@ -328,9 +328,9 @@ def run_b200(args):
         st = m.conv.stride[0]
         act_elems["n"] = act_elems.get("n", 0) + m.conv.out_channels * (-(-i[0].shape[2] // st)) * (-(-i[0].shape[3] // st))
     from eitsynthai_b200.yolo_seg import Conv
-    hooks = [m.register_forward_hook(_count) for m in pipe.axial_model_512.modules() if isinstance(m, Conv)]
+    hooks = [m.register_forward_hook(_count) for m in pipe.axial_512_torch.modules() if isinstance(m, Conv)]
     with torch.no_grad():
-        pipe.axial_model_512(torch.zeros((1, 3, SIZE, SIZE), dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last))
+        pipe.axial_512_torch(torch.zeros((1, 3, SIZE, SIZE), dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last))
     for h in hooks:
         h.remove()
     # exact bytes of the timed region for K9 are filled in below (the rib network adds its own launches)

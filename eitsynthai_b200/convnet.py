@@ -86,8 +86,9 @@ class PackedConv:
         return cls.from_weight(w, b, 1, 1, mods[0].has_act)
 
 
-def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, up=(1, 0, 0)) -> Act:
-    """y = act(conv(x) + bias) [+ res], written to ``out`` (a slice) or to a fresh buffer."""
+def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, up=(1, 0, 0), gray: bool = False) -> Act:
+    """y = act(conv(x) + bias) [+ res], written to ``out`` (a slice) or to a fresh buffer.  ``gray``: the stem's
+    three input channels are equal (a replicated gray image)."""
     B, H, W = x.bhw
     dev = x.buf.device
     assert x.c == L.cin, (x.c, L.cin)
@@ -111,8 +112,8 @@ def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, 
         else:
             assert res is None and up[0] == 1 and x.off == 0 and x.buf.shape[3] == 3
             cabi.call("eitb_stem_conv3x3s2_nhwc", x.buf.data_ptr(), B, H, W, L.w.data_ptr(),
-                      0 if L.bias is None else L.bias.data_ptr(), L.cout, int(L.act), out.buf.data_ptr(), out.buf.shape[3],
-                      out.off, _stream(dev))
+                      0 if L.bias is None else L.bias.data_ptr(), L.cout, int(L.act), int(gray), out.buf.data_ptr(),
+                      out.buf.shape[3], out.off, _stream(dev))
     return out
 
 
@@ -227,12 +228,13 @@ class ConvNet:
 
     # ------------------------------------------------------------------ whole network
     @torch.no_grad()
-    def __call__(self, x: torch.Tensor):
+    def __call__(self, x: torch.Tensor, gray: bool = False):
+        """``gray``: the three channels of ``x`` are equal (K1 / letterbox output) -- lets the stem read one."""
         assert x.is_cuda and x.dtype == torch.float16 and x.shape[1] == 3 and x.is_contiguous(memory_format=torch.channels_last)
         p = self.p
         dev = x.device
         a = Act(x.permute(0, 2, 3, 1))                              # NHWC view of the channels-last input
-        a = conv(conv(a, p["l0"]), p["l1"])
+        a = conv(conv(a, p["l0"], gray=gray), p["l1"])
         a = self._c3k2(a, p["l2"])
         p3 = self._c3k2(conv(a, p["l3"]), p["l4"])
         p4 = self._c3k2(conv(p3, p["l5"]), p["l6"])

@@ -37,7 +37,8 @@ struct ConvArgs {
     int swz_ab, swz_out;               // 16-byte-chunk xor masks: 7 (128B rows), 3 (64B), 1 (32B)
     int tmem_cols;
     int dbg;                           // experiments: 1 no TMA store, 2 no staging writes, 8 halo descriptors carry base_offset = tap column
-    int halo, WB, HB, halo_bytes, halo_tx, halo_stages;   // halo mode (3x3, stride 1): input tile + 1-pixel frame staged once per K chunk
+    int halo, WB, HB, halo_bytes, halo_tx, halo_stages;
+    int ws, ws_bytes;                  // weights stationary: all taps x K chunks of the (single) N tile stay in shared memory   // halo mode (3x3, stride 1): input tile + 1-pixel frame staged once per K chunk
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,6 +73,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum));
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -132,16 +144,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // dynamic shared memory is only 16-byte aligned by contract: align the operand buffers by hand
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* halo = smem;                                            // halo_stages x input halo tile (halo mode)
-    unsigned char* ring = halo + (size_t)p.halo_stages * p.halo_bytes;     // stages x (A | B)   [halo mode: B only]
+    unsigned char* wres = smem;                                            // resident weights (weight-stationary mode)
+    unsigned char* halo = wres + p.ws_bytes;                               // halo_stages x input halo tile (halo mode)
+    unsigned char* ring = halo + (size_t)p.halo_stages * p.halo_bytes;     // stages x (A | B)   [halo: B only; stationary: A only]
     unsigned char* staging = ring + (size_t)p.stages * p.stage_bytes;      // 2 x slab
     float* sbias = reinterpret_cast<float*>(staging + 2 * (size_t)p.slab_bytes);       // [n_tiles * ntile]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.n_tiles * p.ntile);
     // bars: full[8] | empty[8] | tmem_full[2] | tmem_empty[2] | res_full[2] | halo_full[4] | halo_empty[4]
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages;
     const uint32_t bar_tfull = bar_empty + 8 * kMaxStages, bar_tempty = bar_tfull + 16, bar_res = bar_tempty + 16;
-    const uint32_t bar_hfull = bar_res + 16, bar_hempty = bar_hfull + 8 * kMaxHalo;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6 + 2 * kMaxHalo);
+    const uint32_t bar_hfull = bar_res + 16, bar_hempty = bar_hfull + 8 * kMaxHalo, bar_w = bar_hempty + 8 * kMaxHalo;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6 + 2 * kMaxHalo + 1);
 
     constexpr int kThreads = (2 + EW) * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,6 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int s = 0; s < p.halo_stages; ++s) { mbar_init(bar_hfull + 8 * s, 1); mbar_init(bar_hempty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EW); mbar_init(bar_res + 8 * a, 1); }
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -163,42 +177,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t tmem = *tmem_slot;
     const int row_bytes = p.Kc * 2;
 
+    // Warps 0 and 1 run their loops with all 32 lanes (warp-uniform control flow: loop counters and addresses stay in
+    // uniform registers); only the TMA / MMA / commit instructions themselves are issued by one elected lane.
     if (warp == 0) {
         // ================================================================== TMA producer
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int hs = 0; uint32_t hphase = 0;
-            const int pad = p.ksize >> 1;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-                const int bx = mt % p.tiles_x, by = (mt / p.tiles_x) % p.tiles_y, bb = mt / (p.tiles_x * p.tiles_y);
-                if (p.halo) {
-                    // one halo tile per K chunk feeds all nine taps; only the weights stream through the ring
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(bar_hempty + 8 * hs, hphase ^ 1);
+        const bool el = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        int hs = 0; uint32_t hphase = 0;
+        const int pad = p.ksize >> 1;
+        const uint32_t ring_u = smem_u32(ring), halo_u = smem_u32(halo), wres_u = smem_u32(wres);
+        if (p.ws && el) {                                                  // every weight tile once, for the CTA's lifetime
+            mbar_expect_tx(bar_w, (uint32_t)p.ws_bytes);
+            for (int tap = 0; tap < p.taps; ++tap)
+                for (int kc = 0; kc < p.kchunks; ++kc)
+                    tma_load_3d(wres_u + (uint32_t)((tap * p.kchunks + kc) * p.b_bytes), &map_w, kc * p.Kc, 0, tap, bar_w);
+        }
+        const uint32_t tx = (uint32_t)((p.halo ? 0 : p.a_bytes) + (p.ws ? 0 : p.b_bytes));
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+            const int bx = mt % p.tiles_x, by = (mt / p.tiles_x) % p.tiles_y, bb = mt / (p.tiles_x * p.tiles_y);
+            if (p.halo) {
+                // one halo tile per K chunk feeds all nine taps; only the weights stream through the ring
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(bar_hempty + 8 * hs, hphase ^ 1);
+                    if (el) {
                         mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)p.halo_tx);
-                        tma_load_4d(smem_u32(halo + (size_t)hs * p.halo_bytes), &map_x, kc * p.Kc, bx * p.tw - 1, by * p.th - 1, bb,
+                        tma_load_4d(halo_u + (uint32_t)(hs * p.halo_bytes), &map_x, kc * p.Kc, bx * p.tw - 1, by * p.th - 1, bb,
                                     bar_hfull + 8 * hs);
-                        if (++hs == p.halo_stages) { hs = 0; hphase ^= 1; }
-                        for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)p.b_bytes);
-                            tma_load_3d(smem_u32(ring + (size_t)stage * p.stage_bytes), &map_w, kc * p.Kc, nt * p.ntile, tap,
-                                        bar_full + 8 * stage);
-                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                        }
                     }
-                    continue;
+                    if (++hs == p.halo_stages) { hs = 0; hphase ^= 1; }
+                    if (p.ws) continue;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        if (el) {
+                            mbar_expect_tx(bar_full + 8 * stage, tx);
+                            tma_load_3d(ring_u + (uint32_t)(stage * p.stage_bytes), &map_w, kc * p.Kc, nt * p.ntile, tap, bar_full + 8 * stage);
+                        }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
                 }
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int r = tap / p.ksize, s = tap - r * p.ksize;
-                    const int cx = bx * p.tw * p.stride - pad + s, cy = by * p.th * p.stride - pad + r;
+                continue;
+            }
+            const int x0 = bx * p.tw * p.stride - pad, y0 = by * p.th * p.stride - pad, b0 = bb * p.tn;
+            for (int r = 0; r < p.ksize; ++r) {
+                for (int sx = 0; sx < p.ksize; ++sx) {
+                    const int tap = r * p.ksize + sx;
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        const uint32_t a_dst = smem_u32(ring + (size_t)stage * p.stage_bytes);
-                        mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(p.a_bytes + p.b_bytes));
-                        tma_load_4d(a_dst, &map_x, kc * p.Kc, cx, cy, bb * p.tn, bar_full + 8 * stage);
-                        tma_load_3d(a_dst + p.a_bytes, &map_w, kc * p.Kc, nt * p.ntile, tap, bar_full + 8 * stage);
+                        if (el) {
+                            const uint32_t a_dst = ring_u + (uint32_t)(stage * p.stage_bytes);
+                            mbar_expect_tx(bar_full + 8 * stage, tx);
+                            tma_load_4d(a_dst, &map_x, kc * p.Kc, x0 + sx, y0 + r, b0, bar_full + 8 * stage);
+                            if (!p.ws) tma_load_3d(a_dst + p.a_bytes, &map_w, kc * p.Kc, nt * p.ntile, tap, bar_full + 8 * stage);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -206,63 +237,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int hs = 0; uint32_t hphase = 0;
-            // instruction descriptor: D fp32, A/B fp16, both K-major, N = ntile, M = 128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            const int iters = p.taps * p.kchunks;
-            int local = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
-                const int acc = local & 1;
-                mbar_wait(bar_tempty + 8 * acc, (uint32_t)((local >> 1) & 1) ^ 1);
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t d_tmem = tmem + (uint32_t)(acc * p.ntile);
-                if (p.halo) {
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(bar_hfull + 8 * hs, hphase);
-                        const uint32_t h_addr = smem_u32(halo + (size_t)hs * p.halo_bytes);
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int r = tap / 3, s = tap - r * 3;
-                            mbar_wait(bar_full + 8 * stage, phase);
-                            asm volatile("tcgen05.fence::after_thread_sync;");
-                            // tile row y = 8 consecutive halo pixels starting at (y + r, s): 8-row groups WB pixels apart
-                            const uint64_t da = make_desc(h_addr + (uint32_t)((r * p.WB + s) * row_bytes), row_bytes, p.WB * row_bytes,
-                                                          (p.dbg & 8) ? s : 0);
-                            const uint64_t db = make_desc(smem_u32(ring + (size_t)stage * p.stage_bytes), row_bytes, 8 * row_bytes, 0);
-                            for (int k = 0; k < p.Kc / 16; ++k) {
-                                const uint32_t accum = (kc | tap | k) != 0;
-                                asm volatile(
-                                    "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
-                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
-                                    ::"r"(d_tmem), "l"(da + (uint64_t)(k * 2)), "l"(db + (uint64_t)(k * 2)), "r"(idesc), "r"(accum));
+        const bool el = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        int hs = 0; uint32_t hphase = 0;
+        // instruction descriptor: D fp32, A/B fp16, both K-major, N = ntile, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const int iters = p.taps * p.kchunks, ksteps = p.Kc >> 4;
+        // descriptors without the start-address field; adding (address >> 4) completes them
+        const uint64_t dA = make_desc(0, row_bytes, p.halo ? p.WB * row_bytes : 8 * row_bytes, 0);
+        const uint64_t dB = make_desc(0, row_bytes, 8 * row_bytes, 0);
+        const uint32_t ring_u = smem_u32(ring) >> 4, halo_u = smem_u32(halo) >> 4, wres_u = smem_u32(wres) >> 4;
+        const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, halo16 = (uint32_t)p.halo_bytes >> 4, b16 = (uint32_t)p.b_bytes >> 4;
+        const uint32_t a16 = (uint32_t)p.a_bytes >> 4, row16 = (uint32_t)row_bytes >> 4;
+        int local = 0;
+        if (p.ws) mbar_wait(bar_w, 0);
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
+            const int acc = local & 1;
+            mbar_wait(bar_tempty + 8 * acc, (uint32_t)((local >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t d_tmem = tmem + (uint32_t)(acc * p.ntile);
+            if (p.halo) {
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(bar_hfull + 8 * hs, hphase);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t h16 = halo_u + (uint32_t)hs * halo16;
+                    for (int r = 0; r < 3; ++r) {
+                        for (int sx = 0; sx < 3; ++sx) {
+                            const int tap = r * 3 + sx;
+                            uint32_t bq;
+                            if (p.ws) {
+                                bq = wres_u + (uint32_t)(tap * p.kchunks + kc) * b16;
+                            } else {
+                                mbar_wait(bar_full + 8 * stage, phase);
+                                asm volatile("tcgen05.fence::after_thread_sync;");
+                                bq = ring_u + (uint32_t)stage * stage16;
                             }
-                            umma_commit(bar_empty + 8 * stage);
-                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            // tile row y = 8 consecutive halo pixels starting at (y + r, sx): 8-row groups WB pixels apart
+                            const uint32_t aq = h16 + (uint32_t)(r * p.WB + sx) * row16;
+                            if (el && !(p.dbg & 4)) {
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_f16(d_tmem, dA + aq + 2 * k, dB + bq + 2 * k, idesc, (uint32_t)((kc | tap | k) != 0));
+                            }
+                            if (!p.ws) {
+                                __syncwarp();
+                                if (el) umma_commit(bar_empty + 8 * stage);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            }
                         }
-                        umma_commit(bar_hempty + 8 * hs);                  // halo tile free when its 9 x Kc/16 MMAs retire
-                        if (++hs == p.halo_stages) { hs = 0; hphase ^= 1; }
                     }
-                } else {
-                    for (int it = 0; it < iters; ++it) {
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        asm volatile("tcgen05.fence::after_thread_sync;");
-                        const uint32_t a_addr = smem_u32(ring + (size_t)stage * p.stage_bytes);
-                        const uint64_t da = make_desc(a_addr, row_bytes, 8 * row_bytes, 0);
-                        const uint64_t db = make_desc(a_addr + p.a_bytes, row_bytes, 8 * row_bytes, 0);
-                        for (int k = 0; k < p.Kc / 16; ++k) {
-                            const uint32_t accum = (it | k) != 0;
-                            asm volatile(
-                                "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
-                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
-                                ::"r"(d_tmem), "l"(da + (uint64_t)(k * 2)), "l"(db + (uint64_t)(k * 2)), "r"(idesc), "r"(accum));
-                        }
-                        umma_commit(bar_empty + 8 * stage);                // frees the ring slot when these MMAs retire
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                    }
+                    __syncwarp();
+                    if (el) umma_commit(bar_hempty + 8 * hs);              // halo tile free when its 9 x Kc/16 MMAs retire
+                    if (++hs == p.halo_stages) { hs = 0; hphase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * acc);                          // accumulator ready for the epilogue
+            } else {
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t aq = ring_u + (uint32_t)stage * stage16;
+                    const uint32_t bq = p.ws ? wres_u + (uint32_t)it * b16 : aq + a16;
+                    if (el) {
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_f16(d_tmem, dA + aq + 2 * k, dB + bq + 2 * k, idesc, (uint32_t)((it | k) != 0));
+                    }
+                    __syncwarp();
+                    if (el) umma_commit(bar_empty + 8 * stage);            // frees the ring slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
             }
+            __syncwarp();
+            if (el) umma_commit(bar_tfull + 8 * acc);                      // accumulator ready for the epilogue
         }
     } else {
         // ================================================================== epilogue (EW warps)
@@ -404,14 +447,18 @@ bool encode_act(CUtensorMap* m, const void* base, int c, int W, int H, int N, in
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int g_ntile_max = 256, g_stage_cap = kMaxStages, g_grid_cap = EITB_NUM_SMS, g_dbg = 0, g_halo = 1, g_light = 1;
+int g_ntile_max = 256, g_stage_cap = kMaxStages, g_grid_cap = EITB_NUM_SMS, g_dbg = 0, g_halo = 1, g_light = 1, g_ws = 1;
 
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace
 
-// bit 4 (16) turns halo mode off, bit 5 (32) the two-CTAs-per-SM configuration; the others are ConvArgs::dbg
-extern "C" int eitb_conv2d_debug(int flags) { g_dbg = flags & ~48; g_halo = !(flags & 16); g_light = !(flags & 32); return EITB_OK; }
+// bit 4 (16) turns halo mode off, bit 5 (32) the two-CTAs-per-SM configuration, bit 6 (64) resident weights;
+// the others are ConvArgs::dbg
+extern "C" int eitb_conv2d_debug(int flags) {
+    g_dbg = flags & ~112; g_halo = !(flags & 16); g_light = !(flags & 32); g_ws = !(flags & 64);
+    return EITB_OK;
+}
 
 extern "C" int eitb_conv2d_tuning(int ntile_max, int stage_cap, int grid_cap) {
     if (ntile_max >= 16) g_ntile_max = ntile_max;
@@ -444,42 +491,66 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
     p.slabC = p.ntile < 64 ? p.ntile : 64;
     if (p.slabC != 16 && p.slabC != 32 && p.slabC != 64) return EITB_ERR_UNSUPPORTED;
     p.slabs = p.ntile / p.slabC;
-    p.tw = Wo >= 16 ? 16 : pow2_ceil(Wo);
-    p.th = pow2_ceil(Ho) < BM / p.tw ? pow2_ceil(Ho) : BM / p.tw;
-    p.tn = BM / (p.tw * p.th);
-    // halo mode: 3x3 stride-1 layers stage a (16+2) x (8+2 -> 16) pixel tile once per K chunk and take all nine taps
-    // from it (row y of the 16 x 8 output tile = 8 consecutive halo pixels = one 8-row group of the A operand)
-    p.halo = (g_halo && ksize == 3 && stride == 1 && Ho >= 9) ? 1 : 0;
-    if (p.halo) { p.tw = 8; p.th = 16; p.tn = 1; p.WB = 10; p.HB = 18; }
-    const bool light = g_light && p.ntile <= 128;                          // two CTAs per SM
-    p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th; p.tiles_b = (N + p.tn - 1) / p.tn;
-    const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
-    if (total > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
-    p.total_tiles = (int)total;
     p.Cout = Cout; p.act = act; p.has_res = res != nullptr; p.dbg = g_dbg;
     p.a_bytes = BM * p.Kc * 2;
     p.b_bytes = p.ntile * p.Kc * 2;
-    p.stage_bytes = ((p.halo ? 0 : p.a_bytes) + p.b_bytes + 1023) / 1024 * 1024;
-    p.halo_bytes = p.halo ? (p.WB * p.HB * p.Kc * 2 + 1023) / 1024 * 1024 : 0;
-    p.halo_tx = p.WB * p.HB * p.Kc * 2;
     p.slab_bytes = BM * p.slabC * 2;
     p.swz_ab = p.Kc == 64 ? 7 : p.Kc == 32 ? 3 : 1;
     p.swz_out = p.slabC == 64 ? 7 : p.slabC == 32 ? 3 : 1;
     p.tmem_cols = pow2_ceil(2 * p.ntile) < 32 ? 32 : pow2_ceil(2 * p.ntile);
     const int fixed = 1024 /*alignment slack*/ + 2 * p.slab_bytes + p.n_tiles * p.ntile * 4 /*bias*/ + 512 /*barriers*/;
-    int avail = (light ? 113 : 227) * 1024 - fixed;
-    if (p.halo) {
-        // weights: one ring slot per tap in flight is plenty (they are L2 hits); the rest goes to halo tiles
-        p.stages = 4;
-        p.halo_stages = (avail - p.stages * p.stage_bytes) / p.halo_bytes;
-        if (p.halo_stages > kMaxHalo) p.halo_stages = kMaxHalo;
-        if (p.halo_stages < 1) return EITB_ERR_UNSUPPORTED;
-        avail -= p.halo_stages * p.halo_bytes;
+    const int all_w = p.taps * p.kchunks * p.b_bytes;                      // every weight tile of the (single) N tile
+
+    // Configuration, first that fits: {two CTAs per SM ("light", N <= 128), one} x {halo tile, nine shifted loads};
+    // weights stay resident when all of them take at most ~40 % of the CTA's shared memory.
+    bool light = false;
+    size_t smem = 0;
+    auto plan = [&](bool want_light, bool want_halo) -> bool {
+        const int total = (want_light ? 113 : 227) * 1024;
+        int avail = total - fixed;
+        p.halo = want_halo ? 1 : 0;
+        p.ws = (g_ws && p.n_tiles == 1 && all_w <= (total * 2) / 5) ? 1 : 0;
+        p.ws_bytes = p.ws ? (all_w + 1023) / 1024 * 1024 : 0;
+        avail -= p.ws_bytes;
+        p.stage_bytes = ((p.halo ? 0 : p.a_bytes) + (p.ws ? 0 : p.b_bytes) + 1023) / 1024 * 1024;
+        p.halo_stages = 0; p.halo_bytes = 0; p.halo_tx = 0;
+        if (p.halo) {
+            p.WB = (g_dbg & 128) ? 16 : 10; p.HB = 18;                     // 16 x 8 output pixels + a 1-pixel frame
+            p.halo_tx = p.WB * p.HB * p.Kc * 2;
+            p.halo_bytes = (p.halo_tx + 1023) / 1024 * 1024;
+            const int ring_min = p.ws ? 0 : 3 * p.stage_bytes;
+            p.halo_stages = (avail - ring_min) / p.halo_bytes;
+            if (p.halo_stages > kMaxHalo) p.halo_stages = kMaxHalo;
+            if (p.halo_stages < 2) return false;
+            avail -= p.halo_stages * p.halo_bytes;
+        }
+        if (p.halo && p.ws) {
+            p.stages = 0;
+        } else {
+            p.stages = avail / p.stage_bytes;
+            if (p.stages > g_stage_cap) p.stages = g_stage_cap;
+            if (p.stages < (want_light ? 3 : 2)) return false;
+        }
+        smem = (size_t)fixed + p.ws_bytes + (size_t)p.stages * p.stage_bytes + (size_t)p.halo_stages * p.halo_bytes;
+        light = want_light;
+        return true;
+    };
+    const bool halo_ok = g_halo && ksize == 3 && stride == 1 && Ho >= 9;
+    const bool light_ok = g_light && p.ntile <= 128;
+    if (!((light_ok && halo_ok && plan(true, true)) || (halo_ok && plan(false, true)) || (light_ok && plan(true, false)) ||
+          plan(false, false)))
+        return EITB_ERR_UNSUPPORTED;
+    if (p.halo) {                        // row y of the 16 x 8 output tile = 8 consecutive halo pixels = one 8-row group of A
+        p.tw = 8; p.th = 16; p.tn = 1;
+    } else {
+        p.tw = Wo >= 16 ? 16 : pow2_ceil(Wo);
+        p.th = pow2_ceil(Ho) < BM / p.tw ? pow2_ceil(Ho) : BM / p.tw;
+        p.tn = BM / (p.tw * p.th);
     }
-    p.stages = avail / p.stage_bytes;
-    if (p.stages > g_stage_cap) p.stages = g_stage_cap;
-    if (p.stages < 2) return EITB_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes + (size_t)p.halo_stages * p.halo_bytes;
+    p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th; p.tiles_b = (N + p.tn - 1) / p.tn;
+    const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+    if (total > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
+    p.total_tiles = (int)total;
 
     alignas(64) CUtensorMap mx, mw, my, mr;
     const char* xb = static_cast<const char*>(x) + (size_t)x_coff * 2;

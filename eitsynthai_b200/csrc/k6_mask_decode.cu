@@ -35,6 +35,23 @@ __device__ __forceinline__ int class_code(float cls) {
     return c == 0 ? EITB_CODE_BONE : c == 1 ? EITB_CODE_MUSCLE : c == 2 ? EITB_CODE_LUNG : c == 3 ? EITB_CODE_ADIPOSE : 0;
 }
 
+// Crop box of one detection in prototype pixels.  Float form (all ultralytics versions on the GPU, CPU with >= 50
+// masks): keep x1 <= col < x2.  Integer form (late-2025 crop_mask on the CPU with fewer than 50 masks):
+// boxes.round().int() used as Python slice bounds -- masks[:, :x1] = 0, masks[:, x2:] = 0 -- including Python's
+// meaning of a negative bound (counted from the end).  Both reduce to "lo <= col < hi" on float bounds.
+__device__ __forceinline__ float py_slice_bound(float v, int size) {
+    const int i = __float2int_rn(v);                                  // torch.round: half to even, then .int()
+    return (float)(i >= 0 ? min(i, size) : max(0, size + i));
+}
+__device__ __forceinline__ float4 eitb_crop_box(const float* d, float rx, float ry, int mw, int mh, bool int_crop) {
+    float4 b = make_float4(d[0] * rx, d[1] * ry, d[2] * rx, d[3] * ry);
+    if (int_crop) {
+        b.x = py_slice_bound(b.x, mw); b.z = py_slice_bound(b.z, mw);
+        b.y = py_slice_bound(b.y, mh); b.w = py_slice_bound(b.w, mh);
+    }
+    return b;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n_det, int max_det,
@@ -58,6 +75,8 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
     const float* dimg = dets + (long long)b * max_det * D;
     const int n = min(n_det[b], max_det);
     const float rx = (float)((double)mw / (double)W), ry = (float)((double)mh / (double)H);
+    const bool int_crop = (variant & 4) && n_det[b] < 50;
+    variant &= 1;
     if (tid == 0) s_nact = 0;
 
     // ---- stage the prototype tile (halo replicated at the frame)
@@ -89,8 +108,8 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
         const float cy_lo = (float)max(ty * PT - 1, 0), cy_hi = (float)min(ty * PT + PT, mh - 1);
         for (int i = tid; i < n; i += kThreads) {
             const float* d = dimg + (long long)i * D;
-            const float x1 = d[0] * rx, y1 = d[1] * ry, x2 = d[2] * rx, y2 = d[3] * ry;
-            if (x2 > cx_lo && x1 <= cx_hi && y2 > cy_lo && y1 <= cy_hi && class_code(d[5]) != 0)
+            const float4 bx = eitb_crop_box(d, rx, ry, mw, mh, int_crop);
+            if (bx.z > cx_lo && bx.x <= cx_hi && bx.w > cy_lo && bx.y <= cy_hi && class_code(d[5]) != 0)
                 act[atomicAdd(&s_nact, 1)] = i;
         }
     }
@@ -119,8 +138,8 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
         }
         if (tid < ng) {
             const float* d = dimg + (long long)act[c0 + tid] * D;
-            sbox[tid * 4 + 0] = d[0] * rx; sbox[tid * 4 + 1] = d[1] * ry;
-            sbox[tid * 4 + 2] = d[2] * rx; sbox[tid * 4 + 3] = d[3] * ry;
+            const float4 bx = eitb_crop_box(d, rx, ry, mw, mh, int_crop);
+            sbox[tid * 4 + 0] = bx.x; sbox[tid * 4 + 1] = bx.y; sbox[tid * 4 + 2] = bx.z; sbox[tid * 4 + 3] = bx.w;
             sinfo[tid * 2] = class_code(d[5]);
             sinfo[tid * 2 + 1] = act[c0 + tid];
         }
@@ -238,7 +257,7 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
                                 eitb_stream_t stream) {
     (void)ws; (void)ws_bytes;
     if (!dets || !n_det || !protos || !code || B < 0 || nm <= 0 || mh <= 0 || mw <= 0 || max_det <= 0 ||
-        max_det > kMaxDet || (variant & ~0x11))
+        max_det > kMaxDet || (variant & ~0x15))
         return EITB_ERR_BAD_ARG;
     if (H != 4 * mh || W != 4 * mw || (mw % 4) != 0) return EITB_ERR_UNSUPPORTED;
     if (B == 0) return EITB_OK;
@@ -249,9 +268,9 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
         return EITB_ERR_LAUNCH;
     // fp16 prototypes with 32 channels (what the network emits): contraction on the tensor cores
     if (proto_dtype == EITB_F16 && nm == 32 && !(variant & 0x10) && !(reinterpret_cast<uintptr_t>(protos) & 15))
-        return eitb_mask_decode_tc(dets, n_det, max_det, protos, proto_channels_last, B, mh, mw, H, W, variant & 1, code,
+        return eitb_mask_decode_tc(dets, n_det, max_det, protos, proto_channels_last, B, mh, mw, H, W, variant & 5, code,
                                    inst_area, inst_bits, s);
-    variant &= 1;
+    variant &= 5;
     switch (proto_dtype) {
         case EITB_F32: return launch_decode<float>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);
         case EITB_F16: return launch_decode<__half>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);

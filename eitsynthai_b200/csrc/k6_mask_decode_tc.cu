@@ -41,6 +41,19 @@ __device__ __forceinline__ int class_code(float cls) {
     return c == 0 ? EITB_CODE_BONE : c == 1 ? EITB_CODE_MUSCLE : c == 2 ? EITB_CODE_LUNG : c == 3 ? EITB_CODE_ADIPOSE : 0;
 }
 
+__device__ __forceinline__ float py_slice_bound(float v, int size) {       // see k6_mask_decode.cu
+    const int i = __float2int_rn(v);
+    return (float)(i >= 0 ? min(i, size) : max(0, size + i));
+}
+__device__ __forceinline__ float4 crop_box(const float* d, float rx, float ry, int mw, int mh, bool int_crop) {
+    float4 b = make_float4(d[0] * rx, d[1] * ry, d[2] * rx, d[3] * ry);
+    if (int_crop) {
+        b.x = py_slice_bound(b.x, mw); b.z = py_slice_bound(b.z, mw);
+        b.y = py_slice_bound(b.y, mh); b.w = py_slice_bound(b.w, mh);
+    }
+    return b;
+}
+
 // shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -82,6 +95,7 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
     const float* dimg = dets + (long long)b * max_det * D;
     const int n = min(n_det[b], max_det);
     const float rx = (float)((double)mw / (double)W), ry = (float)((double)mh / (double)H);
+    const bool int_crop = (variant & 4) && n_det[b] < 50;
 
     if (tid < NCOL) {
         const int hy = tid / HTX, hx = tid - hy * HTX;
@@ -135,8 +149,8 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
         const float cy_lo = (float)max(ty * PTY_ - 1, 0), cy_hi = (float)min(ty * PTY_ + PTY_, mh - 1);
         for (int i = tid; i < n; i += kThreads) {
             const float* d = dimg + (long long)i * D;
-            const float x1 = d[0] * rx, y1 = d[1] * ry, x2 = d[2] * rx, y2 = d[3] * ry;
-            if (x2 > cx_lo && x1 <= cx_hi && y2 > cy_lo && y1 <= cy_hi && class_code(d[5]) != 0)
+            const float4 bx = crop_box(d, rx, ry, mw, mh, int_crop);
+            if (bx.z > cx_lo && bx.x <= cx_hi && bx.w > cy_lo && bx.y <= cy_hi && class_code(d[5]) != 0)
                 act[atomicAdd(s_nact, 1)] = i;
         }
     }
@@ -181,8 +195,8 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
         }
         if (tid < np) {
             const float* d = dimg + (long long)act[p0 + tid] * D;
-            sbox[tid * 4 + 0] = d[0] * rx; sbox[tid * 4 + 1] = d[1] * ry;
-            sbox[tid * 4 + 2] = d[2] * rx; sbox[tid * 4 + 3] = d[3] * ry;
+            const float4 bx = crop_box(d, rx, ry, mw, mh, int_crop);
+            sbox[tid * 4 + 0] = bx.x; sbox[tid * 4 + 1] = bx.y; sbox[tid * 4 + 2] = bx.z; sbox[tid * 4 + 3] = bx.w;
             sinfo[tid * 2] = class_code(d[5]);
             sinfo[tid * 2 + 1] = act[p0 + tid];
         }

@@ -82,6 +82,11 @@ class ImagingPipeline:
         if calibrate:
             self._calibrate()
 
+    def _net(self, model, x):
+        """Run a network on a replicated gray image (every input of the service is one): lets the own-kernel
+        engine read a single input channel in the stem."""
+        return model(x, gray=True) if self.engine == "eitb" and self.dtype == torch.float16 else model(x)
+
     def _bind_engine(self):
         if self.engine == "eitb" and self.dtype == torch.float16:
             from .convnet import ConvNet
@@ -139,7 +144,7 @@ class ImagingPipeline:
     def rib_select(self, front: torch.Tensor, custom: torch.Tensor | None = None):
         """[S,N,W] coronal images -> ([S,4] int32 (y6, y7, mid+custom, ok), boxes [S,300,4], k [S])."""
         x, (gain, pad_x, pad_y, w0, h0) = self._rib_input(front)
-        head, _ = self.ribs_model(x)
+        head, _ = self._net(self.ribs_model, x)
         dets, _, k = ops.nms(head.contiguous(), 1, CONF, IOU, MAX_DET, want_idx=False)
         boxes = ops.scale_boxes(dets, k, gain, pad_x, pad_y, w0, h0)
         # image_width is hard-coded to 512 in the reference (utils.py:166)
@@ -164,7 +169,7 @@ class ImagingPipeline:
         S = x.shape[-1]
         # get_axial_slice_size / model choice, ai_tools.py:138-146: 256 -> the 256 model, else the 512 one
         model = self.axial_model_256 if S == 256 else self.axial_model_512
-        head, protos = model(x.contiguous(memory_format=torch.channels_last))
+        head, protos = self._net(model, x.contiguous(memory_format=torch.channels_last))
         dets, _, n = ops.nms(head.contiguous(), 4, CONF, IOU, MAX_DET, want_idx=False)
         code, _, _ = ops.mask_decode(dets, n, protos, self.mask_variant)
         ops.label_cleanup(code, body)
@@ -331,7 +336,7 @@ class SeriesBatchRunner:
         with t("K1_hu_window_nchw"):
             _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=pipe.dtype, channels_last=True)
         with t("CNN_axial"):
-            head, protos = (pipe.axial_model_256 if self.size == 256 else pipe.axial_model_512)(x)
+            head, protos = pipe._net(pipe.axial_model_256 if self.size == 256 else pipe.axial_model_512, x)
             head = head.contiguous()
         with t("K5_nms"):
             dets, _, n = ops.nms(head, 4, CONF, IOU, MAX_DET, want_idx=False)
@@ -357,7 +362,7 @@ class SeriesBatchRunner:
                 front = torch.stack([ops.minmax_u8(rows_all[s], mm_all[s]) for s in self.mine])
                 x, (gain, pad_x, pad_y, w0, h0) = pipe._rib_input(front)
             with t("CNN_ribs"):
-                head, _ = pipe.ribs_model(x)
+                head, _ = pipe._net(pipe.ribs_model, x)
                 head = head.contiguous()
             with t("K5_nms_ribs"):
                 dets, _, k = ops.nms(head, 1, CONF, IOU, MAX_DET, want_idx=False)
@@ -369,9 +374,7 @@ class SeriesBatchRunner:
     def rib_stage(self, px, graphed=False, row0=False):
         rows, mm = self.rib_rows(px, row0)
         with self.timer("C1_exchange"):
-            rows_all, mm_all = self.sharded.gather_rows(rows, mm, self.n_slices)
-            for s_ in self.flip_z:                              # FFS / 'P' orientation: reverse the gathered z axis
-                rows_all[s_] = rows_all[s_].flip(0)
+            rows_all, mm_all = self.sharded.gather_rows(rows, mm, self.n_slices, self.flip_z)
         if graphed and self.rib_graph is not None:
             self.rows_static.copy_(rows_all)
             self.mm_static.copy_(mm_all)

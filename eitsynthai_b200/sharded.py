@@ -34,13 +34,23 @@ def owner_of_series(s: int, world_size: int) -> int:
     return s % world_size
 
 
-def gather_rows(rows_local: torch.Tensor, minmax_local: torch.Tensor, n_slices: int):
+def _flip(rows: torch.Tensor, flip_z) -> torch.Tensor:
+    for s in flip_z or ():
+        rows[s] = rows[s].flip(0)
+    return rows
+
+
+def gather_rows(rows_local: torch.Tensor, minmax_local: torch.Tensor, n_slices: int, flip_z=None):
     """rows_local [S, n_local, W] int16 (this rank's z-range, ascending z), minmax_local [S, 2] int32 ->
     (rows [S, n_slices, W], minmax [S, 2]) identical on every rank.  ONE collective: rows and min/max travel
-    in the same byte buffer (neither NCCL nor gloo has a 16-bit integer type)."""
+    in the same byte buffer (neither NCCL nor gloo has a 16-bit integer type).
+
+    ``flip_z``: series whose coronal image is z-reversed (FFS, or PatientOrientation[1] == 'P' when not HFS;
+    utils.py:130-132,155-160).  The reversal is applied to the GATHERED rows: reversing inside each shard and
+    concatenating in rank order would give [rev(shard0), rev(shard1), ...] instead."""
     rank, ws = world()
     if ws == 1:
-        return rows_local, minmax_local
+        return _flip(rows_local, flip_z), minmax_local
     S, nl, W = rows_local.shape
     sizes = [shard_range(n_slices, ws, r)[1] - shard_range(n_slices, ws, r)[0] for r in range(ws)]
     nmax = max(sizes)
@@ -58,7 +68,7 @@ def gather_rows(rows_local: torch.Tensor, minmax_local: torch.Tensor, n_slices: 
         rows = torch.cat([parts[r, :, :sizes[r]] for r in range(ws)], 1)
     mm = recv[:, row_bytes:].view(torch.int32).view(ws, S, 2)
     minmax = torch.stack((mm[:, :, 0].min(0).values, mm[:, :, 1].max(0).values), 1).contiguous()
-    return rows.contiguous(), minmax
+    return _flip(rows.contiguous(), flip_z), minmax
 
 
 def share_selected(sel_mine: torch.Tensor) -> torch.Tensor:

@@ -175,6 +175,8 @@ int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, in
  *   dets/n_det as written by eitb_nms; protos [B,nm,mh,mw] of proto_dtype, stored NCHW
  *   (proto_channels_last 0) or NHWC, i.e. [B,mh,mw,nm] (1: what a channels-last network emits)
  *   variant   bit 0 -- 0: logits, interpolate, > 0 (8.3.x)   1: sigmoid, interpolate, > 0.5 (8.0-8.2)
+ *             bit 2 -- the CPU crop of late-2025 ultralytics: images with fewer than 50 detections
+ *             crop with boxes.round().int() used as Python slice bounds instead of the float comparison
  *             bit 4 -- keep the contraction on the CUDA cores (fp16 prototypes with nm == 32 otherwise
  *             go through tcgen05.mma with the accumulator in tensor memory; same semantics)
  *   code      [B,H,W] u8 out: overlay codes
@@ -255,9 +257,11 @@ int eitb_conv2d_tuning(int ntile_max, int stage_cap, int grid_cap);
  * 8 halo-mode descriptors carry base_offset, 16 halo mode off (nine shifted TMA loads per K chunk instead) */
 int eitb_conv2d_debug(int flags);
 
-/* Stem Conv(3 -> 32, k3, s2, pad 1): x [N,H,W,3] fp16, w27 [27][32] float32 ((r*3+s)*3+ci major). */
+/* Stem Conv(3 -> 32, k3, s2, pad 1): x [N,H,W,3] fp16, w27 [27][32] float32 ((r*3+s)*3+ci major).
+ * gray 1: the caller guarantees three equal input channels (a gray slice replicated by K1 / the letterbox,
+ * ai_tools.py:120,135): channel 0 is read and the weights are summed over the input channel. */
 int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, const float* w27, const float* bias, int Cout, int act,
-                             void* y, int y_ctot, int y_coff, eitb_stream_t stream);
+                             int gray, void* y, int y_ctot, int y_coff, eitb_stream_t stream);
 /* Depthwise Conv(C -> C, k3, s1, pad 1, groups C): w9 [9][C] fp16, C % 8 == 0. */
 int eitb_dwconv3x3_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_coff, int C, const void* w9, const float* bias,
                         int act, void* y, int y_ctot, int y_coff, eitb_stream_t stream);

@@ -1,11 +1,12 @@
 """Stub-import of the *actual* reference module (TEST INFRASTRUCTURE ONLY).
 
-Loads /root/reference/kt_service/ai_tools/utils.py unmodified through importlib
-with the four un-installed third-party modules stubbed (nibabel, pydicom,
-pydicom.config, pydicom.filebase, supervision).  This only works inside the
-authoring container (the GPU box has no /root/reference); it is used by
-``oracle/gen_golden.py`` to freeze golden vectors under ``tests/golden/`` and by
-CPU tests that are skipped when the reference tree is absent.
+Loads kt_service/ai_tools/utils.py of the reference unmodified through importlib with the four
+un-installed third-party modules stubbed (nibabel, pydicom, pydicom.config, pydicom.filebase,
+supervision): from the source tree under /root/reference in the authoring container, or -- on the GPU
+box, where that tree does not exist -- from the byte code ``oracle/build_ref.py`` compiled into
+``oracle/_ref/`` (git-ignored, travels with the gpurun snapshot).  Used by ``oracle/gen_golden.py`` to
+freeze golden vectors under ``tests/golden/``, by the live parity tests, and by the CPU-baseline arm of
+``bench.py`` for the rows the reference owns.
 
 Nothing under ``eitsynthai_b200/`` may import this file.
 """
@@ -18,11 +19,32 @@ import types
 
 REF_ROOT = os.environ.get("EITB_REFERENCE_ROOT", "/root/reference")
 _UTILS = os.path.join(REF_ROOT, "kt_service", "ai_tools", "utils.py")
+_REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _cached = None
 
 
+def _pyc(name: str):
+    p = os.path.join(_REF_DIR, f"{name}.cpython-{sys.version_info.major}{sys.version_info.minor}.pyc")
+    return p if os.path.isfile(p) else None
+
+
 def reference_available() -> bool:
-    return os.path.isfile(_UTILS)
+    return os.path.isfile(_UTILS) or _pyc("ref_utils") is not None
+
+
+def _load(name: str, source: str, pyc_name: str):
+    """Module from the reference source file when the tree is mounted, else from oracle/_ref byte code."""
+    if os.path.isfile(source):
+        spec = importlib.util.spec_from_file_location(name, source)
+    else:
+        from importlib.machinery import SourcelessFileLoader
+        path = _pyc(pyc_name)
+        if path is None:
+            raise FileNotFoundError(f"{source} (and no oracle/_ref/{pyc_name}.*.pyc: run python -m oracle.build_ref)")
+        spec = importlib.util.spec_from_loader(name, SourcelessFileLoader(name, path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
@@ -54,9 +76,7 @@ def load_reference_utils():
         "supervision": _stub("supervision"),
     })
     try:
-        spec = importlib.util.spec_from_file_location("eitb_ref_utils", _UTILS)
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
+        mod = _load("eitb_ref_utils", _UTILS, "ref_utils")
     finally:
         for k, v in saved.items():
             if v is None:

@@ -102,13 +102,27 @@ def crop_mask(masks: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
     return masks * ((r >= x1) * (r < x2) * (c >= y1) * (c < y2))
 
 
+def crop_mask_int(masks: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+    """Late-2025 ``crop_mask`` branch for ``n < 50`` masks on the CPU: the rounded
+    integer box used as Python slice bounds, in place -- a negative bound counts from the end, as slicing does."""
+    masks = masks.clone()
+    for i, (x1, y1, x2, y2) in enumerate(boxes.round().int().tolist()):
+        masks[i, :y1] = 0
+        masks[i, y2:] = 0
+        masks[i, :, :x1] = 0
+        masks[i, :, x2:] = 0
+    return masks
+
+
 def process_mask(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, shape,
-                 variant: str = "logit") -> torch.Tensor:
+                 variant: str = "logit", crop: str = "float") -> torch.Tensor:
     """``ops.process_mask(..., upsample=True)``.
 
     protos (nm, mh, mw), coef (n, nm), boxes (n, 4) xyxy in network-input pixels,
     shape = (ih, iw).  variant "logit": 8.3.x (interpolate then > 0); "sigmoid": 8.0-8.2
-    (sigmoid before crop, > 0.5 after interpolation).  Returns (n, ih, iw) uint8 {0,1}.
+    (sigmoid before crop, > 0.5 after interpolation).  crop "float": comparison on arange grids (every
+    version on the GPU); "cpu": what the reference's CPU-only image runs with a late-2025 ultralytics --
+    integer slicing when n < 50, the float comparison otherwise.  Returns (n, ih, iw) uint8 {0,1}.
     """
     c, mh, mw = protos.shape
     ih, iw = shape
@@ -119,7 +133,8 @@ def process_mask(protos: torch.Tensor, coef: torch.Tensor, boxes: torch.Tensor, 
     if variant == "sigmoid":
         masks = masks.sigmoid()
     ratios = torch.tensor([[mw / iw, mh / ih, mw / iw, mh / ih]])
-    masks = crop_mask(masks, boxes.float() * ratios)
+    scaled = boxes.float() * ratios
+    masks = crop_mask_int(masks, scaled) if (crop == "cpu" and n < 50) else crop_mask(masks, scaled)
     masks = torch.nn.functional.interpolate(masks[None], (ih, iw), mode="bilinear",
                                             align_corners=False)[0]
     return (masks > (0.5 if variant == "sigmoid" else 0.0)).to(torch.uint8)
@@ -141,13 +156,13 @@ def scale_boxes(img1_shape, boxes: torch.Tensor, img0_shape) -> torch.Tensor:
 
 def postprocess(pred: torch.Tensor, protos: torch.Tensor, nc: int, net_shape, orig_shape,
                 conf: float = 0.3, iou: float = 0.7, variant: str = "logit",
-                drop_empty: bool = True):
+                drop_empty: bool = True, crop: str = "float"):
     """One image through NMS -> mask decode -> box rescale -> empty-mask filter.
 
     Returns dict(boxes (n,4) original px, conf, cls, masks (n, ih, iw) u8, anchor_idx).
     """
     dets, idx = nms(pred, nc, conf, iou)
-    masks = process_mask(protos, dets[:, 6:], dets[:, :4], net_shape, variant)
+    masks = process_mask(protos, dets[:, 6:], dets[:, :4], net_shape, variant, crop)
     boxes = scale_boxes(net_shape, dets[:, :4], orig_shape) if dets.shape[0] else dets[:, :4]
     if drop_empty and masks.shape[0]:
         keep = masks.sum((-2, -1)) > 0

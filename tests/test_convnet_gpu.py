@@ -92,6 +92,11 @@ def test_depthwise_and_stem():
     refs = F.silu(F.conv2d(xs.permute(0, 3, 1, 2).float(), ws.float(), bs, 2, 1)).permute(0, 2, 3, 1)
     assert ys.buf.shape == refs.shape
     assert float((ys.buf.float() - refs).abs().max()) <= 2e-3 * float(refs.abs().max()) + 2e-3
+    # replicated gray input: the 9-tap form with channel-summed weights
+    xg = xs[..., :1].expand(-1, -1, -1, 3).contiguous()
+    yg = conv(Act(xg), PackedConv.from_weight(ws, bs, 2, 1, True), gray=True)
+    refg = F.silu(F.conv2d(xg.permute(0, 3, 1, 2).float(), ws.float(), bs, 2, 1)).permute(0, 2, 3, 1)
+    assert float((yg.buf.float() - refg).abs().max()) <= 2e-3 * float(refg.abs().max()) + 2e-3
 
 
 @pytest.mark.parametrize("nc,size", [(4, (512, 512)), (4, (256, 256)), (1, (416, 640))])
@@ -109,8 +114,10 @@ def test_network_matches_fp32_pytorch(nc, size):
     with torch.no_grad():
         head32, proto32 = m32(x16.float())
         head16, proto16 = m16(x16)                                 # cuDNN fp16 + K9 (round-1 path)
-        head, proto = net(x16)
+        head, proto = net(x16, gray=True)
+        head_c, proto_c = net(x16)                                 # generic 27-tap stem: same result up to fp32 summation order
     assert head.shape == head32.shape and proto.shape == proto32.shape
+    assert float((proto_c.float() - proto.float()).abs().max()) <= 5e-3 * float(proto32.abs().max())
 
     def rel(a, b):
         return float((a.float() - b).abs().max() / b.abs().max().clamp_min(1e-6))

@@ -208,11 +208,11 @@ def _unpack_bits(bits, W):
 
 def _decode_case(ops, head, protos, variant, size, tol=1e-4):
     """Per-instance masks, overlay codes and areas vs the CPU restatement."""
-    vname = "logit" if variant == 0 else "sigmoid"
+    vname = "logit" if not (variant & 1) else "sigmoid"
     dets, idx, n = ops.nms(dev(head[None]), 4)
     code, area, bits = ops.mask_decode(dets, n, dev(protos[None]), variant, want_area=True, want_bits=True)
     r = Y.postprocess(torch.from_numpy(head), torch.from_numpy(protos), 4, (size, size), (size, size),
-                      variant=vname, drop_empty=False)
+                      variant=vname, drop_empty=False, crop="cpu" if variant & 4 else "float")
     nn = int(n[0])
     assert nn == r["masks"].shape[0]
     got = _unpack_bits(bits[0, :nn].cpu().numpy(), size)
@@ -243,6 +243,40 @@ def test_mask_decode_teacher(ops, variant, seed, size):
 def test_mask_decode_random(ops, n_cand):
     head, protos = synth.random_heads(1, n_cand, seed=7 + n_cand)
     _decode_case(ops, head[0], protos[0], 0, 512)
+
+
+def _few_box_heads(seed, n_boxes, size=512):
+    """Teacher-like head with < 50 detections whose boxes hang over every image edge (negative and > size
+    coordinates, x.5 bounds): the regime of the integer crop, including Python's negative slice bounds."""
+    rng = np.random.default_rng(seed)
+    head, protos = synth.random_heads(1, 0, seed=seed, size=size)
+    head, protos = head[0], protos[0]
+    head[4:8] = 0.01
+    A = head.shape[1]
+    slots = rng.choice(A, n_boxes, replace=False)
+    for k, a in enumerate(slots):
+        cx, cy = rng.uniform(-20, size + 20, 2)
+        w, h = rng.uniform(30, 300, 2)
+        if k % 3 == 0:                                           # bounds landing on .5 in prototype pixels (ties -> even)
+            cx, w = 4 * round(cx / 4) + 2.0, 8 * round(w / 8) + 4.0
+        head[0, a], head[1, a], head[2, a], head[3, a] = cx, cy, w, h
+        head[4 + k % 4, a] = rng.uniform(0.4, 0.9) - 1e-3 * k
+    return head, protos
+
+
+@pytest.mark.parametrize("seed,n_boxes", [(0, 7), (1, 30), (2, 49), (3, 80)])
+@pytest.mark.parametrize("path", [4, 4 | 0x10])
+def test_mask_decode_int_crop_variant(ops, seed, n_boxes, path):
+    """variant bit 2: the rounded-integer crop ultralytics applies on the CPU for < 50 masks (and the float crop
+    from 50 masks on), on both the tensor-core and the CUDA-core path."""
+    head, protos = _few_box_heads(seed, n_boxes)
+    protos16 = protos.astype(np.float16).astype(np.float32)
+    _decode_case(ops, head, protos16 if not (path & 0x10) else protos, path, 512)
+    if not (path & 0x10):
+        dets, _, n = ops.nms(dev(head[None]), 4)
+        c_tc, _, _ = ops.mask_decode(dets, n, torch.from_numpy(protos16[None]).half().to(DEV), 4)
+        c_cc, _, _ = ops.mask_decode(dets, n, torch.from_numpy(protos16[None]).half().to(DEV), 4 | 0x10)
+        assert (c_tc != c_cc).float().mean() <= 1e-4
 
 
 def test_mask_decode_batch_and_half_protos(ops):

@@ -80,7 +80,7 @@ def test_post_cnn_chain_matches_oracle(pipe):
     body = ops.body_mask(pxd, 1, -1024, True)
     _, x = ops.hu_window(pxd, body_mask=body, want_u8=False, nchw_dtype=pipe.dtype)
     with torch.no_grad():
-        head, protos = pipe.axial_model_512(x.contiguous(memory_format=torch.channels_last))
+        head, protos = pipe._net(pipe.axial_model_512, x.contiguous(memory_format=torch.channels_last))
     code, body2, n = pipe.segment(pxd)
     assert torch.equal(body, body2)
     for b in range(3):
@@ -259,7 +259,7 @@ def test_post_cnn_chain_matches_oracle_256(pipe):
     body = ops.body_mask(pxd, 1, -1024, True)
     _, x = ops.hu_window(pxd, body_mask=body, want_u8=False, nchw_dtype=pipe.dtype, channels_last=True)
     with torch.no_grad():
-        head, protos = pipe.axial_model_256(x)
+        head, protos = pipe._net(pipe.axial_model_256, x)
     assert head.shape == (2, 40, 1344) and protos.shape == (2, 32, 64, 64)
     code, body2, n = pipe.segment(pxd)
     for b in range(2):

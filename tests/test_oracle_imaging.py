@@ -85,3 +85,22 @@ def test_axial_slice_size():
     assert O.get_axial_slice_size(np.zeros((256, 256))) == 256
     assert O.get_axial_slice_size(np.zeros((300, 300))) == []
     assert O.get_axial_slice_size(None) == []
+
+
+def test_crop_mask_int_is_python_slicing():
+    """The integer crop of late-2025 ultralytics (n < 50 on the CPU): rounded bounds, half to even, and Python's
+    meaning of negative slice bounds; equals the float crop for boxes with integer corners inside the map."""
+    import torch
+    from oracle import yolo_post as Y
+    m = torch.ones((4, 12, 16))
+    boxes = torch.tensor([[2.0, 3.0, 9.0, 8.0], [2.5, 3.5, 9.5, 8.5], [-1.2, 0.0, 7.0, 20.0], [3.0, -2.6, 30.0, -0.4]])
+    out = Y.crop_mask_int(m, boxes)
+    assert torch.equal(out[0], Y.crop_mask(m[:1], boxes[:1])[0])
+    keep = torch.zeros((12, 16)); keep[4:8, 2:10] = 1            # 2.5 -> 2, 3.5 -> 4, 9.5 -> 10, 8.5 -> 8
+    assert torch.equal(out[1], keep)
+    keep = torch.zeros((12, 16)); keep[:, 15:7] = 1               # x1 = -1 -> columns [0, 15) cleared, [7, 16) cleared: nothing left
+    assert torch.equal(out[2], keep)
+    keep = torch.zeros((12, 16)); keep[9:12, 3:16] = 1            # y1 = -3 -> rows [0, 9) cleared; y2 = round(-0.4) = 0 -> rows [0, 12) cleared
+    assert out[3].sum() == 0
+    r = Y.process_mask(torch.randn(32, 16, 16), torch.randn(3, 32), torch.tensor([[0., 0, 64, 64]] * 3), (64, 64), crop="cpu")
+    assert r.shape == (3, 64, 64)

@@ -35,7 +35,9 @@ def _worker(rank, world, port, n_slices, tmp):
             r = O.front_rows(srt)                                  # stand-in for eitb_front_rows on this shard
             rows_local.append(r)
             mm_local.append([int(r.min()), int(r.max())])
-        rows, mm = sharded.gather_rows(torch.from_numpy(np.stack(rows_local)), torch.tensor(mm_local, dtype=torch.int32), n_slices)
+        # series 1 is FFS: its coronal image is z-reversed, which must happen on the gathered rows
+        rows, mm = sharded.gather_rows(torch.from_numpy(np.stack(rows_local)), torch.tensor(mm_local, dtype=torch.int32), n_slices,
+                                       flip_z=[1])
         sel = torch.zeros((S, 4), dtype=torch.int32)
         for s in range(S):
             if sharded.owner_of_series(s, world) == rank:
@@ -53,10 +55,10 @@ def test_exchange_world2(tmp_path, n_slices):
     got = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
     for s in range(2):
         vol, inst = synth.phantom_series(n_slices, seed=s, shuffle_seed=None, size=64)
-        want = O.front_rows(vol)
+        want = O.front_rows(vol, "FFS" if s == 1 else "HFS")
         for g in got:
             assert np.array_equal(g["rows"][s], want)
             assert list(g["mm"][s]) == [int(want.min()), int(want.max())]
-            assert np.array_equal(O.minmax_u8(g["rows"][s]), O.front_slice_norm(vol))
+            assert np.array_equal(O.minmax_u8(g["rows"][s]), O.front_slice_norm(vol, "FFS" if s == 1 else "HFS"))
     assert np.array_equal(got[0]["sel"], got[1]["sel"])
     assert got[0]["sel"].tolist() == [[10, 20, 15, 1], [11, 21, 16, 1]]
