@@ -40,6 +40,22 @@ class Act:
         return self.buf[..., self.off:self.off + self.c].permute(0, 3, 1, 2)
 
 
+#: when a dict, ``conv`` adds the algorithmic work of every launch to it (bench.py's roofline accounting):
+#: "flops" (2 * MACs), "bytes" (input + output + residual + weights, each counted once), "launches"
+STATS = None
+
+
+def _account(L, B, Ho, Wo, x: Act, res) -> None:
+    g = L.cin if L.kind == "dw" else 1
+    STATS["flops"] = STATS.get("flops", 0) + 2 * B * Ho * Wo * L.cout * (L.cin // g) * L.k * L.k
+    H, W = x.buf.shape[1], x.buf.shape[2]
+    STATS["bytes"] = STATS.get("bytes", 0) + 2 * B * (H * W * L.cin + Ho * Wo * L.cout * (2 if res is not None else 1)) + L.w.numel() * L.w.element_size()
+    STATS["launches"] = STATS.get("launches", 0) + 1
+    k = STATS.setdefault("by_kind", {}).setdefault(L.kind, [0, 0])
+    k[0] += 2 * B * Ho * Wo * L.cout * (L.cin // g) * L.k * L.k
+    k[1] += 1
+
+
 def _new(B, H, W, C, dev) -> Act:
     return Act(torch.empty((B, H, W, C), dtype=torch.float16, device=dev))
 
@@ -97,6 +113,8 @@ def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, 
     if out is None:
         out = _new(B, Ho * up[0], Wo * up[0], max(8, (L.cout + 7) // 8 * 8), dev)
         out.c = L.cout
+    if STATS is not None:
+        _account(L, B, Ho, Wo, x, res)
     with torch.cuda.device(dev):
         if L.kind == "gemm":
             cabi.call("eitb_conv2d_nhwc", x.buf.data_ptr(), B, H, W, x.buf.shape[3], x.off, L.cin, L.w.data_ptr(),

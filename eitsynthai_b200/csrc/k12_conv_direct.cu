@@ -79,11 +79,13 @@ stem_gray_kernel(const __half* __restrict__ x, const float* __restrict__ w, cons
             wr[t][e] = w[(t * 3 + 0) * 32 + cgp * 8 + e] + w[(t * 3 + 1) * 32 + cgp * 8 + e] + w[(t * 3 + 2) * 32 + cgp * 8 + e];
 #pragma unroll
     for (int e = 0; e < 8; ++e) b8[e] = bias ? bias[cgp * 8 + e] : 0.f;
-    const long long total = (long long)N * Ho * Wo * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long o = i >> 2;
-        const int ox = (int)(o % Wo), oy = (int)((o / Wo) % Ho);
-        const long long n = o / ((long long)Wo * Ho);
+    const unsigned total = (unsigned)N * Ho * Wo * 4;              // < 2^32: checked by the launcher
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned o = i >> 2;
+        const unsigned orow = o / (unsigned)Wo;
+        const int ox = (int)(o - orow * Wo);
+        const unsigned n = orow / (unsigned)Ho;
+        const int oy = (int)(orow - n * Ho);
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = b8[e];
@@ -94,7 +96,7 @@ stem_gray_kernel(const __half* __restrict__ x, const float* __restrict__ w, cons
             for (int s = 0; s < 3; ++s) {
                 const int ix = 2 * ox - 1 + s;
                 const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-                const float v = ok ? __half2float(__ldg(x + ((n * H + iy) * W + ix) * 3)) : 0.f;
+                const float v = ok ? __half2float(__ldg(x + ((size_t)(n * H + iy) * W + ix) * 3)) : 0.f;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[e] = fmaf(v, wr[r * 3 + s][e], acc[e]);
             }
@@ -106,7 +108,7 @@ stem_gray_kernel(const __half* __restrict__ x, const float* __restrict__ w, cons
             const float a = act ? silu_f(acc[2 * e]) : acc[2 * e], b = act ? silu_f(acc[2 * e + 1]) : acc[2 * e + 1];
             h[e] = __floats2half2_rn(a, b);
         }
-        *reinterpret_cast<int4*>(y + o * y_ctot + y_coff + cgp * 8) = v4;
+        *reinterpret_cast<int4*>(y + (size_t)o * y_ctot + y_coff + cgp * 8) = v4;
     }
 }
 
@@ -126,13 +128,14 @@ __global__ void __launch_bounds__(256, 3)
 dwconv3x3_kernel(const __half* __restrict__ x, int x_ctot, int x_coff, const __half* __restrict__ w, const float* __restrict__ bias,
                  int N, int H, int W, int C, int act, __half* __restrict__ y, int y_ctot, int y_coff) {
     const int cg = C >> 2, strips = (H + DW_ROWS - 1) / DW_ROWS;
-    const long long total = (long long)N * strips * W * cg;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i % cg);
-        long long t = i / cg;
-        const int px = (int)(t % W); t /= W;
-        const int st = (int)(t % strips);
-        const long long n = t / strips;
+    const unsigned total = (unsigned)N * strips * W * cg;          // < 2^32: checked by the launcher
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        unsigned t = i / (unsigned)cg;
+        const int g = (int)(i - t * cg);
+        unsigned t2 = t / (unsigned)W;
+        const int px = (int)(t - t2 * W);
+        const size_t n = t2 / (unsigned)strips;
+        const int st = (int)(t2 - (unsigned)n * strips);
         float wr[9][4], b4[4];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
@@ -191,6 +194,7 @@ extern "C" int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, cons
     cudaStream_t s = (cudaStream_t)stream;
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * Ho * Wo;
+    if (total * 4 >= (1LL << 32)) return EITB_ERR_UNSUPPORTED;
     eitb_prof_begin("stem_conv_kernel", s);
     if (gray)
         stem_gray_kernel<<<eitb_grid(total * 4, 256, 8), 256, 0, s>>>((const __half*)x, w27, bias, N, H, W, Ho, Wo, act, (__half*)y, y_ctot,
@@ -208,6 +212,7 @@ extern "C" int eitb_dwconv3x3_nhwc(const void* x, int N, int H, int W, int x_cto
     if (C % 8 || x_ctot % 8 || x_coff % 8 || y_ctot % 8 || y_coff % 8) return EITB_ERR_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     const long long total = (long long)N * ((H + DW_ROWS - 1) / DW_ROWS) * W * (C / 4);
+    if (total >= (1LL << 32)) return EITB_ERR_UNSUPPORTED;
     const int grid = eitb_grid(total, 256, 3);
     eitb_prof_begin("dwconv3x3_kernel", s);
     dwconv3x3_kernel<<<grid, 256, 0, s>>>((const __half*)x, x_ctot, x_coff, (const __half*)w9, bias, N, H, W, C, act, (__half*)y,

@@ -14,6 +14,7 @@
 // Stages: threshold+erode -> dilate -> CC(background, 4, frame-linked) -> CC(filled, 8) ->
 // per-component 2*area accumulation -> arg-max -> write mask.
 #include "cc.cuh"
+#include "bitflood.cuh"
 
 namespace {
 
@@ -235,6 +236,15 @@ extern "C" int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope,
         eitb_prof_begin("morph5_bits_kernel", s);
         morph5_bits_kernel<false><<<eitb_grid(n_words, 256, 8), 256, 0, s>>>(b1, n_words, H, W / 32, b0);
         EITB_CHECK_LAUNCH();
+        if (eitb_flood::flood_supported(H, W)) {
+            // background reachable from the frame = outside every external contour: bit-parallel flood, then the
+            // 8-connected components of everything else straight from the bit image
+            uint32_t* outside = b1;
+            rc = eitb_flood::frame_flood<eitb_flood::SRC_BITS_ZERO>(b0, B, H, W, 1, 0, 0, 0, nullptr, outside, s);
+            if (rc != EITB_OK) return rc;
+            rc = cc_label<PRED_BIT_ZERO, 8>(outside, (size_t)H * W / 8, 0, B, H, W, 0, labB, s);
+            goto labelled;
+        }
         rc = cc_label<PRED_BIT_ZERO, 4>(b0, (size_t)H * W / 8, 0, B, H, W, 1, labA, s);         // background, frame-linked
     } else {
         eitb_prof_begin("thr_erode_kernel", s);
@@ -247,6 +257,7 @@ extern "C" int eitb_body_mask(const int16_t* px, int B, int H, int W, int slope,
     }
     if (rc != EITB_OK) return rc;
     rc = cc_label<PRED_LABEL_NOT_OUT, 8>(labA, (size_t)H * W * 4, 0, B, H, W, 0, labB, s);   // filled regions
+labelled:
     if (rc != EITB_OK) return rc;
     if (cudaMemsetAsync(area2, 0, n * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
     if (cudaMemsetAsync(best, 0xff, (size_t)B * 8, s) != cudaSuccess) return EITB_ERR_LAUNCH;  // -1

@@ -23,6 +23,7 @@
 // OpenCV's contour tracer: clockwise search from the west neighbour, then counter-clockwise
 // search from the previous pixel; a point is emitted where the chain direction changes).
 #include "cc.cuh"
+#include "bitflood.cuh"
 
 namespace {
 
@@ -230,6 +231,64 @@ contour_cand_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__
     }
 }
 
+// All three targets in one pass over the snapshot (bit-image path): byte-compare masks of 8 pixels per thread give the
+// "first pixel of a component" test for bone, muscle and adipose at once; survivors read one bit of the frame flood
+// of their target (is the pixel on my left outside every contour of this colour?) and trace their border.
+__device__ __forceinline__ unsigned eq_mask8(uint2 v, int t) {
+    const uint32_t tt = (uint32_t)t * 0x01010101u;
+    return ((((__vcmpeq4(v.x, tt) & 0x80808080u) * 0x00204081u) >> 28) | ((((__vcmpeq4(v.y, tt) & 0x80808080u) * 0x00204081u) >> 28) << 4));
+}
+
+__global__ void __launch_bounds__(256)
+contour_cand3_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ reach, int B, int H, int W,
+                     unsigned* __restrict__ bitmap, int words_per_img) {
+    const unsigned upr = (unsigned)W >> 3;                         // W % 32 == 0 on this path
+    const unsigned n = (unsigned)B * H * upr;                      // < 2^32 (checked by the launcher)
+    const int T[3] = {EITB_CODE_BONE, EITB_CODE_MUSCLE, EITB_CODE_ADIPOSE};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned rowid = i / upr;
+        const int x0 = (int)(i - rowid * upr) << 3;
+        const int b = (int)(rowid / (unsigned)H), y = (int)(rowid - (unsigned)b * H);
+        const uint8_t* img = src + (long long)b * H * W;
+        const uint8_t* row = img + (long long)y * W;
+        const uint2 cv = *reinterpret_cast<const uint2*>(row + x0);
+        const int lb = x0 > 0 ? row[x0 - 1] : -1;
+        uint2 uv = make_uint2(0u, 0u);
+        int ulb = -1, urb = -1;
+        if (y > 0) {
+            uv = *reinterpret_cast<const uint2*>(row - W + x0);
+            ulb = x0 > 0 ? row[x0 - 1 - W] : -1;
+            urb = x0 + 8 < W ? row[x0 + 8 - W] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int t = T[k];
+            const unsigned cur = eq_mask8(cv, t);
+            if (!cur) continue;
+            const unsigned up = y > 0 ? eq_mask8(uv, t) : 0u;
+            const unsigned left = lb == t, upl = ulb == t, upright = urb == t;
+            // a component's first pixel has no set neighbour earlier in raster order ...
+            unsigned tips = cur & ~((cur << 1) | left) & ~up & ~((up << 1) | upl) & ~((up >> 1) | (upright << 7)) & 0xffu;
+            while (tips) {
+                const int j = __ffs(tips) - 1;
+                tips &= tips - 1;
+                const int x = x0 + j, p = y * W + x;
+                // ... and an external contour has the frame-connected background of its colour on its left
+                if (x > 0) {
+                    const int q = p - 1;
+                    if (!((reach[((long long)b * 3 + k) * words_per_img + (q >> 5)] >> (q & 31)) & 1u)) continue;
+                }
+                int vx[5], vy[5];
+                const int nv = trace_simple(img, H, W, y, x, t, vx, vy);
+                if (nv > 5) continue;
+                bool first = true;                                  // p must be the raster-first vertex
+                for (int m = 0; m < nv; ++m) first = first && (vy[m] > y || (vy[m] == y && vx[m] >= x));
+                if (first) atomicOr(bitmap + ((long long)b * 3 + k) * words_per_img + (p >> 5), 1u << (p & 31));
+            }
+        }
+    }
+}
+
 // inside-or-on-boundary test against a closed polygon with integer vertices (exact)
 __device__ __forceinline__ bool in_poly(int x, int y, const int (&vx)[5], const int (&vy)[5], int nv) {
     bool in = false;
@@ -247,14 +306,18 @@ __device__ __forceinline__ bool in_poly(int x, int y, const int (&vx)[5], const 
 }
 
 // one warp per image, candidates in DESCENDING raster order (cv2 returns contours last-found first)
+// nt == 1: the candidates of target t0 in bitmap [B, words]; nt == 3: bone, muscle, adipose one after the other
+// (dict order, utils.py:782-787) from bitmap [B, 3, words]
 __global__ void __launch_bounds__(32)
-contour_repaint_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ code, int H, int W, int t,
+contour_repaint_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ code, int H, int W, int t0, int nt,
                        const unsigned* __restrict__ bitmap, int words_per_img) {
     const int b = blockIdx.x, lane = threadIdx.x;
     const uint8_t* simg = src + (long long)b * H * W;
     uint8_t* out = code + (long long)b * H * W;
-    const unsigned* bm = bitmap + (long long)b * words_per_img;
     const int nchunks = (words_per_img + 31) / 32;
+    for (int ti = 0; ti < nt; ++ti) {
+    const int t = nt == 1 ? t0 : ti == 0 ? EITB_CODE_BONE : ti == 1 ? EITB_CODE_MUSCLE : EITB_CODE_ADIPOSE;
+    const unsigned* bm = bitmap + ((long long)b * nt + ti) * words_per_img;
     for (int ch = nchunks - 1; ch >= 0; --ch) {
         const int w0 = ch * 32;
         const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
@@ -324,6 +387,8 @@ contour_repaint_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ co
             }
         }
     }
+    __syncwarp();
+    }
 }
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -370,6 +435,22 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
     }
     if (cudaMemcpyAsync(snap, code, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return EITB_ERR_LAUNCH;
     const int targets[3] = {EITB_CODE_BONE, EITB_CODE_MUSCLE, EITB_CODE_ADIPOSE};            // dict order, utils.py:782-787
+    if (eitb_flood::flood_supported(H, W) && !(reinterpret_cast<uintptr_t>(snap) & 15) && (size_t)B * 3 * words * 4 * 2 <= align256(n * 4) &&
+        n / 8 < (1ull << 32)) {
+        // bit-image path: one frame flood per (image, colour), one candidate pass and one repaint pass for all three
+        uint32_t* reach = reinterpret_cast<uint32_t*>(lab);                     // [B, 3, words] in the label area
+        unsigned* bitmap3 = reinterpret_cast<unsigned*>(lab) + (size_t)B * 3 * words;
+        int rc = eitb_flood::frame_flood<eitb_flood::SRC_U8_NE>(snap, B, H, W, 3, targets[0], targets[1], targets[2], nullptr, reach, s);
+        if (rc != EITB_OK) return rc;
+        if (cudaMemsetAsync(bitmap3, 0, (size_t)B * 3 * words * 4, s) != cudaSuccess) return EITB_ERR_LAUNCH;
+        eitb_prof_begin("contour_cand_kernel", s);
+        contour_cand3_kernel<<<eitb_grid((long long)n / 8, 256, 8), 256, 0, s>>>(snap, reach, B, H, W, bitmap3, words);
+        EITB_CHECK_LAUNCH();
+        eitb_prof_begin("contour_repaint_kernel", s);
+        contour_repaint_kernel<<<B, 32, 0, s>>>(snap, code, H, W, 0, 3, bitmap3, words);
+        EITB_CHECK_LAUNCH();
+        return EITB_OK;
+    }
     for (int k = 0; k < 3; ++k) {
         const int t = targets[k];
         const int rc = cc_label<PRED_CODE_NE, 4>(snap, (size_t)H * W, t, B, H, W, 1, lab, s, /*flatten=*/0);
@@ -379,7 +460,7 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
         contour_cand_kernel<<<grid, 256, 0, s>>>(snap, lab, B, H, W, t, bitmap, words);
         EITB_CHECK_LAUNCH();
         eitb_prof_begin("contour_repaint_kernel", s);
-        contour_repaint_kernel<<<B, 32, 0, s>>>(snap, code, H, W, t, bitmap, words);
+        contour_repaint_kernel<<<B, 32, 0, s>>>(snap, code, H, W, t, 1, bitmap, words);
         EITB_CHECK_LAUNCH();
     }
     return EITB_OK;
