@@ -156,13 +156,30 @@ class DICOMabc(abc.ABC):
         return out, body, int(n[0]), round(time.time() - t1, 3)
 
     def _finish(self, code, body, pixel_spacing, n_det, seg_time, mesh=None, extra=None):
+        """create_answer (utils.py:1019-1058): the reference's seven keys -- ``image`` (base64 PNG; here the colour
+        label image, the reference sends a collage of slice and mesh render), ``text_data`` ('' as
+        create_segmentation_results_cnt returns, utils.py:1013-1016), ``segmentation_time``, ``saved_file_name`` and
+        ``simulation_time`` ('' / 0.0: the pyEIT simulation is outside this path), ``status``, ``message`` -- plus what
+        the hot path produced: label codes, polygon list, per-element classes."""
         polygons = utils.codes_to_polygons(code, pixel_spacing, body)
         img_mesh, mesh_data = create_mesh(polygons[:2], polygons[2:], mesh=mesh) if (mesh is not None or body is not None) else (None, [])
-        ans = {"label_codes": code, "polygons": polygons, "mesh_data": mesh_data, "text_data": {"detections": n_det},
-               "segmentation_time": seg_time, "status": "success", "message": "Processing completed successfully"}
+        ans = {"image": self._png_base64(code), "text_data": "", "segmentation_time": seg_time, "saved_file_name": "",
+               "simulation_time": 0.0, "status": "success", "message": "Processing completed successfully",
+               "label_codes": code, "polygons": polygons, "mesh_data": mesh_data, "detections": n_det}
         if extra:
             ans.update(extra)
         return ans
+
+    @staticmethod
+    def _png_base64(code) -> str:
+        import base64
+        from io import BytesIO
+
+        from PIL import Image
+        bgr = utils.codes_to_color(code)                             # reference colours (utils.py:468-473)
+        buf = BytesIO()
+        Image.fromarray(np.ascontiguousarray(bgr[..., ::-1])).save(buf, format="PNG")   # cv2.COLOR_BGR2RGB, utils.py:1037
+        return base64.b64encode(buf.getvalue()).decode("utf-8")
 
 
 class DICOMSequencesToMask(DICOMabc):

@@ -236,6 +236,13 @@ def create_color_output(segmentation_masks_image, only_body_mask=None):
         return []
 
 
+def codes_to_color(code) -> np.ndarray:
+    """(S,S) u8 code image -> the reference's BGR label image (colours of utils.py:468-473) through K7's
+    eitb_codes_to_bgr."""
+    c = _to_dev(np.ascontiguousarray(code)[None], np.uint8)
+    return ops.codes_to_bgr(c)[0].cpu().numpy()
+
+
 def codes_to_polygons(code, pixel_spacing, only_body_mask=None):
     """create_list_crd_from_color_output (utils.py:1191-1279) on a code image.  Contour extraction
     stays on OpenCV like in the reference (row 2 of SURVEY §8(f), next to move to the GPU)."""
