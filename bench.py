@@ -394,7 +394,7 @@ def run_b200(args):
     local_slices = S * nl
     # algorithmic bytes per 512x512 slice and launch; CC passes count source + label traffic
     per_slice_bytes = {
-        "hu_window_kernel": px * (2 + 1 + 6), "thr_bits_kernel": px * 2 + px // 8, "morph5_bits_kernel": px // 4,
+        "hu_window_kernel": px * (2 + 1 + (1 if pipe.fused_input else 6)), "thr_bits_kernel": px * 2 + px // 8, "morph5_bits_kernel": px // 4,
         "frame_flood_kernel": px // 4, "cc_local_kernel": px // 8 + px * 4, "cc_merge_kernel": 15 * SIZE * 8, "cc_flatten_kernel": px * 8,
         "area_kernel": px * 4, "best_kernel": px * 8, "write_mask_kernel": px * 5,
         "nms_kernel": 40 * 5376 * 2 + MAX_DET * 38 * 4,
@@ -402,7 +402,7 @@ def run_b200(args):
         "fill_body_kernel": px * 3, "small_first_kernel": px, "small_repaint_kernel": px // 8,
         "contour_cand_kernel": px + 3 * px // 8, "contour_repaint_kernel": 3 * px // 8,
         "head_decode_kernel": 5376 * (64 + 8 + 32 + 40) * 2, "sppf_kernel": 256 * 256 * 5 * 2,
-        "stem_conv_kernel": px * 6 + (px // 4) * 64, "upsample2x_concat_kernel": 2 * (1024 * 768 + 4096 * 512) * 2,
+        "stem_conv_kernel": px * (1 if pipe.fused_input else 6) + (px // 4) * 64, "upsample2x_concat_kernel": 2 * (1024 * 768 + 4096 * 512) * 2,
     }
     per_slice_bytes["mask_decode_tc_kernel"] = per_slice_bytes["mask_decode_kernel"]
     kroof = {}
@@ -451,6 +451,8 @@ def run_b200(args):
             iso["K1_hu_window_nchw"] = {"ms": t, "bytes_per_slice": px * (2 + 1 + 6)}
             t = _events_ms(torch, lambda: ops.hu_window(pxd, body_mask=body, want_u8=False, nchw_dtype=torch.float16, channels_last=True))
             iso["K1_hu_window_nhwc"] = {"ms": t, "bytes_per_slice": px * (2 + 1 + 6)}
+            t = _events_ms(torch, lambda: ops.hu_window(pxd, body_mask=body, want_u8=True, nchw_dtype=None))
+            iso["K1_hu_window_u8_for_fused_stem"] = {"ms": t, "bytes_per_slice": px * (2 + 1 + 1)}
             t = _events_ms(torch, lambda: ops.body_mask(pxd, 1, -1024, True))
             iso["K2_body_mask"] = {"ms": t, "bytes_per_slice": 786432}
             hd, pr = synth.random_heads(8, 48, seed=3)
@@ -486,8 +488,7 @@ def run_b200(args):
 
             def teacher_chunk():
                 body_ = ops.body_mask(pxd, 1, -1024, True)
-                _, x_ = ops.hu_window(pxd, body_mask=body_, want_u8=False, nchw_dtype=torch.float16, channels_last=True)
-                pipe._net(pipe.axial_model_512, x_)                # the CNN runs; its head is replaced by the teacher's
+                pipe._net(pipe.axial_model_512, pipe.window_input(pxd, body_))                # the CNN runs; its head is replaced by the teacher's
                 d_, _, n_ = ops.nms(thd, 4, CONF, IOU, MAX_DET, want_idx=False)
                 c_, _, _ = ops.mask_decode(d_, n_, tpr, pipe.mask_variant)
                 ops.label_cleanup(c_, body_)

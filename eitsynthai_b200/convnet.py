@@ -135,6 +135,26 @@ def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, 
     return out
 
 
+def stem_u8(img: torch.Tensor, L: PackedConv) -> Act:
+    """The stem on the u8 window image [B, H, W] (K1's u8 output): preprocess (u8 -> fp16 / 255, three equal channels)
+    fused into the kernel's tile loader."""
+    assert L.kind == "stem" and img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+    B, H, W = img.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = _new(B, Ho, Wo, L.cout, img.device)
+    if STATS is not None:
+        STATS["flops"] = STATS.get("flops", 0) + 2 * B * Ho * Wo * L.cout * 27
+        STATS["bytes"] = STATS.get("bytes", 0) + B * H * W + 2 * B * Ho * Wo * L.cout + L.w.numel() * 4
+        STATS["launches"] = STATS.get("launches", 0) + 1
+        k = STATS.setdefault("by_kind", {}).setdefault("stem", [0, 0])
+        k[0] += 2 * B * Ho * Wo * L.cout * 27
+        k[1] += 1
+    with torch.cuda.device(img.device):
+        cabi.call("eitb_stem_conv3x3s2_nhwc", img.data_ptr(), B, H, W, L.w.data_ptr(), 0 if L.bias is None else L.bias.data_ptr(),
+                  L.cout, int(L.act), 2, out.buf.data_ptr(), out.buf.shape[3], 0, _stream(img.device))
+    return out
+
+
 class ConvNet:
     """Executes a fused ``YOLO11sSeg`` with libeitb200 kernels.  ``net(x)`` takes the channels-last
     [B, 3, H, W] fp16 input K1 produces and returns (head [B, 4+nc+nm, A] fp16, protos [B, 32, H/4, W/4]
@@ -248,11 +268,14 @@ class ConvNet:
     @torch.no_grad()
     def __call__(self, x: torch.Tensor, gray: bool = False):
         """``gray``: the three channels of ``x`` are equal (K1 / letterbox output) -- lets the stem read one."""
-        assert x.is_cuda and x.dtype == torch.float16 and x.shape[1] == 3 and x.is_contiguous(memory_format=torch.channels_last)
         p = self.p
         dev = x.device
-        a = Act(x.permute(0, 2, 3, 1))                              # NHWC view of the channels-last input
-        a = conv(conv(a, p["l0"], gray=gray), p["l1"])
+        if x.dtype == torch.uint8:                                  # the u8 window image [B, H, W]: preprocess fused into the stem
+            a = stem_u8(x, p["l0"])
+        else:
+            assert x.is_cuda and x.dtype == torch.float16 and x.shape[1] == 3 and x.is_contiguous(memory_format=torch.channels_last)
+            a = conv(Act(x.permute(0, 2, 3, 1)), p["l0"], gray=gray)    # NHWC view of the channels-last input
+        a = conv(a, p["l1"])
         a = self._c3k2(a, p["l2"])
         p3 = self._c3k2(conv(a, p["l3"]), p["l4"])
         p4 = self._c3k2(conv(p3, p["l5"]), p["l6"])

@@ -20,7 +20,7 @@ namespace eitb_flood {
 
 constexpr int kWarps = 4;
 
-enum Src { SRC_U8_NE = 0, SRC_BITS_ZERO = 1 };
+enum Src { SRC_U8_NE = 0, SRC_BITS_ZERO = 1, SRC_U8_EQ = 2 };
 
 // multi-word a + s over the lanes [0, wpr); returns this lane's word of the sum
 __device__ __forceinline__ uint32_t mw_add(uint32_t a, uint32_t s, int lane, unsigned lane_mask) {
@@ -57,13 +57,14 @@ __device__ __forceinline__ uint32_t ne_word(const uint8_t* p, int t) {
     return out;
 }
 
-// grid (jobs_per_image, B).  SRC_U8_NE: src u8 [B,H,W], the set of job j is {src != targets[j]}.
+// grid (jobs_per_image, B).  SRC_U8_NE: src u8 [B,H,W], the set of job j is {src != targets[j]}; SRC_U8_EQ: {src == targets[j]}.
 // SRC_BITS_ZERO: src bit image [B, H*W/32] words, one job, the set is the zero bits.
-// reach_out [B, jobs, H*W/32]: bit = pixel is in the set and frame-connected.
+// reach_out [B, out_jobs, H*W/32], this launch fills the jobs [job_off, job_off + gridDim.x): bit = pixel is in the
+// set and frame-connected.
 template <int SRC>
 __global__ void __launch_bounds__(kWarps * 32)
 frame_flood_kernel(const void* __restrict__ src, int H, int W, int t0, int t1, int t2, const int* __restrict__ skip,
-                   uint32_t* __restrict__ reach_out) {
+                   uint32_t* __restrict__ reach_out, int out_jobs, int job_off) {
     extern __shared__ uint32_t fsm[];
     const int wpr = W >> 5, job = blockIdx.x, b = blockIdx.y, jobs = gridDim.x;
     if (skip && skip[b * jobs + job]) return;
@@ -80,6 +81,7 @@ frame_flood_kernel(const void* __restrict__ src, int H, int W, int t0, int t1, i
         uint32_t a = 0;
         if (lane < wpr) {
             if (SRC == SRC_U8_NE) a = ne_word(reinterpret_cast<const uint8_t*>(src) + ((size_t)b * H + y) * W + lane * 32, t);
+            else if (SRC == SRC_U8_EQ) a = ~ne_word(reinterpret_cast<const uint8_t*>(src) + ((size_t)b * H + y) * W + lane * 32, t);
             else a = ~reinterpret_cast<const uint32_t*>(src)[((size_t)b * H + y) * wpr + lane];
         }
         uint32_t s = (y == 0 || y == H - 1) ? a : 0u;
@@ -120,7 +122,7 @@ frame_flood_kernel(const void* __restrict__ src, int H, int W, int t0, int t1, i
         }
         if (!__syncthreads_or(changed ? 1 : 0)) break;
     }
-    uint32_t* out = reach_out + ((size_t)b * jobs + job) * H * wpr;
+    uint32_t* out = reach_out + ((size_t)b * out_jobs + job_off + job) * H * wpr;
     for (int i = threadIdx.x; i < H * wpr; i += kWarps * 32) out[i] = reach[i];
 }
 
@@ -131,13 +133,14 @@ inline bool flood_supported(int H, int W) {
 // src: see the kernel; reach_out [B, jobs, H*W/32] words
 template <int SRC>
 int frame_flood(const void* src, int B, int H, int W, int jobs, int t0, int t1, int t2, const int* skip, uint32_t* reach_out,
-                cudaStream_t s) {
+                cudaStream_t s, int out_jobs = 0, int job_off = 0) {
     if (!flood_supported(H, W) || jobs < 1 || jobs > 3 || B > 65535) return EITB_ERR_UNSUPPORTED;
     const size_t smem = (size_t)H * (W >> 5) * 8;
     if (cudaFuncSetAttribute(frame_flood_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     eitb_prof_begin("frame_flood_kernel", s);
-    frame_flood_kernel<SRC><<<dim3(jobs, B), kWarps * 32, smem, s>>>(src, H, W, t0, t1, t2, skip, reach_out);
+    frame_flood_kernel<SRC><<<dim3(jobs, B), kWarps * 32, smem, s>>>(src, H, W, t0, t1, t2, skip, reach_out, out_jobs > 0 ? out_jobs : jobs,
+                                                                     job_off);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

@@ -112,75 +112,160 @@ stem_gray_kernel(const __half* __restrict__ x, const float* __restrict__ w, cons
     }
 }
 
-// depthwise 3x3, stride 1, pad 1; w [9][C] fp16.  One thread = 4 channels x one column x a strip of DW_ROWS output
-// rows: the nine weight vectors stay in registers and every input row is loaded once (3 x 8 B, the next row
-// prefetched while this one is used) and feeds the three output rows it touches -- 3.75 loads per output, not 18.
-constexpr int DW_ROWS = 8;
+// Stem on the u8 window image itself (K1's out_u8 / the body-masked classic_norm image): the network input
+// x = half(u8 / 255) replicated to three channels never exists in HBM -- the kernel converts through a 256-entry table
+// while it stages a (2*TO_H+1) x (2*TO_W+1) input tile in shared memory, and the three equal channels fold into one 9-tap
+// filter.  One thread = one output column x 8 output channels x TO_H output rows (its 72 weights stay in registers);
+// four neighbouring threads store the 64 contiguous bytes of a pixel, a warp 512.  SiLU through one tanh.approx per
+// output: x * sigmoid(x) = h + h * tanh(h), h = x / 2.
+constexpr int ST_TO_H = 8, ST_TO_W = 64, ST_IN_H = 2 * ST_TO_H + 1, ST_IN_W = 2 * ST_TO_W + 1, ST_PITCH = ST_IN_W + 3;
 
-__device__ __forceinline__ void dw_fma4(float* acc, const uint2& xv, const float* wf) {
-    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-    const float2 a = __half22float2(xh[0]), b = __half22float2(xh[1]);
-    acc[0] = fmaf(a.x, wf[0], acc[0]); acc[1] = fmaf(a.y, wf[1], acc[1]);
-    acc[2] = fmaf(b.x, wf[2], acc[2]); acc[3] = fmaf(b.y, wf[3], acc[3]);
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
 }
 
-__global__ void __launch_bounds__(256, 3)
-dwconv3x3_kernel(const __half* __restrict__ x, int x_ctot, int x_coff, const __half* __restrict__ w, const float* __restrict__ bias,
-                 int N, int H, int W, int C, int act, __half* __restrict__ y, int y_ctot, int y_coff) {
-    const int cg = C >> 2, strips = (H + DW_ROWS - 1) / DW_ROWS;
-    const unsigned total = (unsigned)N * strips * W * cg;          // < 2^32: checked by the launcher
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        unsigned t = i / (unsigned)cg;
-        const int g = (int)(i - t * cg);
-        unsigned t2 = t / (unsigned)W;
-        const int px = (int)(t - t2 * W);
-        const size_t n = t2 / (unsigned)strips;
-        const int st = (int)(t2 - (unsigned)n * strips);
-        float wr[9][4], b4[4];
+__global__ void __launch_bounds__(256, 2)
+stem_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int N, int H, int W,
+               int Ho, int Wo, int act, __half* __restrict__ y, int y_ctot, int y_coff, int tiles_x, int tiles_y) {
+    __shared__ float lut[256];
+    __shared__ float tile[ST_IN_H][ST_PITCH];
+    const int cgp = threadIdx.x & 3, col = threadIdx.x >> 2;       // 8 of the 32 output channels; output column in the tile
+    lut[threadIdx.x] = __half2float(unit_from_u8<__half>((int)threadIdx.x));
+    float wr[9][8], b8[8];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const uint2 wv = __ldg(reinterpret_cast<const uint2*>(w + k * C + g * 4));
-            const __half2* wh = reinterpret_cast<const __half2*>(&wv);
-            const float2 p = __half22float2(wh[0]), q = __half22float2(wh[1]);
-            wr[k][0] = p.x; wr[k][1] = p.y; wr[k][2] = q.x; wr[k][3] = q.y;
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            wr[t][e] = w[(t * 3 + 0) * 32 + cgp * 8 + e] + w[(t * 3 + 1) * 32 + cgp * 8 + e] + w[(t * 3 + 2) * 32 + cgp * 8 + e];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) b8[e] = bias ? bias[cgp * 8 + e] : 0.f;
+    const int total = N * tiles_y * tiles_x;
+    for (int tix = blockIdx.x; tix < total; tix += gridDim.x) {
+        const int tx = tix % tiles_x, ty = (tix / tiles_x) % tiles_y, n = tix / (tiles_x * tiles_y);
+        const int ox0 = tx * ST_TO_W, oy0 = ty * ST_TO_H;
+        const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+        const uint8_t* img = x + (size_t)n * H * W;
+        __syncthreads();                                           // the previous tile is consumed (and the table is written)
+        for (int i = threadIdx.x; i < ST_IN_H * ST_IN_W; i += 256) {
+            const int r = i / ST_IN_W, c = i - r * ST_IN_W;
+            const int iy = iy0 + r, ix = ix0 + c;
+            tile[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? lut[__ldg(img + (size_t)iy * W + ix)] : 0.f;
         }
+        __syncthreads();
+        const int ox = ox0 + col;
+        if (ox >= Wo) continue;
+        float r0[3], r1[3], r2[3];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) b4[e] = bias ? __ldg(bias + g * 4 + e) : 0.f;
-        const int y0 = st * DW_ROWS, y1 = min(y0 + DW_ROWS, H);
-        float a0[4], a1[4], a2[4];                              // output rows iy-1, iy, iy+1 while input row iy is read
+        for (int s = 0; s < 3; ++s) r0[s] = tile[0][2 * col + s];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { a0[e] = b4[e]; a1[e] = b4[e]; a2[e] = b4[e]; }
-        const bool has_l = px > 0, has_r = px + 1 < W;
-        const uint2 z = make_uint2(0u, 0u);
-        auto load = [&](int iy, uint2& l, uint2& c, uint2& r) {
-            if (iy >= 0 && iy < H) {
-                const __half* row = x + ((n * H + iy) * W + px) * x_ctot + x_coff + g * 4;
-                l = has_l ? __ldg(reinterpret_cast<const uint2*>(row - x_ctot)) : z;
-                c = __ldg(reinterpret_cast<const uint2*>(row));
-                r = has_r ? __ldg(reinterpret_cast<const uint2*>(row + x_ctot)) : z;
-            } else {
-                l = z; c = z; r = z;
-            }
-        };
-        uint2 xl, xc, xr, nl, nc, nr;
-        load(y0 - 1, xl, xc, xr);
-        for (int iy = y0 - 1; iy <= y1; ++iy) {
-            load(iy + 1 <= y1 ? iy + 1 : -1, nl, nc, nr);       // prefetch the next input row
-            // input row iy is tap row 2 of output iy-1 (a0), row 1 of output iy (a1), row 0 of output iy+1 (a2)
-            dw_fma4(a0, xl, wr[6]); dw_fma4(a0, xc, wr[7]); dw_fma4(a0, xr, wr[8]);
-            dw_fma4(a1, xl, wr[3]); dw_fma4(a1, xc, wr[4]); dw_fma4(a1, xr, wr[5]);
-            dw_fma4(a2, xl, wr[0]); dw_fma4(a2, xc, wr[1]); dw_fma4(a2, xr, wr[2]);
-            const int oy = iy - 1;                              // a0 is complete once input row oy + 1 has been added
-            if (oy >= y0 && oy < y1) {
-                uint2 v;
-                __half2* h = reinterpret_cast<__half2*>(&v);
-                h[0] = __floats2half2_rn(act ? silu_f(a0[0]) : a0[0], act ? silu_f(a0[1]) : a0[1]);
-                h[1] = __floats2half2_rn(act ? silu_f(a0[2]) : a0[2], act ? silu_f(a0[3]) : a0[3]);
-                *reinterpret_cast<uint2*>(y + ((n * H + oy) * W + px) * y_ctot + y_coff + g * 4) = v;
+        for (int r = 0; r < ST_TO_H; ++r) {
+            const int oy = oy0 + r;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) { r1[s] = tile[2 * r + 1][2 * col + s]; r2[s] = tile[2 * r + 2][2 * col + s]; }
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = b8[e];
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    acc[e] = fmaf(r0[s], wr[s][e], acc[e]);
+                    acc[e] = fmaf(r1[s], wr[3 + s][e], acc[e]);
+                    acc[e] = fmaf(r2[s], wr[6 + s][e], acc[e]);
+                }
+            if (oy < Ho) {
+                int4 v4;
+                __half2* h = reinterpret_cast<__half2*>(&v4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float a = act ? silu_tanh(acc[2 * e]) : acc[2 * e], b = act ? silu_tanh(acc[2 * e + 1]) : acc[2 * e + 1];
+                    h[e] = __floats2half2_rn(a, b);
+                }
+                *reinterpret_cast<int4*>(y + ((size_t)(n * Ho + oy) * Wo + ox) * y_ctot + y_coff + cgp * 8) = v4;
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { a0[e] = a1[e]; a1[e] = a2[e]; a2[e] = b4[e]; }
-            xl = nl; xc = nc; xr = nr;
+            for (int s = 0; s < 3; ++s) r0[s] = r2[s];
+        }
+    }
+}
+
+// depthwise 3x3, stride 1, pad 1; w [9][C] fp16.  One thread = 8 channels (one 16-byte vector) x DW_PX consecutive
+// output pixels of one row: its 3 x (DW_PX + 2) input vectors are 18 independent 16-byte loads issued back to back (288 B
+// in flight per thread -- the round-1 kernel had 24 B and sat at 19 % of the DRAM peak), the 72 weights live in
+// registers, and every loaded vector feeds up to three outputs.  A CTA covers DW_ROWS rows x a run of pixels x all channel
+// groups, channel group fastest (a pixel's C * 2 bytes are contiguous), so the vertical re-use of input rows is served by
+// L1 and the DRAM sees every input byte about 1.5 times.
+constexpr int DW_PX = 4, DW_ROWS = 4, DW_THREADS = 256;
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dwconv3x3_kernel(const __half* __restrict__ x, int x_ctot, int x_coff, const __half* __restrict__ w, const float* __restrict__ bias,
+                 int N, int H, int W, int C, int act, __half* __restrict__ y, int y_ctot, int y_coff, int xb_per_cta, int tiles_x,
+                 int tiles_y) {
+    const int cgs = C >> 3;
+    const int g = threadIdx.x % cgs;                               // channel group
+    const int xb = (threadIdx.x / cgs) % xb_per_cta;               // block of DW_PX pixels inside the CTA's run
+    const int rr = threadIdx.x / (cgs * xb_per_cta);               // row inside the CTA's strip
+    float wr[9][8], b8[8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int4 wv = __ldg(reinterpret_cast<const int4*>(w + k * C + g * 8));
+        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(wh[e]); wr[k][2 * e] = f.x; wr[k][2 * e + 1] = f.y; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) b8[e] = bias ? __ldg(bias + g * 8 + e) : 0.f;
+    const int total = N * tiles_y * tiles_x;
+    for (int tix = blockIdx.x; tix < total; tix += gridDim.x) {
+        const int tx = tix % tiles_x, ty = (tix / tiles_x) % tiles_y, n = tix / (tiles_x * tiles_y);
+        const int oy = ty * DW_ROWS + rr, ox0 = (tx * xb_per_cta + xb) * DW_PX;
+        if (rr >= DW_ROWS || oy >= H || ox0 >= W) continue;
+        int4 in[3][DW_PX + 2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int iy = oy - 1 + r;
+#pragma unroll
+            for (int c = 0; c < DW_PX + 2; ++c) {
+                const int ix = ox0 - 1 + c;
+                in[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                               ? __ldg(reinterpret_cast<const int4*>(x + ((size_t)(n * H + iy) * W + ix) * x_ctot + x_coff + g * 8))
+                               : make_int4(0, 0, 0, 0);
+            }
+        }
+        float acc[DW_PX][8];
+#pragma unroll
+        for (int j = 0; j < DW_PX; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j][e] = b8[e];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < DW_PX + 2; ++c) {
+                float f[8];
+                const __half2* h = reinterpret_cast<const __half2*>(&in[r][c]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const int j = c - s;                           // input column c is tap s of output pixel c - s
+                    if (j >= 0 && j < DW_PX) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(f[e], wr[r * 3 + s][e], acc[j][e]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int j = 0; j < DW_PX; ++j) {
+            if (ox0 + j >= W) break;
+            int4 v;
+            __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                h[e] = __floats2half2_rn(act ? silu_tanh(acc[j][2 * e]) : acc[j][2 * e], act ? silu_tanh(acc[j][2 * e + 1]) : acc[j][2 * e + 1]);
+            *reinterpret_cast<int4*>(y + ((size_t)(n * H + oy) * W + ox0 + j) * y_ctot + y_coff + g * 8) = v;
         }
     }
 }
@@ -196,7 +281,13 @@ extern "C" int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, cons
     const long long total = (long long)N * Ho * Wo;
     if (total * 4 >= (1LL << 32)) return EITB_ERR_UNSUPPORTED;
     eitb_prof_begin("stem_conv_kernel", s);
-    if (gray)
+    if (gray == 2) {                                               // x is the u8 window image [N,H,W]
+        const int tiles_x = eitb_div_up(Wo, ST_TO_W), tiles_y = eitb_div_up(Ho, ST_TO_H);
+        const long long tiles = (long long)N * tiles_x * tiles_y;
+        if (tiles > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
+        const int grid = tiles < 2 * EITB_NUM_SMS ? (int)tiles : 2 * EITB_NUM_SMS;
+        stem_u8_kernel<<<grid, 256, 0, s>>>((const uint8_t*)x, w27, bias, N, H, W, Ho, Wo, act, (__half*)y, y_ctot, y_coff, tiles_x, tiles_y);
+    } else if (gray)
         stem_gray_kernel<<<eitb_grid(total * 4, 256, 8), 256, 0, s>>>((const __half*)x, w27, bias, N, H, W, Ho, Wo, act, (__half*)y, y_ctot,
                                                                       y_coff);
     else
@@ -209,14 +300,20 @@ extern "C" int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, cons
 extern "C" int eitb_dwconv3x3_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_coff, int C, const void* w9, const float* bias,
                                    int act, void* y, int y_ctot, int y_coff, eitb_stream_t stream) {
     if (!x || !w9 || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0) return EITB_ERR_BAD_ARG;
-    if (C % 8 || x_ctot % 8 || x_coff % 8 || y_ctot % 8 || y_coff % 8) return EITB_ERR_UNSUPPORTED;
+    if (C % 8 || x_ctot % 8 || x_coff % 8 || y_ctot % 8 || y_coff % 8 || C / 8 > DW_THREADS) return EITB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w9)) & 15) return EITB_ERR_BAD_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    const long long total = (long long)N * ((H + DW_ROWS - 1) / DW_ROWS) * W * (C / 4);
-    if (total >= (1LL << 32)) return EITB_ERR_UNSUPPORTED;
-    const int grid = eitb_grid(total, 256, 3);
+    const int cgs = C / 8;
+    int xb = DW_THREADS / (cgs * DW_ROWS);                        // pixel blocks per CTA row
+    if (xb < 1) xb = 1;
+    const int tiles_x = eitb_div_up(W, xb * DW_PX), tiles_y = eitb_div_up(H, DW_ROWS);
+    const long long tiles = (long long)N * tiles_x * tiles_y;
+    if (tiles > 0x7fffffffLL || (long long)N * H * W * x_ctot >= (1LL << 40)) return EITB_ERR_UNSUPPORTED;
+    const int resident = eitb_resident_ctas(dwconv3x3_kernel, DW_THREADS, 0);
+    const int grid = tiles < resident ? (int)tiles : resident;
     eitb_prof_begin("dwconv3x3_kernel", s);
-    dwconv3x3_kernel<<<grid, 256, 0, s>>>((const __half*)x, x_ctot, x_coff, (const __half*)w9, bias, N, H, W, C, act, (__half*)y,
-                                          y_ctot, y_coff);
+    dwconv3x3_kernel<<<grid, DW_THREADS, 0, s>>>((const __half*)x, x_ctot, x_coff, (const __half*)w9, bias, N, H, W, C, act, (__half*)y,
+                                                  y_ctot, y_coff, xb, tiles_x, tiles_y);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

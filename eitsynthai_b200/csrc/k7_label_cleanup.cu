@@ -102,15 +102,122 @@ small_first_kernel(const uint8_t* __restrict__ code, const int* __restrict__ any
     }
 }
 
-// one warp per image, candidates in ascending raster order
-__global__ void __launch_bounds__(32)
+// Order-dependent repaints, parallel where the order cannot matter: a candidate reads and writes only the bounding box
+// of its pixels grown by one pixel.  Every candidate registers that box in a coarse grid of cells (shared memory, one
+// counter per cell); a candidate whose cells all count exactly one is isolated -- no other candidate's reads or writes
+// come near it -- so the eight warps of the CTA process isolated candidates concurrently and clear their bits; one warp
+// then walks the remaining (conflicting) candidates in the reference's order.
+constexpr int kRepaintWarps = 8;
+constexpr int kMaxCells = 4096;
+
+__device__ __forceinline__ int cell_shift_for(int H, int W) {
+    int cs = 3;
+    while (((H >> cs) + 1) * ((W >> cs) + 1) > kMaxCells) ++cs;
+    return cs;
+}
+// lanes cooperate: add `delta` to (delta != 0) or test == 1 (delta == 0) every cell of the box; returns "all cells == 1"
+__device__ __forceinline__ bool cells_box(int* cells, int cw, int cs, int x0, int y0, int x1, int y1, int delta, int lane, int nlanes) {
+    const int cx0 = x0 >> cs, cx1 = x1 >> cs, cy0 = y0 >> cs, cy1 = y1 >> cs;
+    const int bw = cx1 - cx0 + 1, total = bw * (cy1 - cy0 + 1);
+    bool ok = true;
+    for (int c = lane; c < total; c += nlanes) {
+        int* cell = cells + (cy0 + c / bw) * cw + cx0 + c % bw;
+        if (delta) atomicAdd(cell, delta);
+        else ok = ok && *cell == 1;
+    }
+    return ok;
+}
+
+// one candidate (warp-cooperative, uniform control flow): relabel the < 5-pixel component that starts at p
+__device__ __forceinline__ void small_repaint_one(uint8_t* img, int H, int W, int p, int lane) {
+    const int dY[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, dX[8] = {-1, 0, 1, -1, 1, -1, 0, 1};       // utils.py:734-736
+    int px[5];
+    const int n = small_component(img, H, W, p, px);               // uniform across the warp
+    const int d = lane >> 2, k = lane & 3;
+    int v = 0;
+    if (k < n) {
+        const int y = px[k] / W + dY[d], x = px[k] % W + dX[d];
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const uint8_t c = ldv(img + y * W + x);
+            if (not_bg(c)) v = c;
+        }
+    }
+    // Counter.most_common(1): highest count, first seen wins ties
+    int best = EITB_CODE_MUSCLE, best_cnt = 0, best_first = 64;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const int val = ci == 0 ? EITB_CODE_ADIPOSE : ci == 1 ? EITB_CODE_LUNG : EITB_CODE_BONE;
+        const unsigned m = __ballot_sync(0xffffffffu, v == val);
+        const int cnt = __popc(m), first = m ? __ffs(m) - 1 : 64;
+        if (cnt > best_cnt || (cnt == best_cnt && cnt > 0 && first < best_first)) { best = val; best_cnt = cnt; best_first = first; }
+    }
+    // any other non-background code (does not occur in overlay images) is left alone
+    __syncwarp();
+    if (d == 0 && k < n) __stcg(img + px[k], (uint8_t)best);
+    __syncwarp();
+}
+
+// the box a small candidate touches: its (at most four) pixels grown by one
+__device__ __forceinline__ void small_box(const uint8_t* img, int H, int W, int p, int& x0, int& y0, int& x1, int& y1) {
+    int px[5];
+    const int n = small_component(img, H, W, p, px);
+    x0 = W; y0 = H; x1 = -1; y1 = -1;
+    for (int k = 0; k < n && k < 4; ++k) {
+        const int y = px[k] / W, x = px[k] - y * W;
+        x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+    }
+    x0 = max(x0 - 1, 0); y0 = max(y0 - 1, 0); x1 = min(x1 + 1, W - 1); y1 = min(y1 + 1, H - 1);
+}
+
+// one CTA per image; candidates in ascending raster order
+__global__ void __launch_bounds__(kRepaintWarps * 32)
 small_repaint_kernel(uint8_t* __restrict__ code, const int* __restrict__ anybody, int H, int W,
-                     const unsigned* __restrict__ bitmap, int words_per_img) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+                     unsigned* __restrict__ bitmap, int words_per_img) {
+    __shared__ int cells[kMaxCells];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (!anybody[b]) return;
     uint8_t* img = code + (long long)b * H * W;
-    const unsigned* bm = bitmap + (long long)b * words_per_img;
-    const int dY[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, dX[8] = {-1, 0, 1, -1, 1, -1, 0, 1};       // utils.py:734-736
+    unsigned* bm = bitmap + (long long)b * words_per_img;
+    const int cs = cell_shift_for(H, W), cw = (W >> cs) + 1;
+    for (int i = threadIdx.x; i < kMaxCells; i += kRepaintWarps * 32) cells[i] = 0;
+    __syncthreads();
+    // A. every candidate registers its box (one lane per bitmap word)
+    for (int w = threadIdx.x; w < words_per_img; w += kRepaintWarps * 32) {
+        unsigned word = bm[w];
+        while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            int x0, y0, x1, y1;
+            small_box(img, H, W, (w << 5) + bit, x0, y0, x1, y1);
+            cells_box(cells, cw, cs, x0, y0, x1, y1, 1, 0, 1);
+        }
+    }
+    __syncthreads();
+    // B. isolated candidates, all warps (a chunk of 32 words per warp trip)
+    for (int w0 = warp * 32; w0 < words_per_img; w0 += kRepaintWarps * 32) {
+        const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
+        unsigned keep = mine;
+        unsigned nz = __ballot_sync(0xffffffffu, mine != 0);
+        while (nz) {
+            const int wl = __ffs(nz) - 1;
+            nz &= nz - 1;
+            unsigned word = __shfl_sync(0xffffffffu, mine, wl);
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                const int p = ((w0 + wl) << 5) + bit;
+                int x0, y0, x1, y1;
+                small_box(img, H, W, p, x0, y0, x1, y1);           // uniform
+                if (!__all_sync(0xffffffffu, cells_box(cells, cw, cs, x0, y0, x1, y1, 0, lane, 32))) continue;
+                small_repaint_one(img, H, W, p, lane);
+                if (lane == wl) keep &= ~(1u << bit);
+            }
+        }
+        if (keep != mine) bm[w0 + lane] = keep;
+    }
+    __syncthreads();
+    // C. the rest, in order, one warp
+    if (warp != 0) return;
     for (int w0 = 0; w0 < words_per_img; w0 += 32) {
         const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
         unsigned nz = __ballot_sync(0xffffffffu, mine != 0);
@@ -121,31 +228,7 @@ small_repaint_kernel(uint8_t* __restrict__ code, const int* __restrict__ anybody
             while (word) {
                 const int bit = __ffs(word) - 1;
                 word &= word - 1;
-                const int p = ((w0 + wl) << 5) + bit;
-                int px[5];
-                const int n = small_component(img, H, W, p, px);       // uniform across the warp
-                const int d = lane >> 2, k = lane & 3;
-                int v = 0;
-                if (k < n) {
-                    const int y = px[k] / W + dY[d], x = px[k] % W + dX[d];
-                    if (y >= 0 && y < H && x >= 0 && x < W) {
-                        const uint8_t c = ldv(img + y * W + x);
-                        if (not_bg(c)) v = c;
-                    }
-                }
-                // Counter.most_common(1): highest count, first seen wins ties
-                int best = EITB_CODE_MUSCLE, best_cnt = 0, best_first = 64;
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {
-                    const int val = ci == 0 ? EITB_CODE_ADIPOSE : ci == 1 ? EITB_CODE_LUNG : EITB_CODE_BONE;
-                    const unsigned m = __ballot_sync(0xffffffffu, v == val);
-                    const int cnt = __popc(m), first = m ? __ffs(m) - 1 : 64;
-                    if (cnt > best_cnt || (cnt == best_cnt && cnt > 0 && first < best_first)) { best = val; best_cnt = cnt; best_first = first; }
-                }
-                // any other non-background code (does not occur in overlay images) is left alone
-                __syncwarp();
-                if (d == 0 && k < n) __stcg(img + px[k], (uint8_t)best);
-                __syncwarp();
+                small_repaint_one(img, H, W, ((w0 + wl) << 5) + bit, lane);
             }
         }
     }
@@ -239,54 +322,127 @@ __device__ __forceinline__ unsigned eq_mask8(uint2 v, int t) {
     return ((((__vcmpeq4(v.x, tt) & 0x80808080u) * 0x00204081u) >> 28) | ((((__vcmpeq4(v.y, tt) & 0x80808080u) * 0x00204081u) >> 28) << 4));
 }
 
+// trace_simple without storing the vertices: does the border from (y0, x0) have at most five CHAIN_APPROX_SIMPLE points,
+// none of them before (y0, x0) in raster order?  Chain-code steps come from two packed constants (no local arrays).
+__device__ __forceinline__ int cdx(int s) { return (int)((0x21000122u >> (4 * s)) & 0xfu) - 1; }
+__device__ __forceinline__ int cdy(int s) { return (int)((0x22210001u >> (4 * s)) & 0xfu) - 1; }
+
+__device__ bool trace_is_small_first(const uint8_t* img, int H, int W, int y0, int x0, int t) {
+    int s = 4;
+    do { s = (s - 1) & 7; } while (!is_t(img, H, W, y0 + cdy(s), x0 + cdx(s), t) && s != 4);
+    if (s == 4) return true;                                       // isolated pixel: one point
+    const int y1 = y0 + cdy(s), x1 = x0 + cdx(s);
+    int y3 = y0, x3 = x0, prev_s = s ^ 4, n = 0;
+    for (;;) {
+        int y4, x4;
+        for (;;) {
+            s = (s + 1) & 7;
+            y4 = y3 + cdy(s); x4 = x3 + cdx(s);
+            if (is_t(img, H, W, y4, x4, t)) break;
+        }
+        if (s != prev_s) {
+            if (n == 5) return false;
+            if (y3 < y0 || (y3 == y0 && x3 < x0)) return false;
+            ++n;
+        }
+        prev_s = s;
+        if (y4 == y0 && x4 == x0 && y3 == y1 && x3 == x1) break;
+        y3 = y4; x3 = x4; s = (s + 4) & 7;
+    }
+    return true;
+}
+
+// Tracing is the expensive, divergent part (a few percent of the threads find a candidate), so the warp pools its
+// candidates: every lane pushes the first pixels it found (after the one-bit frame-flood test) into a 64-entry queue in
+// shared memory, and whenever 32 are waiting all 32 lanes trace one each.
+__device__ __forceinline__ void trace_one(const uint8_t* __restrict__ src, int H, int W, unsigned item, unsigned* __restrict__ bitmap,
+                                          int words_per_img) {
+    const unsigned hw = (unsigned)H * W;
+    const unsigned bk = item / hw;                                 // b * 3 + k
+    const int p = (int)(item - bk * hw);
+    const int k = (int)(bk % 3u), y = p / W, x = p - y * W;
+    const int t = k == 0 ? EITB_CODE_BONE : k == 1 ? EITB_CODE_MUSCLE : EITB_CODE_ADIPOSE;
+    if (trace_is_small_first(src + (size_t)(bk / 3u) * hw, H, W, y, x, t))
+        atomicOr(bitmap + (size_t)bk * words_per_img + (p >> 5), 1u << (p & 31));
+}
+
 __global__ void __launch_bounds__(256)
 contour_cand3_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ reach, int B, int H, int W,
                      unsigned* __restrict__ bitmap, int words_per_img) {
+    __shared__ unsigned queue[8][64];
+    unsigned* q = queue[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int qn = 0;                                                    // warp-uniform
     const unsigned upr = (unsigned)W >> 3;                         // W % 32 == 0 on this path
     const unsigned n = (unsigned)B * H * upr;                      // < 2^32 (checked by the launcher)
+    const unsigned hw = (unsigned)H * W;
     const int T[3] = {EITB_CODE_BONE, EITB_CODE_MUSCLE, EITB_CODE_ADIPOSE};
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned rowid = i / upr;
-        const int x0 = (int)(i - rowid * upr) << 3;
-        const int b = (int)(rowid / (unsigned)H), y = (int)(rowid - (unsigned)b * H);
-        const uint8_t* img = src + (long long)b * H * W;
-        const uint8_t* row = img + (long long)y * W;
-        const uint2 cv = *reinterpret_cast<const uint2*>(row + x0);
-        const int lb = x0 > 0 ? row[x0 - 1] : -1;
-        uint2 uv = make_uint2(0u, 0u);
-        int ulb = -1, urb = -1;
-        if (y > 0) {
-            uv = *reinterpret_cast<const uint2*>(row - W + x0);
-            ulb = x0 > 0 ? row[x0 - 1 - W] : -1;
-            urb = x0 + 8 < W ? row[x0 + 8 - W] : -1;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int t = T[k];
-            const unsigned cur = eq_mask8(cv, t);
-            if (!cur) continue;
-            const unsigned up = y > 0 ? eq_mask8(uv, t) : 0u;
-            const unsigned left = lb == t, upl = ulb == t, upright = urb == t;
-            // a component's first pixel has no set neighbour earlier in raster order ...
-            unsigned tips = cur & ~((cur << 1) | left) & ~up & ~((up << 1) | upl) & ~((up >> 1) | (upright << 7)) & 0xffu;
-            while (tips) {
-                const int j = __ffs(tips) - 1;
-                tips &= tips - 1;
-                const int x = x0 + j, p = y * W + x;
-                // ... and an external contour has the frame-connected background of its colour on its left
-                if (x > 0) {
-                    const int q = p - 1;
-                    if (!((reach[((long long)b * 3 + k) * words_per_img + (q >> 5)] >> (q & 31)) & 1u)) continue;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned n_round = (n + stride - 1) / stride * stride;   // every lane of a warp runs the same number of trips
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        unsigned tips[3] = {0u, 0u, 0u};
+        unsigned rowbase = 0;                                      // (b * 3) * hw + y * W + x0
+        unsigned bb = 0;
+        if (i < n) {
+            const unsigned rowid = i / upr;
+            const int x0 = (int)(i - rowid * upr) << 3;
+            const int b = (int)(rowid / (unsigned)H), y = (int)(rowid - (unsigned)b * H);
+            const uint8_t* row = src + ((size_t)b * H + y) * W;
+            const uint2 cv = *reinterpret_cast<const uint2*>(row + x0);
+            bb = (unsigned)b;
+            rowbase = (unsigned)(y * W + x0);
+            if (cv.x | cv.y) {
+                const int lb = x0 > 0 ? row[x0 - 1] : -1;
+                uint2 uv = make_uint2(0u, 0u);
+                int ulb = -1, urb = -1;
+                if (y > 0) {
+                    uv = *reinterpret_cast<const uint2*>(row - W + x0);
+                    ulb = x0 > 0 ? row[x0 - 1 - W] : -1;
+                    urb = x0 + 8 < W ? row[x0 + 8 - W] : -1;
                 }
-                int vx[5], vy[5];
-                const int nv = trace_simple(img, H, W, y, x, t, vx, vy);
-                if (nv > 5) continue;
-                bool first = true;                                  // p must be the raster-first vertex
-                for (int m = 0; m < nv; ++m) first = first && (vy[m] > y || (vy[m] == y && vx[m] >= x));
-                if (first) atomicOr(bitmap + ((long long)b * 3 + k) * words_per_img + (p >> 5), 1u << (p & 31));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int t = T[k];
+                    const unsigned cur = eq_mask8(cv, t);
+                    if (!cur) continue;
+                    const unsigned up = y > 0 ? eq_mask8(uv, t) : 0u;
+                    const unsigned left = lb == t, upl = ulb == t, upright = urb == t;
+                    // a component's first pixel has no set neighbour earlier in raster order ...
+                    tips[k] = cur & ~((cur << 1) | left) & ~up & ~((up << 1) | upl) & ~((up >> 1) | (upright << 7)) & 0xffu;
+                }
+            }
+        }
+        unsigned all = tips[0] | (tips[1] << 8) | (tips[2] << 16);
+        while (__any_sync(0xffffffffu, all != 0u)) {
+            unsigned item = 0xffffffffu;
+            if (all) {
+                const int bit = __ffs(all) - 1;
+                all &= all - 1;
+                const int k = bit >> 3, j = bit & 7;
+                const unsigned p = rowbase + (unsigned)j;
+                // ... and an external contour has the frame-connected background of its colour on its left
+                bool ok = true;
+                if ((p % (unsigned)W) != 0u) {
+                    const unsigned qq = p - 1;
+                    ok = (reach[((size_t)bb * 3 + k) * words_per_img + (qq >> 5)] >> (qq & 31)) & 1u;
+                }
+                if (ok) item = (bb * 3u + (unsigned)k) * hw + p;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, item != 0xffffffffu);
+            if (item != 0xffffffffu) q[qn + __popc(m & lt_mask)] = item;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                const unsigned it = q[qn + lane];
+                __syncwarp();
+                trace_one(src, H, W, it, bitmap, words_per_img);
             }
         }
     }
+    __syncwarp();
+    if (lane < qn) trace_one(src, H, W, q[lane], bitmap, words_per_img);
 }
 
 // inside-or-on-boundary test against a closed polygon with integer vertices (exact)
@@ -305,89 +461,149 @@ __device__ __forceinline__ bool in_poly(int x, int y, const int (&vx)[5], const 
     return in;
 }
 
-// one warp per image, candidates in DESCENDING raster order (cv2 returns contours last-found first)
-// nt == 1: the candidates of target t0 in bitmap [B, words]; nt == 3: bone, muscle, adipose one after the other
-// (dict order, utils.py:782-787) from bitmap [B, 3, words]
-__global__ void __launch_bounds__(32)
-contour_repaint_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ code, int H, int W, int t0, int nt,
-                       const unsigned* __restrict__ bitmap, int words_per_img) {
-    const int b = blockIdx.x, lane = threadIdx.x;
-    const uint8_t* simg = src + (long long)b * H * W;
-    uint8_t* out = code + (long long)b * H * W;
-    const int nchunks = (words_per_img + 31) / 32;
-    for (int ti = 0; ti < nt; ++ti) {
-    const int t = nt == 1 ? t0 : ti == 0 ? EITB_CODE_BONE : ti == 1 ? EITB_CODE_MUSCLE : EITB_CODE_ADIPOSE;
-    const unsigned* bm = bitmap + ((long long)b * nt + ti) * words_per_img;
-    for (int ch = nchunks - 1; ch >= 0; --ch) {
-        const int w0 = ch * 32;
-        const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
-        unsigned nz = __ballot_sync(0xffffffffu, mine != 0);
-        while (nz) {
-            const int wl = 31 - __clz(nz);
-            nz &= ~(1u << wl);
-            unsigned word = __shfl_sync(0xffffffffu, mine, wl);
-            while (word) {
-                const int bit = 31 - __clz(word);
-                word &= ~(1u << bit);
-                const int p = ((w0 + wl) << 5) + bit;
-                int vx[5], vy[5];
-                const int nv = trace_simple(simg, H, W, p / W, p % W, t, vx, vy);   // uniform across the warp
-                int x0 = vx[0], x1 = vx[0], y0 = vy[0], y1 = vy[0];
-                for (int k = 1; k < nv; ++k) { x0 = min(x0, vx[k]); x1 = max(x1, vx[k]); y0 = min(y0, vy[k]); y1 = max(y1, vy[k]); }
-                // ring votes over the bounding box grown by one pixel, raster order
-                const int rx0 = max(x0 - 1, 0), rx1 = min(x1 + 1, W - 1), ry0 = max(y0 - 1, 0), ry1 = min(y1 + 1, H - 1);
-                const int bw = rx1 - rx0 + 1;
-                const long long cells = (long long)bw * (ry1 - ry0 + 1);
-                int cnt[4] = {0, 0, 0, 0};
-                long long first[4] = {-1, -1, -1, -1};               // votes: muscle, adipose, lung, bone
-                for (long long c0 = 0; c0 < cells; c0 += 32) {
-                    const long long c = c0 + lane;
-                    int v = 0;
-                    if (c < cells) {
-                        const int y = ry0 + (int)(c / bw), x = rx0 + (int)(c % bw);
-                        if (!in_poly(x, y, vx, vy, nv)) {
-                            bool near = false;
-                            for (int dy = -1; dy <= 1; ++dy)
-                                for (int dx = -1; dx <= 1; ++dx)
-                                    if ((dy || dx) && x + dx >= x0 && x + dx <= x1 && y + dy >= y0 && y + dy <= y1)
-                                        near = near || in_poly(x + dx, y + dy, vx, vy, nv);
-                            if (near) {
-                                const int cc = ldv(out + y * W + x);
-                                if (cc != t && cc != EITB_CODE_BLACK) v = cc;
-                            }
-                        }
-                    }
+// one candidate (warp-cooperative, uniform control flow): fill the contour traced from p with the ring's majority colour
+__device__ __forceinline__ void contour_repaint_one(const uint8_t* simg, uint8_t* out, int H, int W, int t, int p, int lane) {
+    int vx[5], vy[5];
+    const int nv = trace_simple(simg, H, W, p / W, p % W, t, vx, vy);   // uniform across the warp
+    int x0 = vx[0], x1 = vx[0], y0 = vy[0], y1 = vy[0];
+    for (int k = 1; k < nv; ++k) { x0 = min(x0, vx[k]); x1 = max(x1, vx[k]); y0 = min(y0, vy[k]); y1 = max(y1, vy[k]); }
+    // ring votes over the bounding box grown by one pixel, raster order
+    const int rx0 = max(x0 - 1, 0), rx1 = min(x1 + 1, W - 1), ry0 = max(y0 - 1, 0), ry1 = min(y1 + 1, H - 1);
+    const int bw = rx1 - rx0 + 1;
+    const long long cells = (long long)bw * (ry1 - ry0 + 1);
+    int cnt[4] = {0, 0, 0, 0};
+    long long first[4] = {-1, -1, -1, -1};               // votes: muscle, adipose, lung, bone
+    for (long long c0 = 0; c0 < cells; c0 += 32) {
+        const long long c = c0 + lane;
+        int v = 0;
+        if (c < cells) {
+            const int y = ry0 + (int)(c / bw), x = rx0 + (int)(c % bw);
+            if (!in_poly(x, y, vx, vy, nv)) {
+                bool near = false;
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx)
+                        if ((dy || dx) && x + dx >= x0 && x + dx <= x1 && y + dy >= y0 && y + dy <= y1)
+                            near = near || in_poly(x + dx, y + dy, vx, vy, nv);
+                if (near) {
+                    const int cc = ldv(out + y * W + x);
+                    if (cc != t && cc != EITB_CODE_BLACK) v = cc;
+                }
+            }
+        }
 #pragma unroll
-                    for (int ci = 0; ci < 4; ++ci) {
-                        const int val = ci == 0 ? EITB_CODE_MUSCLE : ci == 1 ? EITB_CODE_ADIPOSE : ci == 2 ? EITB_CODE_LUNG : EITB_CODE_BONE;
-                        const unsigned m = __ballot_sync(0xffffffffu, v == val);
-                        if (m) {
-                            cnt[ci] += __popc(m);
-                            if (first[ci] < 0) first[ci] = c0 + __ffs(m) - 1;
-                        }
-                    }
-                }
-                int fill = t, best_cnt = 0;
-                long long best_first = 0;
-#pragma unroll
-                for (int ci = 0; ci < 4; ++ci) {
-                    const int val = ci == 0 ? EITB_CODE_MUSCLE : ci == 1 ? EITB_CODE_ADIPOSE : ci == 2 ? EITB_CODE_LUNG : EITB_CODE_BONE;
-                    if (cnt[ci] > best_cnt || (cnt[ci] == best_cnt && cnt[ci] > 0 && first[ci] < best_first)) {
-                        fill = val; best_cnt = cnt[ci]; best_first = first[ci];
-                    }
-                }
-                __syncwarp();
-                const int fw = x1 - x0 + 1;
-                const long long fcells = (long long)fw * (y1 - y0 + 1);
-                for (long long c = lane; c < fcells; c += 32) {
-                    const int y = y0 + (int)(c / fw), x = x0 + (int)(c % fw);
-                    if (x >= 0 && x < W && y >= 0 && y < H && in_poly(x, y, vx, vy, nv)) __stcg(out + y * W + x, (uint8_t)fill);
-                }
-                __syncwarp();
+        for (int ci = 0; ci < 4; ++ci) {
+            const int val = ci == 0 ? EITB_CODE_MUSCLE : ci == 1 ? EITB_CODE_ADIPOSE : ci == 2 ? EITB_CODE_LUNG : EITB_CODE_BONE;
+            const unsigned m = __ballot_sync(0xffffffffu, v == val);
+            if (m) {
+                cnt[ci] += __popc(m);
+                if (first[ci] < 0) first[ci] = c0 + __ffs(m) - 1;
             }
         }
     }
+    int fill = t, best_cnt = 0;
+    long long best_first = 0;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+        const int val = ci == 0 ? EITB_CODE_MUSCLE : ci == 1 ? EITB_CODE_ADIPOSE : ci == 2 ? EITB_CODE_LUNG : EITB_CODE_BONE;
+        if (cnt[ci] > best_cnt || (cnt[ci] == best_cnt && cnt[ci] > 0 && first[ci] < best_first)) {
+            fill = val; best_cnt = cnt[ci]; best_first = first[ci];
+        }
+    }
     __syncwarp();
+    const int fw = x1 - x0 + 1;
+    const long long fcells = (long long)fw * (y1 - y0 + 1);
+    for (long long c = lane; c < fcells; c += 32) {
+        const int y = y0 + (int)(c / fw), x = x0 + (int)(c % fw);
+        if (x >= 0 && x < W && y >= 0 && y < H && in_poly(x, y, vx, vy, nv)) __stcg(out + y * W + x, (uint8_t)fill);
+    }
+    __syncwarp();
+}
+
+// the box a contour candidate touches: the bounding box of its (at most five) vertices grown by one
+__device__ __forceinline__ void contour_box(const uint8_t* simg, int H, int W, int t, int p, int& x0, int& y0, int& x1, int& y1) {
+    int vx[5], vy[5];
+    const int nv = trace_simple(simg, H, W, p / W, p % W, t, vx, vy);
+    x0 = vx[0]; x1 = vx[0]; y0 = vy[0]; y1 = vy[0];
+    for (int k = 1; k < nv && k < 5; ++k) { x0 = min(x0, vx[k]); x1 = max(x1, vx[k]); y0 = min(y0, vy[k]); y1 = max(y1, vy[k]); }
+    x0 = max(x0 - 1, 0); y0 = max(y0 - 1, 0); x1 = min(x1 + 1, W - 1); y1 = min(y1 + 1, H - 1);
+}
+
+// one CTA per image, candidates in DESCENDING raster order (cv2 returns contours last-found first)
+// nt == 1: the candidates of target t0 in bitmap [B, words]; nt == 3: bone, muscle, adipose one after the other
+// (dict order, utils.py:782-787) from bitmap [B, 3, words].  Isolated candidates first, in parallel (see small_repaint).
+__global__ void __launch_bounds__(kRepaintWarps * 32)
+contour_repaint_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ code, int H, int W, int t0, int nt,
+                       unsigned* __restrict__ bitmap, int words_per_img) {
+    __shared__ int cells[kMaxCells];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t* simg = src + (long long)b * H * W;
+    uint8_t* out = code + (long long)b * H * W;
+    const int nchunks = (words_per_img + 31) / 32;
+    const int cs = cell_shift_for(H, W), cw = (W >> cs) + 1;
+    for (int i = threadIdx.x; i < kMaxCells; i += kRepaintWarps * 32) cells[i] = 0;
+    __syncthreads();
+    // A. every candidate of every target registers its box (one lane per bitmap word)
+    for (int w = threadIdx.x; w < nt * words_per_img; w += kRepaintWarps * 32) {
+        unsigned word = bitmap[(long long)b * nt * words_per_img + w];
+        if (!word) continue;
+        const int ti = w / words_per_img, wi = w - ti * words_per_img;
+        const int t = nt == 1 ? t0 : ti == 0 ? EITB_CODE_BONE : ti == 1 ? EITB_CODE_MUSCLE : EITB_CODE_ADIPOSE;
+        while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            int x0, y0, x1, y1;
+            contour_box(simg, H, W, t, (wi << 5) + bit, x0, y0, x1, y1);
+            cells_box(cells, cw, cs, x0, y0, x1, y1, 1, 0, 1);
+        }
+    }
+    __syncthreads();
+    // B. isolated candidates, all warps
+    for (int idx = warp; idx < nt * nchunks; idx += kRepaintWarps) {
+        const int ti = idx / nchunks, w0 = (idx - ti * nchunks) * 32;
+        const int t = nt == 1 ? t0 : ti == 0 ? EITB_CODE_BONE : ti == 1 ? EITB_CODE_MUSCLE : EITB_CODE_ADIPOSE;
+        unsigned* bm = bitmap + ((long long)b * nt + ti) * words_per_img;
+        const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
+        unsigned keep = mine;
+        unsigned nz = __ballot_sync(0xffffffffu, mine != 0);
+        while (nz) {
+            const int wl = __ffs(nz) - 1;
+            nz &= nz - 1;
+            unsigned word = __shfl_sync(0xffffffffu, mine, wl);
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                const int p = ((w0 + wl) << 5) + bit;
+                int x0, y0, x1, y1;
+                contour_box(simg, H, W, t, p, x0, y0, x1, y1);     // uniform
+                if (!__all_sync(0xffffffffu, cells_box(cells, cw, cs, x0, y0, x1, y1, 0, lane, 32))) continue;
+                contour_repaint_one(simg, out, H, W, t, p, lane);
+                if (lane == wl) keep &= ~(1u << bit);
+            }
+        }
+        if (keep != mine) bm[w0 + lane] = keep;
+    }
+    __syncthreads();
+    // C. the rest in the reference's order, one warp
+    if (warp != 0) return;
+    for (int ti = 0; ti < nt; ++ti) {
+        const int t = nt == 1 ? t0 : ti == 0 ? EITB_CODE_BONE : ti == 1 ? EITB_CODE_MUSCLE : EITB_CODE_ADIPOSE;
+        const unsigned* bm = bitmap + ((long long)b * nt + ti) * words_per_img;
+        for (int ch = nchunks - 1; ch >= 0; --ch) {
+            const int w0 = ch * 32;
+            const unsigned mine = w0 + lane < words_per_img ? bm[w0 + lane] : 0u;
+            unsigned nz = __ballot_sync(0xffffffffu, mine != 0);
+            while (nz) {
+                const int wl = 31 - __clz(nz);
+                nz &= ~(1u << wl);
+                unsigned word = __shfl_sync(0xffffffffu, mine, wl);
+                while (word) {
+                    const int bit = 31 - __clz(word);
+                    word &= ~(1u << bit);
+                    contour_repaint_one(simg, out, H, W, t, ((w0 + wl) << 5) + bit, lane);
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -430,7 +646,7 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
         small_first_kernel<<<dim3(eitb_div_up(W, 256), H, B), 256, 0, s>>>(code, anybody, B, H, W, bitmap, words);
         EITB_CHECK_LAUNCH();
         eitb_prof_begin("small_repaint_kernel", s);
-        small_repaint_kernel<<<B, 32, 0, s>>>(code, anybody, H, W, bitmap, words);
+        small_repaint_kernel<<<B, kRepaintWarps * 32, 0, s>>>(code, anybody, H, W, bitmap, words);
         EITB_CHECK_LAUNCH();
     }
     if (cudaMemcpyAsync(snap, code, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return EITB_ERR_LAUNCH;
@@ -447,7 +663,7 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
         contour_cand3_kernel<<<eitb_grid((long long)n / 8, 256, 8), 256, 0, s>>>(snap, reach, B, H, W, bitmap3, words);
         EITB_CHECK_LAUNCH();
         eitb_prof_begin("contour_repaint_kernel", s);
-        contour_repaint_kernel<<<B, 32, 0, s>>>(snap, code, H, W, 0, 3, bitmap3, words);
+        contour_repaint_kernel<<<B, kRepaintWarps * 32, 0, s>>>(snap, code, H, W, 0, 3, bitmap3, words);
         EITB_CHECK_LAUNCH();
         return EITB_OK;
     }
@@ -460,7 +676,7 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
         contour_cand_kernel<<<grid, 256, 0, s>>>(snap, lab, B, H, W, t, bitmap, words);
         EITB_CHECK_LAUNCH();
         eitb_prof_begin("contour_repaint_kernel", s);
-        contour_repaint_kernel<<<B, 32, 0, s>>>(snap, code, H, W, t, 1, bitmap, words);
+        contour_repaint_kernel<<<B, kRepaintWarps * 32, 0, s>>>(snap, code, H, W, t, 1, bitmap, words);
         EITB_CHECK_LAUNCH();
     }
     return EITB_OK;

@@ -264,7 +264,7 @@ class NIIToMask(DICOMSequencesToMask):
             t1 = time.time()
             from ... import ops
             body = ops.body_mask(px, 1, 0, False)
-            _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.pipeline.dtype, rot180=False)
+            x = self.pipeline.window_input(px, body, rot180=False)
             code, body, n = self.pipeline._segment_nchw(x, body)
             answer = self._finish(code[0].cpu().numpy(), body[0].cpu().numpy(), spacing, int(n[0]), round(time.time() - t1, 3), mesh)
         except Exception as e:

@@ -251,6 +251,65 @@ def codes_to_bgr(code: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------ K13
+class LabelPolygons:
+    """Device-resident result of ``label_polygons``: per image the reference's polygon list."""
+
+    def __init__(self, n, cls, off, xy, status, max_polys, max_points):
+        self.n, self.cls, self.off, self.xy, self.status = n, cls, off, xy, status
+        self.max_polys, self.max_points = max_polys, max_points
+
+    def to_host(self):
+        """[(status, [(class id, (n, 2) int32 array of x, y), ...])] per image (one device->host copy each)."""
+        n, cls, off, xy, st = (t.cpu().numpy() for t in (self.n, self.cls, self.off, self.xy, self.status))
+        out = []
+        for b in range(len(n)):
+            polys = [(int(cls[b, i]), xy[b, off[b, i]:off[b, i + 1]].copy()) for i in range(int(n[b]))]
+            out.append((int(st[b]), polys))
+        return out
+
+
+def label_polygons(code: torch.Tensor, body: torch.Tensor | None, max_polys: int = 1024, max_points: int = 0) -> LabelPolygons:
+    """create_list_crd_from_color_output + get_only_body_mask_contours (utils.py:1191-1279, 1157-1188) on code images."""
+    _chk(code, torch.uint8, "code")
+    B, H, W = code.shape
+    if body is not None:
+        _chk(body, torch.uint8, "body")
+    max_points = max_points or H * W // 4
+    dev = code.device
+    n = torch.zeros(B, dtype=torch.int32, device=dev)
+    cls = torch.zeros((B, max_polys), dtype=torch.int32, device=dev)
+    off = torch.zeros((B, max_polys + 1), dtype=torch.int32, device=dev)
+    xy = torch.empty((B, max_points, 2), dtype=torch.int32, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    lib = cabi.load()
+    nbytes = lib.eitb_label_polygons_workspace_bytes(B, H, W, max_polys)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        cabi.call("eitb_label_polygons", code.data_ptr(), _ptr(body), B, H, W, max_polys, max_points, n.data_ptr(), cls.data_ptr(),
+                  off.data_ptr(), xy.data_ptr(), status.data_ptr(), ws.data_ptr(), nbytes, _stream(code))
+    return LabelPolygons(n, cls, off, xy, status, max_polys, max_points)
+
+
+def polygons_for_mesh(lp: LabelPolygons):
+    """The polygon list as K8 reads it (outer contour removed, short polygons dropped, rings closed, ascending area):
+    ``(poly_xy [B, max_points + max_polys, 2] f64, poly_off [B, max_polys + 1], poly_cls [B, max_polys], P [B])``."""
+    B = lp.n.shape[0]
+    dev = lp.n.device
+    out_xy = torch.empty((B, lp.max_points + lp.max_polys, 2), dtype=torch.float64, device=dev)
+    out_off = torch.zeros((B, lp.max_polys + 1), dtype=torch.int32, device=dev)
+    out_cls = torch.zeros((B, lp.max_polys), dtype=torch.int32, device=dev)
+    out_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    lib = cabi.load()
+    nbytes = lib.eitb_polygons_for_mesh_workspace_bytes(B, lp.max_polys)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        cabi.call("eitb_polygons_for_mesh", lp.n.data_ptr(), lp.cls.data_ptr(), lp.off.data_ptr(), lp.xy.data_ptr(), B, lp.max_polys,
+                  lp.max_points, out_xy.data_ptr(), out_off.data_ptr(), out_cls.data_ptr(), out_n.data_ptr(), ws.data_ptr(), nbytes,
+                  _stream(lp.n))
+    return out_xy, out_off, out_cls, out_n
+
+
 # ------------------------------------------------------------------------------------ K9
 def bias_act_(x: torch.Tensor, bias: torch.Tensor | None, silu: bool = True) -> torch.Tensor:
     """In-place bias + SiLU on a channels-last [B,C,H,W] half tensor (conv epilogue of the CNN)."""

@@ -85,7 +85,21 @@ class ImagingPipeline:
     def _net(self, model, x):
         """Run a network on a replicated gray image (every input of the service is one): lets the own-kernel
         engine read a single input channel in the stem."""
-        return model(x, gray=True) if self.engine == "eitb" and self.dtype == torch.float16 else model(x)
+        return model(x, gray=True) if self.fused_input else model(x)
+
+    @property
+    def fused_input(self) -> bool:
+        """Own-kernel engine: the stem takes the u8 window image (K1's u8 output) and applies the ultralytics
+        preprocess itself, so the normalised [B,3,H,W] tensor is never written."""
+        return self.engine == "eitb" and self.dtype == torch.float16
+
+    def window_input(self, px, body, rot180: bool = True):
+        """K1 for the axial networks: the u8 window image on the fused path, the normalised NCHW tensor otherwise."""
+        if self.fused_input:
+            u8, _ = ops.hu_window(px, body_mask=body, want_u8=True, nchw_dtype=None, rot180=rot180)
+            return u8
+        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype, rot180=rot180, channels_last=True)
+        return x
 
     def _bind_engine(self):
         if self.engine == "eitb" and self.dtype == torch.float16:
@@ -157,19 +171,19 @@ class ImagingPipeline:
         """[B,S,S] int16 stored pixels -> (labels [B,S,S] u8 codes, body [B,S,S] u8, n_det [B])."""
         B, H, W = px.shape
         body = ops.body_mask(px, slope, intercept, True) if use_body else None
-        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype, rot180=rot180, channels_last=True)
-        return self._segment_nchw(x, body)
+        return self._segment_nchw(self.window_input(px, body, rot180), body)
 
     @torch.no_grad()
     def segment_u8(self, gray: torch.Tensor):
         """jpg_png route (ai_tools.py:365-400): [B,S,S] u8, no windowing, no body mask."""
-        return self._segment_nchw(ops.u8_to_nchw(gray, self.dtype), None)
+        return self._segment_nchw(gray.contiguous() if self.fused_input else ops.u8_to_nchw(gray, self.dtype), None)
 
     def _segment_nchw(self, x: torch.Tensor, body):
+        """``x``: the normalised [B,3,S,S] network input, or (fused path) the u8 image [B,S,S] it is made from."""
         S = x.shape[-1]
         # get_axial_slice_size / model choice, ai_tools.py:138-146: 256 -> the 256 model, else the 512 one
         model = self.axial_model_256 if S == 256 else self.axial_model_512
-        head, protos = self._net(model, x.contiguous(memory_format=torch.channels_last))
+        head, protos = self._net(model, x if x.dtype == torch.uint8 else x.contiguous(memory_format=torch.channels_last))
         dets, _, n = ops.nms(head.contiguous(), 4, CONF, IOU, MAX_DET, want_idx=False)
         code, _, _ = ops.mask_decode(dets, n, protos, self.mask_variant)
         ops.label_cleanup(code, body)
@@ -334,7 +348,7 @@ class SeriesBatchRunner:
                     body[lo:hi] = ops.body_mask(px_chunk[lo:hi], self.rescale[s0][0], self.rescale[s0][1], True)
                     s0 += 1
         with t("K1_hu_window_nchw"):
-            _, x = ops.hu_window(px_chunk, body_mask=body, want_u8=False, nchw_dtype=pipe.dtype, channels_last=True)
+            x = pipe.window_input(px_chunk, body)
         with t("CNN_axial"):
             head, protos = pipe._net(pipe.axial_model_256 if self.size == 256 else pipe.axial_model_512, x)
             head = head.contiguous()

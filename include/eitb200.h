@@ -259,7 +259,10 @@ int eitb_conv2d_debug(int flags);
 
 /* Stem Conv(3 -> 32, k3, s2, pad 1): x [N,H,W,3] fp16, w27 [27][32] float32 ((r*3+s)*3+ci major).
  * gray 1: the caller guarantees three equal input channels (a gray slice replicated by K1 / the letterbox,
- * ai_tools.py:120,135): channel 0 is read and the weights are summed over the input channel. */
+ * ai_tools.py:120,135): channel 0 is read and the weights are summed over the input channel.
+ * gray 2: x is the u8 image itself, [N,H,W] (K1's out_u8): the kernel applies the ultralytics preprocess
+ * (u8 -> fp16 / 255, three equal channels) while it stages its input tile, so the normalised NCHW tensor is
+ * never written to HBM. */
 int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, const float* w27, const float* bias, int Cout, int act,
                              int gray, void* y, int y_ctot, int y_coff, eitb_stream_t stream);
 /* Depthwise Conv(C -> C, k3, s1, pad 1, groups C): w9 [9][C] fp16, C % 8 == 0. */
@@ -289,6 +292,37 @@ int eitb_tri_label(const double* nodes_xy, int64_t n_nodes, const int64_t* tri, 
 int eitb_tri_label_raster(const double* nodes_xy, int64_t n_nodes, const int64_t* tri, int64_t T,
                           const uint8_t* code, int H, int W, int outer_cls, int32_t* cls_out,
                           eitb_stream_t stream);
+
+/* ---- K13: polygons of the cleaned label image ---------------------------------------------------
+ * Replaces create_list_crd_from_color_output (utils.py:1191-1279) and get_only_body_mask_contours
+ * (utils.py:1157-1188): per tissue colour in the reference's dict order (classes "3","0","1","2"),
+ * cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) -> approxPolyDP(0.001 * arcLength, closed)
+ * -> closing point when the polygon has more than two points; then, when body != NULL, the body
+ * outline (class 4: every border pixel of the last external contour with >= 5 points).
+ *   code   [B,H,W] u8 code image (K6/K7 output); body [B,H,W] u8 or NULL; W % 32 == 0, W <= 1024,
+ *          both 16-byte aligned
+ *   n_polys [B]; poly_cls [B,max_polys]; poly_off [B,max_polys+1] point offsets; points_xy
+ *          [B,max_points,2] int32 (x, y); polygons in the order the reference lists them
+ *   status [B] bit 0: more than max_polys polygons, bit 1: more than max_points points, bit 2:
+ *          contour scratch (3*H*W raw points) exhausted -- the lists are truncated; bit 3: a body mask
+ *          was given but has no outline with >= 5 points (the reference appends [] then) */
+size_t eitb_label_polygons_workspace_bytes(int B, int H, int W, int max_polys);
+int eitb_label_polygons(const uint8_t* code, const uint8_t* body, int B, int H, int W, int max_polys,
+                        int max_points, int32_t* n_polys, int32_t* poly_cls, int32_t* poly_off,
+                        int32_t* points_xy, int32_t* status, void* ws, size_t ws_bytes,
+                        eitb_stream_t stream);
+
+/* K13 -> K8 without leaving the device: what create_mesh / divide_triangles_into_groups /
+ * build_polygons_with_area (mesh_tools/femm_generator.py:454-459, 49-60, 88-115) do to that list:
+ * the class-4 outline is the outer contour and leaves the list, polygons with fewer than four points
+ * are dropped, rings are closed, and the rest is sorted (stable) by ascending shoelace area.
+ *   out_xy [B,max_points+max_polys,2] f64; out_off [B,max_polys+1]; out_cls [B,max_polys]; out_n [B]
+ * -- per image exactly eitb_tri_label's poly_xy / poly_off / poly_cls / P. */
+size_t eitb_polygons_for_mesh_workspace_bytes(int B, int max_polys);
+int eitb_polygons_for_mesh(const int32_t* n_polys, const int32_t* poly_cls, const int32_t* poly_off,
+                           const int32_t* points_xy, int B, int max_polys, int max_points,
+                           double* out_xy, int32_t* out_off, int32_t* out_cls, int32_t* out_n,
+                           void* ws, size_t ws_bytes, eitb_stream_t stream);
 
 #ifdef __cplusplus
 }

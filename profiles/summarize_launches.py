@@ -5,7 +5,7 @@ with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for row in csv.DictReader(lines):
-    n = row["Kernel Name"].replace("(anonymous namespace)::", "").replace("void ", "")
+    n = row["Kernel Name"].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
     n = re.sub(r"\(.*", "", re.sub(r"<.*", "", n))
     n = n.split("::")[-1] if "eitb" in n or "GLOBAL__N" in n else n
     agg[n][0] += 1

@@ -97,6 +97,15 @@ def test_depthwise_and_stem():
     yg = conv(Act(xg), PackedConv.from_weight(ws, bs, 2, 1, True), gray=True)
     refg = F.silu(F.conv2d(xg.permute(0, 3, 1, 2).float(), ws.float(), bs, 2, 1)).permute(0, 2, 3, 1)
     assert float((yg.buf.float() - refg).abs().max()) <= 2e-3 * float(refg.abs().max()) + 2e-3
+    # the u8 image itself: u8 -> fp16 / 255 -> three equal channels fused into the stem's tile loader; odd sizes, tile edges
+    from eitsynthai_b200.convnet import stem_u8
+    for (h, w_) in ((37, 64), (512, 512), (208, 130)):
+        u8 = torch.randint(0, 256, (3, h, w_), device=dev, dtype=torch.uint8)
+        yu = stem_u8(u8, PackedConv.from_weight(ws, bs, 2, 1, True))
+        xin = (u8.float() / 255).half().float()[:, None].expand(-1, 3, -1, -1)
+        refu = F.silu(F.conv2d(xin, ws.float(), bs, 2, 1)).permute(0, 2, 3, 1)
+        assert yu.buf.shape == refu.shape
+        assert float((yu.buf.float() - refu).abs().max()) <= 2e-3 * float(refu.abs().max()) + 2e-3
 
 
 @pytest.mark.parametrize("nc,size", [(4, (512, 512)), (4, (256, 256)), (1, (416, 640))])
@@ -116,8 +125,12 @@ def test_network_matches_fp32_pytorch(nc, size):
         head16, proto16 = m16(x16)                                 # cuDNN fp16 + K9 (round-1 path)
         head, proto = net(x16, gray=True)
         head_c, proto_c = net(x16)                                 # generic 27-tap stem: same result up to fp32 summation order
+        u8 = (x[:, 0] * 255).round().to(torch.uint8).contiguous()
+        head_u, proto_u = net(u8)                                  # preprocess fused into the stem (the production path)
     assert head.shape == head32.shape and proto.shape == proto32.shape
     assert float((proto_c.float() - proto.float()).abs().max()) <= 5e-3 * float(proto32.abs().max())
+    assert float((proto_u.float() - proto.float()).abs().max()) <= 5e-3 * float(proto32.abs().max())
+    assert float((head_u.float() - head.float()).abs().max()) <= 5e-3 * float(head32.abs().max())
 
     def rel(a, b):
         return float((a.float() - b).abs().max() / b.abs().max().clamp_min(1e-6))
