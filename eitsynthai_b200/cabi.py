@@ -58,7 +58,7 @@ SIGNATURES = {
     "eitb_upsample2x_concat_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "eitb_yolo_head_decode": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "eitb_sppf_pool_concat": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-    "eitb_conv2d_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "eitb_conv2d_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "eitb_conv2d_tuning": (_i, [_i, _i, _i]),
     "eitb_conv2d_debug": (_i, [_i]),
     "eitb_stem_conv3x3s2_nhwc": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _p]),

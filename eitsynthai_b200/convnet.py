@@ -102,9 +102,14 @@ class PackedConv:
         return cls.from_weight(w, b, 1, 1, mods[0].has_act)
 
 
-def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, up=(1, 0, 0), gray: bool = False) -> Act:
+def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, up=(1, 0, 0), gray: bool = False,
+         pre: Act | None = None) -> Act:
     """y = act(conv(x) + bias) [+ res], written to ``out`` (a slice) or to a fresh buffer.  ``gray``: the stem's
-    three input channels are equal (a replicated gray image)."""
+    three input channels are equal (a replicated gray image).  ``pre``: a half-resolution map added, 2x nearest
+    upsampled, BEFORE the activation (1x1 convolutions only): y = act(conv(x) + bias + up2(pre))."""
+    if pre is not None:
+        assert res is None and L.kind == "gemm" and L.k == 1 and L.s == 1
+        res = pre
     B, H, W = x.bhw
     dev = x.buf.device
     assert x.c == L.cin, (x.c, L.cin)
@@ -120,8 +125,8 @@ def conv(x: Act, L: PackedConv, out: Act | None = None, res: Act | None = None, 
             cabi.call("eitb_conv2d_nhwc", x.buf.data_ptr(), B, H, W, x.buf.shape[3], x.off, L.cin, L.w.data_ptr(),
                       0 if L.bias is None else L.bias.data_ptr(), L.cout, L.k, L.s, int(L.act),
                       0 if res is None else res.buf.data_ptr(), 0 if res is None else res.buf.shape[3],
-                      0 if res is None else res.off, out.buf.data_ptr(), out.buf.shape[3], out.off, up[0], up[1], up[2],
-                      _stream(dev))
+                      0 if res is None else res.off, 2 if pre is not None else 1, out.buf.data_ptr(), out.buf.shape[3], out.off,
+                      up[0], up[1], up[2], _stream(dev))
         elif L.kind == "dw":
             assert res is None and up[0] == 1
             cabi.call("eitb_dwconv3x3_nhwc", x.buf.data_ptr(), B, H, W, x.buf.shape[3], x.off, L.cin, L.w.data_ptr(),
@@ -167,8 +172,11 @@ class ConvNet:
         self.p = {}
         for name in ("l0", "l1", "l3", "l5", "l7", "l17", "l20"):
             self.p[name] = P(getattr(model, name))
-        for name in ("l2", "l4", "l6", "l8", "l13", "l16", "l19", "l22"):
+        for name in ("l2", "l4", "l6", "l8", "l19", "l22"):
             self.p[name] = self._pack_c3k2(getattr(model, name))
+        # the two blocks behind Upsample + Concat (yaml 11-13, 14-16): cv1 split at the upsampled channels
+        self.p["l13"] = self._pack_c3k2(model.l13, split=model.l10.cv2.conv.out_channels)
+        self.p["l16"] = self._pack_c3k2(model.l16, split=model.l13.cv2.conv.out_channels)
         self.p["l9"] = (P(model.l9.cv1), P(model.l9.cv2))
         self.p["l10"] = self._pack_c2psa(model.l10)
         h = model.head
@@ -200,9 +208,18 @@ class ConvNet:
         return ("c3k", PackedConv.merged([m.cv1, m.cv2]), PackedConv.from_module(m.cv3), [self._pack_bottleneck(b) for b in m.m],
                 m.cv1.conv.out_channels)
 
-    def _pack_c3k2(self, m: C3k2):
+    def _pack_c3k2(self, m: C3k2, split: int | None = None):
+        """``split``: the block reads Concat(Upsample(a), b) with ``split`` channels in ``a``: cv1 becomes the pair
+        (Wa without bias / activation, Wb with both) for  act(up2(Wa a) + Wb b + bias)."""
         hv = self._halves(m)
-        cv1 = PackedConv.merged(hv) if hv else PackedConv.from_module(m.cv1)
+        mods = hv if hv else [m.cv1]
+        if split is None:
+            cv1 = PackedConv.merged(mods)
+        else:
+            w = torch.cat([x.conv.weight for x in mods], 0)
+            b = torch.cat([x.fused_bias for x in mods], 0)
+            cv1 = (PackedConv.from_weight(w[:, :split].contiguous(), None, 1, 1, False),
+                   PackedConv.from_weight(w[:, split:].contiguous(), b, 1, 1, mods[0].has_act))
         inner = [self._pack_c3k(b) if isinstance(b, C3k) else self._pack_bottleneck(b) for b in m.m]
         return (cv1, PackedConv.from_module(m.cv2), inner, m.c)
 
@@ -232,19 +249,24 @@ class ConvNet:
             h = self._bottleneck(h, b, buf.slice(0, c_) if last else None)   # the last one overwrites cv1(x): no longer needed
         return conv(buf, cv3, out=out)
 
-    def _c3k2(self, x: Act, pk, out: Act | None = None) -> Act:
+    def _c3k2(self, x: Act, pk, out: Act | None = None, low: Act | None = None) -> Act:
+        """``low``: the block's input is Concat(Upsample(low), x) (cv1 packed with ``split``): Wa runs at the low
+        resolution and its result enters the full-resolution Wb convolution before the activation."""
         cv1, cv2, inner, c = pk
         B, H, W = x.bhw
         n = len(inner)
         buf = _new(B, H, W, (2 + n) * c, x.buf.device)
-        conv(x, cv1, out=buf.slice(0, 2 * c))
+        if low is None:
+            conv(x, cv1, out=buf.slice(0, 2 * c))
+        else:
+            conv(x, cv1[1], out=buf.slice(0, 2 * c), pre=conv(low, cv1[0]))
         h = buf.slice(c, c)
         for i, b in enumerate(inner):
             dst = buf.slice((2 + i) * c, c)
             h = self._c3k(h, b, dst) if b[0] == "c3k" else self._bottleneck(h, b, dst)
         return conv(buf, cv2, out=out)
 
-    def _c2psa(self, x: Act, pk) -> Act:
+    def _c2psa(self, x: Act, pk, out: Act | None = None) -> Act:
         cv1, cv2, blocks, c = pk
         B, H, W = x.bhw
         dev = x.buf.device
@@ -262,7 +284,7 @@ class ConvNet:
             o = Act((o + conv(vimg, pe_l).buf).contiguous())
             x1 = conv(o, proj_l, res=b)
             conv(conv(x1, f0), f1, out=b, res=x1)
-        return conv(buf, cv2)
+        return conv(buf, cv2, out=out)
 
     # ------------------------------------------------------------------ whole network
     @torch.no_grad()
@@ -282,20 +304,18 @@ class ConvNet:
         a = self._c3k2(conv(p4, p["l7"]), p["l8"])
         y0 = conv(a, p["l9"][0])
         a = conv(Act(ops.sppf_pool_concat(y0.nchw()).permute(0, 2, 3, 1)), p["l9"][1])
-        p5 = self._c2psa(a, p["l10"])
         B = x.shape[0]
-        # neck: Upsample + Concat stay one K9 pass; the two down-path concats are written in place by their producers
-        u4in = Act(ops.upsample2x_concat(p5.nchw(), p4.nchw()).permute(0, 2, 3, 1))
-        cat19 = _new(B, p4.buf.shape[1], p4.buf.shape[2], 128 + 256, dev)           # [l17(n3) | u4]
-        u4 = self._c3k2(u4in, p["l13"], out=cat19.slice(128, 256))
-        u4t = u4.buf[..., 128:].permute(0, 3, 1, 2)                                  # strided view for the upsample kernel
-        n3in = Act(ops.upsample2x_concat(u4t.contiguous(memory_format=torch.channels_last), p3.nchw()).permute(0, 2, 3, 1))
-        n3 = self._c3k2(n3in, p["l16"])
+        cat22 = _new(B, a.buf.shape[1], a.buf.shape[2], 256 + 512, dev)              # [l20(n4) | p5]: p5 is born in place
+        p5 = self._c2psa(a, p["l10"], out=cat22.slice(256, 512))
+        # neck: Upsample + Concat never exist -- a 1x1 convolution commutes with nearest upsampling, so cv1 of l13 / l16
+        # runs its upsampled half at the low resolution and adds it inside the epilogue of the other half (K11 res_mode 2);
+        # the two down-path concats are written in place by their producers
+        cat19 = _new(B, p4.buf.shape[1], p4.buf.shape[2], 128 + 256, dev)            # [l17(n3) | u4]
+        u4 = self._c3k2(p4, p["l13"], out=cat19.slice(128, 256), low=p5)
+        n3 = self._c3k2(p3, p["l16"], low=u4)
         conv(n3, p["l17"], out=cat19.slice(0, 128))
-        cat22 = _new(B, p5.buf.shape[1], p5.buf.shape[2], 256 + 512, dev)            # [l20(n4) | p5]
         n4 = self._c3k2(cat19, p["l19"])
         conv(n4, p["l20"], out=cat22.slice(0, 256))
-        cat22.buf[..., 256:] = p5.buf
         n5 = self._c3k2(cat22, p["l22"])
         return self._head((n3, n4, n5))
 

@@ -257,7 +257,7 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
                                 eitb_stream_t stream) {
     (void)ws; (void)ws_bytes;
     if (!dets || !n_det || !protos || !code || B < 0 || nm <= 0 || mh <= 0 || mw <= 0 || max_det <= 0 ||
-        max_det > kMaxDet || (variant & ~0x15))
+        max_det > kMaxDet || (variant & ~0x35))
         return EITB_ERR_BAD_ARG;
     if (H != 4 * mh || W != 4 * mw || (mw % 4) != 0) return EITB_ERR_UNSUPPORTED;
     if (B == 0) return EITB_OK;
@@ -267,7 +267,7 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
     if (inst_bits && cudaMemsetAsync(inst_bits, 0, (size_t)B * max_det * H * (W / 8), s) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     // fp16 prototypes with 32 channels (what the network emits): contraction on the tensor cores
-    if (proto_dtype == EITB_F16 && nm == 32 && !(variant & 0x10) && !(reinterpret_cast<uintptr_t>(protos) & 15))
+    if (proto_dtype == EITB_F16 && nm == 32 && (variant & 0x20) && !(variant & 0x10) && !(reinterpret_cast<uintptr_t>(protos) & 15))
         return eitb_mask_decode_tc(dets, n_det, max_det, protos, proto_channels_last, B, mh, mw, H, W, variant & 5, code,
                                    inst_area, inst_bits, s);
     variant &= 5;

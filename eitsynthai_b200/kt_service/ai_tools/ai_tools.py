@@ -161,8 +161,10 @@ class DICOMabc(abc.ABC):
         create_segmentation_results_cnt returns, utils.py:1013-1016), ``segmentation_time``, ``saved_file_name`` and
         ``simulation_time`` ('' / 0.0: the pyEIT simulation is outside this path), ``status``, ``message`` -- plus what
         the hot path produced: label codes, polygon list, per-element classes."""
-        polygons = utils.codes_to_polygons(code, pixel_spacing, body)
-        img_mesh, mesh_data = create_mesh(polygons[:2], polygons[2:], mesh=mesh) if (mesh is not None or body is not None) else (None, [])
+        lp = utils.device_polygons(code, body)                       # K13: the polygon list stays on the device for K8
+        polygons = utils.codes_to_polygons(code, pixel_spacing, body, device_result=lp)
+        img_mesh, mesh_data = (create_mesh(polygons[:2], polygons[2:], mesh=mesh, device_polygons=lp)
+                               if (mesh is not None or body is not None) else (None, []))
         ans = {"image": self._png_base64(code), "text_data": "", "segmentation_time": seg_time, "saved_file_name": "",
                "simulation_time": 0.0, "status": "success", "message": "Processing completed successfully",
                "label_codes": code, "polygons": polygons, "mesh_data": mesh_data, "detections": n_det}

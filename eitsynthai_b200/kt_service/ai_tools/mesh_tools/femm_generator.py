@@ -29,7 +29,7 @@ def find_outer_contour(polygons, distance_threshold=0.1):
 
 
 def divide_triangles_into_groups(contours, outer_contour_class, outer_contour=None, skin_width=1, *, nodes_xy=None,
-                                 triangles=None):
+                                 triangles=None, device_polygons=None):
     """femm_generator.py:12-85 with the mesh passed explicitly instead of read from Gmsh's global
     state.  Returns ``{class_id: [element index, ...]}``; pops short contours from the caller's list
     like the reference (:49-56)."""
@@ -39,20 +39,28 @@ def divide_triangles_into_groups(contours, outer_contour_class, outer_contour=No
         if k <= len(contours) - 1 and len(contours[k]) < 9:
             contours.pop(k)
             k -= 1
-    cls = label_triangles(nodes_xy, triangles, contours, outer_contour_class)
+    cls = label_triangles(nodes_xy, triangles, contours, outer_contour_class, device_polygons)
     groups = {}
     for i, c in enumerate(cls.tolist()):
         groups.setdefault(c, []).append(i)
     return groups
 
 
-def label_triangles(nodes_xy, triangles, contours, outer_contour_class=4) -> np.ndarray:
-    """process_triangle for every element (femm_generator.py:118-184): int32 class per triangle."""
-    xy, off, pc = host.prepare_polygons(contours)
+def label_triangles(nodes_xy, triangles, contours, outer_contour_class=4, device_polygons=None) -> np.ndarray:
+    """process_triangle for every element (femm_generator.py:118-184): int32 class per triangle.
+    ``device_polygons``: K13's result for this label image (``ops.LabelPolygons``): the polygon list then goes
+    K13 -> eitb_polygons_for_mesh -> K8 without leaving the device, instead of being parsed back from the strings."""
     dev = _device()
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
-    out = ops.tri_label(t(nodes_xy, np.float64), t(triangles, np.int64), t(xy, np.float64), t(off, np.int32),
-                        t(pc, np.int32), int(outer_contour_class))
+    if device_polygons is not None:
+        xy, off, pc, n = ops.polygons_for_mesh(device_polygons)
+        P = int(n[0])
+        V = int(off[0, P])
+        xy, off, pc = xy[0, :V].contiguous(), off[0, :P + 1].contiguous(), pc[0, :P].contiguous()
+    else:
+        xy, off, pc = host.prepare_polygons(contours)
+        xy, off, pc = t(xy, np.float64), t(off, np.int32), t(pc, np.int32)
+    out = ops.tri_label(t(nodes_xy, np.float64), t(triangles, np.int64), xy, off, pc, int(outer_contour_class))
     return out.cpu().numpy()
 
 
@@ -78,7 +86,7 @@ def export_mesh_for_femm(filename, nodes_xy, triangles, classes, isSaveToFile=Fa
 
 def create_mesh(pixel_spacing, polygons, lc=7, distance_threshold=1.3, skin_width=1, is_show_inner_contours=False,
                 show_meshing_result_method="opencv", number_of_showed_class=-1, is_saving_to_file=False,
-                export_filename=None, mesh=None):
+                export_filename=None, mesh=None, device_polygons=None):
     """femm_generator.py:369-491.  ``mesh=(nodes_xy [Nn,2], triangles [T,3])`` supplies the Gmsh
     output; the skin buffer polygon (add_skin, Shapely) and the OpenCV rendering are not mirrored
     (``img`` is None)."""
@@ -97,7 +105,7 @@ def create_mesh(pixel_spacing, polygons, lc=7, distance_threshold=1.3, skin_widt
             mesh = delaunay_mesh((o[:, 0].min(), o[:, 1].min(), o[:, 0].max(), o[:, 1].max()), float(lc), 0, inside)
         nodes_xy, triangles = mesh
         groups = divide_triangles_into_groups(contours, outer_class, None, skin_width, nodes_xy=nodes_xy,
-                                              triangles=triangles)
+                                              triangles=triangles, device_polygons=device_polygons if outer_class == 4 else None)
         cls = np.empty(len(triangles), np.int64)
         for c, idx in groups.items():
             cls[idx] = c

@@ -243,27 +243,31 @@ def codes_to_color(code) -> np.ndarray:
     return ops.codes_to_bgr(c)[0].cpu().numpy()
 
 
-def codes_to_polygons(code, pixel_spacing, only_body_mask=None):
-    """create_list_crd_from_color_output (utils.py:1191-1279) on a code image.  Contour extraction
-    stays on OpenCV like in the reference (row 2 of SURVEY §8(f), next to move to the GPU)."""
-    import cv2
-    out = []
-    for target, name in ((3, "3"), (7, "0"), (1, "1"), (6, "2")):                 # utils.py:1224-1243
-        mask = np.where(code == target, 255, 0).astype(np.uint8)
-        contours, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
-        for cnt in contours:
-            approx = cv2.approxPolyDP(cnt, 0.001 * cv2.arcLength(cnt, True), True).reshape(-1, 2)
-            if len(approx) > 2 and not np.array_equal(approx[0], approx[-1]):
-                approx = np.vstack([approx, approx[:1]])
-            out.append(name + " " + " ".join(f"{x} {y}" for x, y in approx))
+def device_polygons(code, only_body_mask=None):
+    """K13 on one code image (numpy or device tensor): the device-resident polygon list (``ops.LabelPolygons``).
+    Capacities grow on overflow, so pathological (pure-noise) label images are still answered on the device."""
+    c = code if torch.is_tensor(code) else _to_dev(np.ascontiguousarray(code), np.uint8)
+    c = c.reshape((1,) + tuple(c.shape[-2:])).contiguous()
+    b = None
     if only_body_mask is not None:
-        res = []
-        if np.any(only_body_mask):
-            contours, _ = cv2.findContours(np.asarray(only_body_mask, np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
-            for cnt in contours:
-                if len(cnt) >= 5:
-                    res = "4 " + " ".join(f"{int(x)} {int(y)}" for x, y in cnt.reshape(-1, 2))
-        out.append(res)
+        b = only_body_mask if torch.is_tensor(only_body_mask) else _to_dev(np.ascontiguousarray(only_body_mask), np.uint8)
+        b = b.reshape(c.shape).contiguous()
+    H, W = c.shape[-2:]
+    for max_polys, max_points in ((1024, H * W // 4), (H * W // 2, 3 * H * W)):
+        lp = ops.label_polygons(c, b, max_polys=max_polys, max_points=max_points)
+        if not int(lp.status[0]) & 7:
+            return lp
+    raise RuntimeError("label image too fragmented for the polygon scratch buffers")
+
+
+def codes_to_polygons(code, pixel_spacing, only_body_mask=None, device_result=None):
+    """create_list_crd_from_color_output (utils.py:1191-1279) on a code image, through K13 (contour following,
+    arcLength, approxPolyDP and the body outline run on the device; the host only formats the strings)."""
+    lp = device_result if device_result is not None else device_polygons(code, only_body_mask)
+    (status, polys), = lp.to_host()
+    out = [f"{cls} " + " ".join(f"{x} {y}" for x, y in pts) for cls, pts in polys]
+    if only_body_mask is not None and status & 8:
+        out.append([])                                            # utils.py:1165: no outline -> the empty list is appended
     return [str(pixel_spacing[0]), str(pixel_spacing[1])] + out
 
 

@@ -177,8 +177,10 @@ int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, in
  *   variant   bit 0 -- 0: logits, interpolate, > 0 (8.3.x)   1: sigmoid, interpolate, > 0.5 (8.0-8.2)
  *             bit 2 -- the CPU crop of late-2025 ultralytics: images with fewer than 50 detections
  *             crop with boxes.round().int() used as Python slice bounds instead of the float comparison
- *             bit 4 -- keep the contraction on the CUDA cores (fp16 prototypes with nm == 32 otherwise
- *             go through tcgen05.mma with the accumulator in tensor memory; same semantics)
+ *             bit 5 (0x20) -- fp16 prototypes with nm == 32: contraction as tcgen05.mma with the accumulator in
+ *             tensor memory (same semantics).  Not the default: the contraction is K = 32 per pixel and the kernel
+ *             is bound by the crop / upsample / threshold epilogue, where the CUDA-core kernel is 1.3-1.6x faster
+ *             (bench.py kernels_isolated).  bit 4 (0x10) forces the CUDA-core kernel.
  *   code      [B,H,W] u8 out: overlay codes
  *   inst_area [B,max_det] int32 out or NULL: mask pixel count (the empty-mask filter)
  *   inst_bits [B,max_det,H,W/8] u8 out or NULL: per-instance bit masks (LSB = lowest x)
@@ -243,13 +245,17 @@ int eitb_sppf_pool_concat(const void* x, int B, int h, int w, int C, void* out, 
  *   y = act(conv(x, w) + bias) + res          (res added after the activation: Bottleneck shortcut)
  *   x [N,H,W,x_ctot], channels [x_coff, x_coff+Cin), Cin % 16 == 0
  *   w_packed [ksize*ksize][ceil16(Cout)][Cin] fp16 (tap-major, K contiguous; padded output rows zero)
- *   bias [Cout] float32 or NULL; act 1 = SiLU, 0 = none; res NULL or [N,Ho,Wo,res_ctot] slice
+ *   bias [Cout] float32 or NULL; act 1 = SiLU, 0 = none; res NULL or [N,Ho,Wo,res_ctot] slice (res_mode 1)
+ *   res_mode 2 (ksize 1, stride 1, even H and W): y = act(conv(x, w) + bias + up2(res)), res [N,Ho/2,Wo/2,res_ctot]
+ *   read with nearest-neighbour x2 upsampling.  A 1x1 convolution commutes with Upsample, so
+ *   Conv1x1(Concat(Upsample(a), b)) = act(up2(Wa a) + Wb b + bias): the neck's Upsample + Concat tensors
+ *   (yaml layers 11-12, 14-15) are never built
  *   ksize 1 or 3 (padding ksize/2), stride 1 or 2;  Ho = (H + 2*pad - ksize)/stride + 1
  *   y_up 1: y [N,Ho,Wo,y_ctot].  y_up 2: y [N,2Ho,2Wo,y_ctot] and the result lands on pixels
  *   (2*oy + y_dy, 2*ox + y_dx) -- one of the four phases of ConvTranspose2d(k=2, s=2). */
 int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_coff, int Cin,
                      const void* w_packed, const float* bias, int Cout, int ksize, int stride, int act,
-                     const void* res, int res_ctot, int res_coff,
+                     const void* res, int res_ctot, int res_coff, int res_mode,
                      void* y, int y_ctot, int y_coff, int y_up, int y_dy, int y_dx, eitb_stream_t stream);
 /* tile-shape experiments (host, process-wide): largest MMA N, deepest shared-memory ring, grid cap; <= 0 keeps a value */
 int eitb_conv2d_tuning(int ntile_max, int stage_cap, int grid_cap);

@@ -109,3 +109,67 @@ int oracle_tri_label(const double* nodes_xy, const int64_t* tri, int64_t T, cons
     free(buf0); free(buf1);
     return 0;
 }
+
+
+/* Decision margins (sensitivity report): for every triangle the smallest distance of any quantity
+ * process_triangle compared on its way to the label from the value at which the comparison flips, all made
+ * dimensionless with the triangle's area / size:
+ *   - centroid to the nearest edge of every polygon tested with contains(), divided by sqrt(triangle area);
+ *   - |inter / area - 0.5| of every intersection ratio tested against 0.5;
+ *   - inter / area when it is positive (how far the "inter > max_intersection" winner is from an empty intersection),
+ *     and |inter - max_intersection| / area against the running maximum.
+ * A triangle whose margin is >= 1e-6 is decided identically by any fp64 implementation of the same predicates
+ * (GEOS included): the restatement's own rounding is ~1e-12.  margin_out[t] = that minimum (1e30: nothing was compared). */
+static double seg_dist(pt q, double ux, double uy, double vx, double vy) {
+    const double dx = vx - ux, dy = vy - uy, L = dx * dx + dy * dy;
+    double t = L > 0.0 ? ((q.x - ux) * dx + (q.y - uy) * dy) / L : 0.0;
+    if (t < 0.0) t = 0.0;
+    if (t > 1.0) t = 1.0;
+    const double ex = ux + t * dx - q.x, ey = uy + t * dy - q.y;
+    return sqrt(ex * ex + ey * ey);
+}
+
+int oracle_tri_margins(const double* nodes_xy, const int64_t* tri, int64_t T, const double* poly_xy,
+                       const int32_t* poly_off, const int32_t* poly_cls, int P, int outer_cls, double* margin_out) {
+    int vmax = 0;
+    for (int p = 0; p < P; ++p) if (poly_off[p + 1] - poly_off[p] > vmax) vmax = poly_off[p + 1] - poly_off[p];
+    pt* buf0 = (pt*)malloc(sizeof(pt) * (size_t)(2 * vmax + 16));
+    pt* buf1 = (pt*)malloc(sizeof(pt) * (size_t)(2 * vmax + 16));
+    if (!buf0 || !buf1) { free(buf0); free(buf1); return -1; }
+    for (int64_t t = 0; t < T; ++t) {
+        pt a = {nodes_xy[2 * tri[3 * t]], nodes_xy[2 * tri[3 * t] + 1]};
+        pt b = {nodes_xy[2 * tri[3 * t + 1]], nodes_xy[2 * tri[3 * t + 1] + 1]};
+        pt c = {nodes_xy[2 * tri[3 * t + 2]], nodes_xy[2 * tri[3 * t + 2] + 1]};
+        double a2 = (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
+        if (a2 < 0.0) { pt tmp = b; b = c; c = tmp; a2 = -a2; }
+        const double tri_area = 0.5 * a2, size = sqrt(tri_area > 0.0 ? tri_area : 1.0);
+        const pt ctr = {(a.x + b.x + c.x) / 3.0, (a.y + b.y + c.y) / 3.0};
+        double margin = 1e30, max_inter = 0.0;
+        for (int p = 0; p < P; ++p) {
+            if (poly_cls[p] == outer_cls) continue;
+            const double* ring = poly_xy + 2 * (size_t)poly_off[p];
+            const int n = poly_off[p + 1] - poly_off[p];
+            double d = 1e30;
+            for (int i = 0; i + 1 < n; ++i) {
+                const double e = seg_dist(ctr, ring[2 * i], ring[2 * i + 1], ring[2 * i + 2], ring[2 * i + 3]);
+                if (e < d) d = e;
+            }
+            if (d / size < margin) margin = d / size;
+            if (contains(ring, n, ctr)) break;
+            if (!(tri_area > 0.0)) continue;
+            double inter = intersection_area(ring, n, a, b, c, buf0, buf1);
+            if (!(inter > 1e-9 * tri_area)) inter = 0.0;
+            const double r = inter / tri_area;
+            if (fabs(r - 0.5) < margin) margin = fabs(r - 0.5);
+            if (r > 0.5) break;
+            if (inter > 0.0) {
+                if (r < margin) margin = r;
+                if (max_inter > 0.0 && fabs(inter - max_inter) / tri_area < margin) margin = fabs(inter - max_inter) / tri_area;
+            }
+            if (inter > max_inter) max_inter = inter;
+        }
+        margin_out[t] = margin;
+    }
+    free(buf0); free(buf1);
+    return 0;
+}

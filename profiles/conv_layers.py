@@ -48,8 +48,12 @@ def main():
     ap.add_argument("--batch", type=int, default=160)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--debug", type=int, default=0, help="eitb_conv2d_debug flags (include/eitb200.h)")
+    ap.add_argument("--noact", action="store_true", help="time every layer without SiLU (epilogue cost experiment)")
+    ap.add_argument("--own-only", action="store_true", help="skip the cuDNN timings")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    cabi.load().eitb_conv2d_debug(args.debug)
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
     out = []
@@ -57,6 +61,8 @@ def main():
         if args.only and args.only not in name:
             continue
         B = 4 if args.quick else args.batch
+        if args.noact:
+            act = 0
         x = torch.randn((B, H, H, cin), device=dev).half()
         w = (torch.randn((cout, cin // groups, k, k), device=dev) * (1.0 / (cin // groups * k * k) ** 0.5)).half()
         bias = torch.randn((cout,), device=dev)
@@ -97,8 +103,8 @@ def main():
                 if cout % 8:
                     return yy
                 return ops.conv_epilogue(yy, bias, bool(act), rc, True, None, 0) if has_res else ops.bias_act_(yy, bias, bool(act))
-            t_ref = timed(cudnn_path)
-            t_conv = timed(lambda: F.conv2d(xc, wc, None, s, k // 2, 1, groups))
+            t_ref = t_own if args.own_only else timed(cudnn_path)
+            t_conv = t_own if args.own_only else timed(lambda: F.conv2d(xc, wc, None, s, k // 2, 1, groups))
             flops = 2.0 * B * Ho * Ho * cout * (cin // groups) * k * k
             byts = (x.numel() + y.buf.numel() + (res.numel() if has_res else 0)) * 2
             rec.update({"ms_own": t_own, "ms_cudnn_plus_k9": t_ref, "ms_cudnn_conv_only": t_conv, "tflops_own": flops / t_own / 1e9,

@@ -46,6 +46,31 @@ def test_conv2d_matches_fp32(cin, cout, k, s, H, W, B, act, has_res):
     assert float((got - ref).abs().max()) <= tol
 
 
+@pytest.mark.parametrize("cin,cout,H,W,B,act", [(256, 256, 32, 32, 3, True), (256, 128, 64, 64, 2, True), (64, 32, 26, 40, 2, True),
+                                               (512, 256, 8, 8, 5, False), (128, 64, 4, 6, 3, True)])
+def test_conv1x1_with_upsampled_addend(cin, cout, H, W, B, act):
+    """res_mode 2: y = act(conv1x1(x) + bias + up2(pre)) == Conv1x1(Concat(Upsample(a), x)) with pre = Wa a."""
+    from eitsynthai_b200.convnet import Act, PackedConv, conv
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + H)
+    ca = 2 * cin                                                   # channels of the low-resolution input
+    a = torch.randn((B, H // 2, W // 2, ca), generator=g).half().to(dev)
+    x = torch.randn((B, H, W, cin), generator=g).half().to(dev)
+    w = (torch.randn((cout, ca + cin, 1, 1), generator=g) / (ca + cin) ** 0.5).half().to(dev)
+    bias = torch.randn((cout,), generator=g).to(dev)
+    yb = torch.full((B, H, W, cout + 16), 3.0, device=dev).half()
+    t = conv(Act(a), PackedConv.from_weight(w[:, :ca].contiguous(), None, 1, 1, False))
+    conv(Act(x), PackedConv.from_weight(w[:, ca:].contiguous(), bias, 1, 1, act), out=Act(yb, 8, cout), pre=t)
+    cat = torch.cat([F.interpolate(a.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest"), x.permute(0, 3, 1, 2).float()], 1)
+    ref = F.conv2d(cat, w.float(), bias)
+    if act:
+        ref = F.silu(ref)
+    got = yb[..., 8:8 + cout].permute(0, 3, 1, 2).float()
+    # the low-resolution partial sum is rounded to fp16 once more than in the unsplit convolution
+    assert float((got - ref).abs().max()) <= 3e-3 * float(ref.abs().max()) + 3e-3
+    assert bool((yb[..., :8] == 3).all()) and bool((yb[..., 8 + cout:] == 3).all())
+
+
 def test_conv2d_reads_and_writes_channel_slices():
     from eitsynthai_b200.convnet import Act, PackedConv, conv
     dev = _dev()

@@ -265,7 +265,7 @@ def _few_box_heads(seed, n_boxes, size=512):
 
 
 @pytest.mark.parametrize("seed,n_boxes", [(0, 7), (1, 30), (2, 49), (3, 80)])
-@pytest.mark.parametrize("path", [4, 4 | 0x10])
+@pytest.mark.parametrize("path", [4 | 0x20, 4 | 0x10])
 def test_mask_decode_int_crop_variant(ops, seed, n_boxes, path):
     """variant bit 2: the rounded-integer crop ultralytics applies on the CPU for < 50 masks (and the float crop
     from 50 masks on), on both the tensor-core and the CUDA-core path."""
@@ -274,7 +274,7 @@ def test_mask_decode_int_crop_variant(ops, seed, n_boxes, path):
     _decode_case(ops, head, protos16 if not (path & 0x10) else protos, path, 512)
     if not (path & 0x10):
         dets, _, n = ops.nms(dev(head[None]), 4)
-        c_tc, _, _ = ops.mask_decode(dets, n, torch.from_numpy(protos16[None]).half().to(DEV), 4)
+        c_tc, _, _ = ops.mask_decode(dets, n, torch.from_numpy(protos16[None]).half().to(DEV), 4 | 0x20)
         c_cc, _, _ = ops.mask_decode(dets, n, torch.from_numpy(protos16[None]).half().to(DEV), 4 | 0x10)
         assert (c_tc != c_cc).float().mean() <= 1e-4
 
@@ -297,7 +297,7 @@ def test_mask_decode_batch_and_half_protos(ops):
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("case", ["teacher", "random50", "random300", "empty"])
 def test_mask_decode_tensor_core_path(ops, case, variant):
-    """fp16 prototypes go through tcgen05.mma; the result must match the CUDA-core kernel (variant bit 4)
+    """fp16 prototypes go through tcgen05.mma; (variant bit 5); the result must match the CUDA-core kernel (variant bit 4)
     and the CPU restatement within the mask tolerance, for NCHW and channels-last prototypes."""
     if case == "teacher":
         head, protos = synth.teacher_heads(seed=4)
@@ -306,13 +306,13 @@ def test_mask_decode_tensor_core_path(ops, case, variant):
         head, protos = synth.random_heads(2, {"random50": 50, "random300": 300, "empty": 0}[case], seed=31)
     ph = torch.from_numpy(protos).half()
     dets, idx, n = ops.nms(dev(head), 4)
-    tc, area_tc, bits_tc = ops.mask_decode(dets, n, ph.to(DEV), variant, want_area=True, want_bits=True)
+    tc, area_tc, bits_tc = ops.mask_decode(dets, n, ph.to(DEV), variant | 0x20, want_area=True, want_bits=True)
     cc, area_cc, bits_cc = ops.mask_decode(dets, n, ph.to(DEV), variant | 0x10, want_area=True, want_bits=True)
     total = bits_cc.numel() * 8
     diff = int((np.unpackbits(bits_tc.cpu().numpy()) != np.unpackbits(bits_cc.cpu().numpy())).sum())
     assert diff <= 1e-5 * max(total, 1), (diff, total)
     assert (tc != cc).float().mean().item() <= 1e-4
-    nhwc, _, _ = ops.mask_decode(dets, n, ph.to(DEV).contiguous(memory_format=torch.channels_last), variant)
+    nhwc, _, _ = ops.mask_decode(dets, n, ph.to(DEV).contiguous(memory_format=torch.channels_last), variant | 0x20)
     assert torch.equal(nhwc, tc)
     for b in range(head.shape[0]):
         r = Y.postprocess(torch.from_numpy(head[b]), ph[b].float(), 4, (512, 512), (512, 512),
@@ -332,7 +332,7 @@ def test_mask_decode_tensor_core_small_size_ragged_batch(ops):
     for max_det in (300, 40):
         dets, idx, n = ops.nms(dev(head), 4, max_det=max_det)
         assert n.cpu().tolist()[0] == 0 and int(n[2]) <= max_det
-        tc, a1, b1 = ops.mask_decode(dets, n, ph.to(DEV), 0, want_area=True, want_bits=True)
+        tc, a1, b1 = ops.mask_decode(dets, n, ph.to(DEV), 0x20, want_area=True, want_bits=True)
         cc, a2, b2 = ops.mask_decode(dets, n, ph.to(DEV), 0x10, want_area=True, want_bits=True)
         assert (tc != cc).float().mean().item() <= 1e-4
         assert int((np.unpackbits(b1.cpu().numpy()) != np.unpackbits(b2.cpu().numpy())).sum()) <= 1e-5 * b1.numel() * 8

@@ -97,3 +97,24 @@ def test_mirror_overlay_and_mask_helpers_on_cpu_tensors(golden):
     assert np.array_equal(O.code_to_bgr(code), golden["seg1_overlay"])
     img, m = torch.from_numpy(golden["p0_norm"]), torch.from_numpy(golden["p0_body"])
     assert np.array_equal(U._masked(img, m).numpy(), golden["p0_normbody"])
+
+
+def test_tri_label_oracle_against_exact_rational_arithmetic_on_the_most_delicate_triangles():
+    """oracle/tri_label.c (fp64, with its 1e-9 * area noise floor) against process_triangle evaluated in exact rational
+    arithmetic (no rounding, no noise-floor rule), on the triangles of two real polygon sets whose decisions are closest
+    to flipping; and the sensitivity report: almost no triangle comes within 1e-6 of a decision boundary."""
+    from eitsynthai_b200 import synth
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_polygon_sets.npz"))
+    for s, pitch in ((1, 6.0), (6, 6.0)):
+        xy, off, cls = z[f"set{s}_xy"], z[f"set{s}_off"], z[f"set{s}_cls"]
+        nodes, tri = synth.delaunay_mesh((xy[:, 0].min(), xy[:, 1].min(), xy[:, 0].max(), xy[:, 1].max()), pitch, seed=s)
+        m = TL.decision_margins(nodes, tri, xy, off, cls)
+        assert (m < 1e-6).mean() < 1e-3
+        idx = np.argsort(m)[:60]
+        assert np.array_equal(TL.label_triangles_exact(nodes, tri[idx], xy, off, cls), TL.label_triangles(nodes, tri[idx], xy, off, cls))
+    # a degenerate overlap: the triangle touches the polygon along an edge only (area exactly 0 in rational arithmetic)
+    sq = np.array([[0, 0], [10, 0], [10, 10], [0, 10], [0, 0]], np.float64)
+    nodes = np.array([[10, 2], [14, 5], [10, 8], [3, 3], [6, 3], [4, 7]], np.float64)
+    tri = np.array([[0, 1, 2], [3, 4, 5]], np.int64)
+    args = (nodes, tri, sq, np.array([0, 5], np.int32), np.array([2], np.int32))
+    assert TL.label_triangles_exact(*args).tolist() == [4, 2] == TL.label_triangles(*args).tolist()
