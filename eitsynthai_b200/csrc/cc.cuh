@@ -80,9 +80,10 @@ __device__ __forceinline__ void gunion(int* L, int a, int b) {     // a: pixel i
 template <int PRED, int CONN>
 __global__ void __launch_bounds__(kThreads)
 cc_local_kernel(const void* __restrict__ src, size_t src_img_stride_bytes, int arg, int H, int W, int strip_h,
-                int strips_per_img, int32_t* __restrict__ labels) {
+                int strips_per_img, int32_t* __restrict__ labels, const int* __restrict__ skip) {
     extern __shared__ int sl[];
     const int b = blockIdx.x / strips_per_img;
+    if (skip && skip[b]) return;                         // this image was answered without labelling (K2 fast path)
     const int sidx = blockIdx.x - b * strips_per_img;
     const int y0 = sidx * strip_h;
     const int rows = min(strip_h, H - y0);
@@ -184,7 +185,7 @@ cc_local_kernel(const void* __restrict__ src, size_t src_img_stride_bytes, int a
 
 template <int CONN>
 __global__ void __launch_bounds__(256)
-cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __restrict__ labels) {
+cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __restrict__ labels, const int* __restrict__ skip) {
     const int nb = (H - 1) / strip_h;                    // number of strip borders per image
     const long long border_items = (long long)B * nb * W;
     const long long frame_per_img = link_outside ? 2LL * W + 2LL * H : 0;
@@ -192,6 +193,7 @@ cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __r
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         if (t < border_items) {
             const int b = (int)(t / ((long long)nb * W));
+            if (skip && skip[b]) continue;
             const int r = (int)(t - (long long)b * nb * W);
             const int k = r / W, x = r - k * W;
             const int y = (k + 1) * strip_h;
@@ -208,6 +210,7 @@ cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __r
         } else {
             const long long u = t - border_items;
             const int b = (int)(u / frame_per_img);
+            if (skip && skip[b]) continue;
             const int r = (int)(u - (long long)b * frame_per_img);
             int y, x;
             if (r < W) { y = 0; x = r; }
@@ -222,7 +225,8 @@ cc_merge_kernel(int B, int H, int W, int strip_h, int link_outside, int32_t* __r
 }
 
 static __global__ void __launch_bounds__(256)
-cc_flatten_kernel(int hw, int32_t* __restrict__ labels) {       // grid (x: pixel blocks, y: image)
+cc_flatten_kernel(int hw, int32_t* __restrict__ labels, const int* __restrict__ skip) {       // grid (x: pixel blocks, y: image)
+    if (skip && skip[blockIdx.y]) return;
     int* L = labels + (long long)blockIdx.y * hw;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
         const int l = L[i];
@@ -243,7 +247,7 @@ inline int strip_rows(int H, int W) {
 // they need with gfind().
 template <int PRED, int CONN>
 int cc_label(const void* src, size_t src_img_stride_bytes, int arg, int B, int H, int W, int link_outside,
-             int32_t* labels, cudaStream_t s, int flatten = 1) {
+             int32_t* labels, cudaStream_t s, int flatten = 1, const int* skip = nullptr) {
     if (W > kStripPixels) return EITB_ERR_UNSUPPORTED;
     const int sh = strip_rows(H, W);
     const int spi = eitb_div_up(H, sh);
@@ -251,17 +255,17 @@ int cc_label(const void* src, size_t src_img_stride_bytes, int arg, int B, int H
     if (cudaFuncSetAttribute(cc_local_kernel<PRED, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     eitb_prof_begin("cc_local_kernel", s);
-    cc_local_kernel<PRED, CONN><<<B * spi, kThreads, smem, s>>>(src, src_img_stride_bytes, arg, H, W, sh, spi, labels);
+    cc_local_kernel<PRED, CONN><<<B * spi, kThreads, smem, s>>>(src, src_img_stride_bytes, arg, H, W, sh, spi, labels, skip);
     EITB_CHECK_LAUNCH();
     const long long items = (long long)B * ((H - 1) / sh) * W + (link_outside ? (long long)B * (2LL * W + 2LL * H) : 0);
     if (items > 0) {
         eitb_prof_begin("cc_merge_kernel", s);
-        cc_merge_kernel<CONN><<<eitb_grid(items, 256, 8), 256, 0, s>>>(B, H, W, sh, link_outside, labels);
+        cc_merge_kernel<CONN><<<eitb_grid(items, 256, 8), 256, 0, s>>>(B, H, W, sh, link_outside, labels, skip);
         EITB_CHECK_LAUNCH();
     }
     if (!flatten) return EITB_OK;
     eitb_prof_begin("cc_flatten_kernel", s);
-    cc_flatten_kernel<<<dim3(eitb_grid_per_image((long long)H * W, 256, B), B), 256, 0, s>>>(H * W, labels);
+    cc_flatten_kernel<<<dim3(eitb_grid_per_image((long long)H * W, 256, B), B), 256, 0, s>>>(H * W, labels, skip);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

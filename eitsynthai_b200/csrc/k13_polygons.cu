@@ -37,20 +37,31 @@ __device__ __forceinline__ int job_class(int j) { return j == 0 ? 3 : j == 1 ? 0
 __device__ __forceinline__ int step_dx(int s) { return (int)((0x21000122u >> (4 * s)) & 0xfu) - 1; }
 __device__ __forceinline__ int step_dy(int s) { return (int)((0x22210001u >> (4 * s)) & 0xfu) - 1; }
 
-// t >= 0: pixel == t (tissue colour); t < 0: pixel != 0 (body mask)
-__device__ __forceinline__ bool px_on(const uint8_t* img, int H, int W, int y, int x, int t) {
-    if (y < 0 || y >= H || x < 0 || x >= W) return false;
-    const int v = img[y * W + x];
-    return t >= 0 ? v == t : v != 0;
-}
+// Where the tracer reads "is this pixel in the set": a one-bit-per-pixel plane in shared memory (the usual case: the
+// five planes of a 512 x 512 image are 160 KB), or the byte image in global memory when the planes do not fit.
+struct BitPlane {
+    const uint32_t* plane; int H, W, wpr;
+    __device__ __forceinline__ bool operator()(int y, int x) const {
+        if (y < 0 || y >= H || x < 0 || x >= W) return false;
+        return (plane[y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+    }
+};
+struct ByteImage {                               // t >= 0: pixel == t (tissue colour); t < 0: pixel != 0 (body mask)
+    const uint8_t* img; int H, W, t;
+    __device__ __forceinline__ bool operator()(int y, int x) const {
+        if (y < 0 || y >= H || x < 0 || x >= W) return false;
+        const int v = img[y * W + x];
+        return t >= 0 ? v == t : v != 0;
+    }
+};
 
 // Outer border from the candidate first pixel (y0, x0).  emit(i, x, y) receives the points in OpenCV's order; returns
 // their number, or -1 as soon as the border reaches a pixel that precedes (y0, x0) in raster order (then (y0, x0) is
 // not the first pixel of its component and some other candidate owns this border).
-template <class Emit>
-__device__ int trace_border(const uint8_t* img, int H, int W, int y0, int x0, int t, bool simple, Emit emit) {
+template <class On, class Emit>
+__device__ int trace_border(const On& on, int y0, int x0, bool simple, Emit emit) {
     int s = 4;
-    do { s = (s - 1) & 7; } while (!px_on(img, H, W, y0 + step_dy(s), x0 + step_dx(s), t) && s != 4);
+    do { s = (s - 1) & 7; } while (!on(y0 + step_dy(s), x0 + step_dx(s)) && s != 4);
     if (s == 4) { emit(0, x0, y0); return 1; }                       // isolated pixel (the west neighbour is never set here)
     const int y1 = y0 + step_dy(s), x1 = x0 + step_dx(s);
     int y3 = y0, x3 = x0, prev_s = s ^ 4, n = 0;
@@ -59,7 +70,7 @@ __device__ int trace_border(const uint8_t* img, int H, int W, int y0, int x0, in
         for (;;) {
             s = (s + 1) & 7;
             y4 = y3 + step_dy(s); x4 = x3 + step_dx(s);
-            if (px_on(img, H, W, y4, x4, t)) break;
+            if (on(y4, x4)) break;
         }
         if (!simple || s != prev_s) { emit(n, x3, y3); ++n; }
         prev_s = s;
@@ -253,7 +264,7 @@ struct PolyWs {
 __global__ void __launch_bounds__(kThreads)
 poly_build_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ body, int H, int W, int words, PolyWs ws,
                   int max_polys, int max_points, int32_t* __restrict__ n_polys, int32_t* __restrict__ poly_cls,
-                  int32_t* __restrict__ poly_off, int32_t* __restrict__ points_xy, int32_t* __restrict__ status) {
+                  int32_t* __restrict__ poly_off, int32_t* __restrict__ points_xy, int32_t* __restrict__ status, int use_planes) {
     __shared__ int s_scan[kThreads];
     __shared__ int s_base, s_nslots, s_status, s_body_slot;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -268,21 +279,48 @@ poly_build_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ 
     int32_t* dst = ws.dst + (size_t)b * (ws.raw_cap + ws.max_slots);
     int2* stack = ws.stack + (size_t)b * (ws.raw_cap + 2 * ws.max_slots);
     if (tid == 0) { s_base = 0; s_status = 0; s_body_slot = -1; }
-    __syncthreads();
-
-    // ---- A. keep the candidates that are the first pixel of their component (their border never runs above them)
     const int njobs = bimg ? kJobs : kJobs - 1;
+    const int wpr = W >> 5, hw = H * W;
+    // the five sets as bit planes in shared memory (when they fit): border following then probes shared memory
+    extern __shared__ uint32_t planes[];
+    if (use_planes) {
+        for (int w = tid; w < words; w += kThreads) {
+            const int4 v0 = *reinterpret_cast<const int4*>(cimg + (size_t)w * 32), v1 = *reinterpret_cast<const int4*>(cimg + (size_t)w * 32 + 16);
+            const uint2 q[4] = {make_uint2((unsigned)v0.x, (unsigned)v0.y), make_uint2((unsigned)v0.z, (unsigned)v0.w),
+                                make_uint2((unsigned)v1.x, (unsigned)v1.y), make_uint2((unsigned)v1.z, (unsigned)v1.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = job_target(j);
+                planes[j * words + w] = eq_mask8(q[0], t) | (eq_mask8(q[1], t) << 8) | (eq_mask8(q[2], t) << 16) | (eq_mask8(q[3], t) << 24);
+            }
+            if (bimg) {
+                const int4 b0 = *reinterpret_cast<const int4*>(bimg + (size_t)w * 32), b1 = *reinterpret_cast<const int4*>(bimg + (size_t)w * 32 + 16);
+                planes[4 * words + w] = nz_mask8(make_uint2((unsigned)b0.x, (unsigned)b0.y)) | (nz_mask8(make_uint2((unsigned)b0.z, (unsigned)b0.w)) << 8) |
+                                        (nz_mask8(make_uint2((unsigned)b1.x, (unsigned)b1.y)) << 16) | (nz_mask8(make_uint2((unsigned)b1.z, (unsigned)b1.w)) << 24);
+            }
+        }
+    }
+    __syncthreads();
+    auto trace = [&](int j, int p, auto emit) -> int {
+        const int y = p / W, x = p - y * W;
+        if (use_planes) return trace_border(BitPlane{planes + j * words, H, W, wpr}, y, x, j < 4, emit);
+        return trace_border(ByteImage{j < 4 ? cimg : bimg, H, W, j < 4 ? job_target(j) : -1}, y, x, j < 4, emit);
+    };
+
+    // ---- A. keep the candidates that are the first pixel of their component (their border never runs above them);
+    // the point count of the survivors is parked per pixel (in the not yet used `dst` area: tissue at p, body at hw + p)
+    int32_t* cnt_px = dst;
     for (int w = tid; w < njobs * words; w += kThreads) {
         unsigned word = tips[w], keep = word;
         if (!word) continue;
         const int j = w / words, wi = w - j * words;
-        const uint8_t* img = j < 4 ? cimg : bimg;
-        const int t = j < 4 ? job_target(j) : -1;
         while (word) {
             const int bit = __ffs(word) - 1;
             word &= word - 1;
             const int p = (wi << 5) + bit;
-            if (trace_border(img, H, W, p / W, p % W, t, j < 4, NoEmit()) < 0) keep &= ~(1u << bit);
+            const int n = trace(j, p, NoEmit());
+            if (n < 0) keep &= ~(1u << bit);
+            else cnt_px[(j == 4 ? hw : 0) + p] = n;
         }
         tips[w] = keep;
     }
@@ -322,11 +360,8 @@ poly_build_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ 
     __syncthreads();
     const int nslots = s_nslots;
 
-    // ---- C. raw point counts
-    for (int s = tid; s < nslots; s += kThreads) {
-        const int j = slot_job[s], p = slot_p[s];
-        slot_cnt[s] = trace_border(j < 4 ? cimg : bimg, H, W, p / W, p % W, j < 4 ? job_target(j) : -1, j < 4, NoEmit());
-    }
+    // ---- C. raw point counts (parked in phase A)
+    for (int sl = tid; sl < nslots; sl += kThreads) slot_cnt[sl] = cnt_px[(slot_job[sl] == 4 ? hw : 0) + slot_p[sl]];
     __syncthreads();
     // ---- D. offsets (a few hundred slots: one thread)
     if (tid == 0) {
@@ -343,7 +378,7 @@ poly_build_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ 
     for (int s = tid; s < ns; s += kThreads) {
         const int j = slot_job[s], p = slot_p[s], off = slot_off[s];
         int32_t* r = raw + off;
-        const int cnt = trace_border(j < 4 ? cimg : bimg, H, W, p / W, p % W, j < 4 ? job_target(j) : -1, j < 4, StoreEmit{r});
+        const int cnt = trace(j, p, StoreEmit{r});
         if (j < 4) {
             double perimeter = 0.0;                                // cv2.arcLength(cnt, True)
             if (cnt > 1) {
@@ -546,9 +581,13 @@ extern "C" int eitb_label_polygons(const uint8_t* code, const uint8_t* body, int
     eitb_prof_begin("poly_tips_kernel", s);
     poly_tips_kernel<<<eitb_grid((long long)B * H * W / 8, 256, 8), 256, 0, s>>>(code, body, w.reach, B, H, W, w.tips, l.words);
     EITB_CHECK_LAUNCH();
+    const size_t plane_bytes = (size_t)kJobs * l.words * 4;
+    const int use_planes = plane_bytes <= 200 * 1024 && (H * W) % 32 == 0;
+    if (use_planes && cudaFuncSetAttribute(poly_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes) != cudaSuccess)
+        return EITB_ERR_LAUNCH;
     eitb_prof_begin("poly_build_kernel", s);
-    poly_build_kernel<<<B, kThreads, 0, s>>>(code, body, H, W, l.words, w, max_polys, max_points, n_polys, poly_cls, poly_off,
-                                             points_xy, status);
+    poly_build_kernel<<<B, kThreads, use_planes ? plane_bytes : 0, s>>>(code, body, H, W, l.words, w, max_polys, max_points, n_polys,
+                                                                        poly_cls, poly_off, points_xy, status, use_planes);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

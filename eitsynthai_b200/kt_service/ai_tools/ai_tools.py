@@ -149,9 +149,11 @@ class DICOMabc(abc.ABC):
         if ds is not None:
             px = torch.from_numpy(np.array(ds.pixel_array, np.int16)[None]).to(self.device)
             code, body, n = self.pipeline.segment(px, int(_tag(ds, (0x0028, 0x1053), 1)), int(_tag(ds, (0x0028, 0x1052), -1024)))
+            self._dev_last = (code[0], body[0])                      # stay on the device for K13 / K8
             body = body[0].cpu().numpy()
         else:
             code, body, n = self.pipeline.segment_u8(torch.from_numpy(np.ascontiguousarray(px_or_u8, np.uint8)[None]).to(self.device))
+            self._dev_last = (code[0], None)
         out = code[0].cpu().numpy()
         return out, body, int(n[0]), round(time.time() - t1, 3)
 
@@ -161,7 +163,15 @@ class DICOMabc(abc.ABC):
         create_segmentation_results_cnt returns, utils.py:1013-1016), ``segmentation_time``, ``saved_file_name`` and
         ``simulation_time`` ('' / 0.0: the pyEIT simulation is outside this path), ``status``, ``message`` -- plus what
         the hot path produced: label codes, polygon list, per-element classes."""
-        lp = utils.device_polygons(code, body)                       # K13: the polygon list stays on the device for K8
+        dev_code, dev_body = getattr(self, "_dev_last", None) or (None, None)
+        self._dev_last = None
+        if dev_code is None or tuple(dev_code.shape) != tuple(np.shape(code)):
+            dev_code, dev_body = code, body
+        elif body is None:
+            dev_body = None
+        elif dev_body is None:
+            dev_body = body
+        lp = utils.device_polygons(dev_code, dev_body)                # K13: the polygon list stays on the device for K8
         polygons = utils.codes_to_polygons(code, pixel_spacing, body, device_result=lp)
         img_mesh, mesh_data = (create_mesh(polygons[:2], polygons[2:], mesh=mesh, device_polygons=lp)
                                if (mesh is not None or body is not None) else (None, []))
@@ -175,10 +185,17 @@ class DICOMabc(abc.ABC):
     @staticmethod
     def _png_base64(code) -> str:
         import base64
+        bgr = utils.codes_to_color(code)                             # reference colours (utils.py:468-473)
+        try:                                                         # OpenCV's encoder: same image, a fraction of PIL's time
+            import cv2
+            ok, enc = cv2.imencode(".png", np.ascontiguousarray(bgr))    # imencode takes BGR and stores RGB, like utils.py:1037-1041
+            if ok:
+                return base64.b64encode(enc.tobytes()).decode("utf-8")
+        except ImportError:
+            pass
         from io import BytesIO
 
         from PIL import Image
-        bgr = utils.codes_to_color(code)                             # reference colours (utils.py:468-473)
         buf = BytesIO()
         Image.fromarray(np.ascontiguousarray(bgr[..., ::-1])).save(buf, format="PNG")   # cv2.COLOR_BGR2RGB, utils.py:1037
         return base64.b64encode(buf.getvalue()).decode("utf-8")
@@ -268,6 +285,7 @@ class NIIToMask(DICOMSequencesToMask):
             body = ops.body_mask(px, 1, 0, False)
             x = self.pipeline.window_input(px, body, rot180=False)
             code, body, n = self.pipeline._segment_nchw(x, body)
+            self._dev_last = (code[0], body[0])
             answer = self._finish(code[0].cpu().numpy(), body[0].cpu().numpy(), spacing, int(n[0]), round(time.time() - t1, 3), mesh)
         except Exception as e:
             logger.error(f"NIIToMask.get_coordinate_slice_from_nii failed: {e}")
