@@ -502,7 +502,8 @@ int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // bit 4 (16) turns halo mode off, bit 5 (32) the two-CTAs-per-SM configuration, bit 6 (64) resident weights,
 // bit 8 (256) tries resident weights + half-N split first on 3x3 layers, bit 9 (512) keeps weights resident whenever they
-// fit (both measured slower, kept for A/B runs), bit 10 (1024) the two-op fp32 SiLU;
+// fit (both measured slower, kept for A/B runs), bit 10 (1024) the two-op fp32 SiLU, bit 11 (2048) turns the
+// wave-quantisation choice of the N tile on (measured slower);
 // the others are ConvArgs::dbg
 extern "C" int eitb_conv2d_debug(int flags) {
     g_dbg = flags & ~112; g_halo = !(flags & 16); g_light = !(flags & 32); g_ws = !(flags & 64);
@@ -559,7 +560,34 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
         all_w = p.taps * p.kchunks * p.b_bytes;                            // every weight tile of one N tile
         return true;
     };
-    const int ntile_full = cout_pad < g_ntile_max ? cout_pad : g_ntile_max;
+    int ntile_full = cout_pad < g_ntile_max ? cout_pad : g_ntile_max;
+    const bool halo_ok = g_halo && ksize == 3 && stride == 1 && Ho >= 9;
+    if (g_dbg & 2048) {
+        // Experiment 2048 (measured slower on 9 of 30 layer shapes, e.g. l5 159 -> 196 us, and faster on none):
+        // Wave quantisation: a persistent grid of C CTAs runs ceil(tiles / C) rounds, and on the 16 x 16 / 32 x 32 maps of
+        // the deep layers that is 2-5 rounds with the last one mostly empty (320 tiles on 296 CTAs = 2 rounds for 1.08
+        // rounds of work).  Halving the N tile doubles the tile count: pick the N tile with the least rounds x (N + fixed
+        // per-tile cost in MMA columns); large maps keep the full N (their cost is proportional to tiles x (N + fixed)).
+        long long mt;
+        if (halo_ok) mt = (long long)((Wo + 7) / 8) * ((Ho + 15) / 16) * N;
+        else {
+            const int tw = Wo >= 16 ? 16 : pow2_ceil(Wo);
+            const int th = pow2_ceil(Ho) < BM / tw ? pow2_ceil(Ho) : BM / tw;
+            const int tn = BM / (tw * th);
+            mt = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
+        }
+        double best_cost = 1e300;
+        int best = ntile_full;
+        for (int nt = ntile_full; nt >= 32; nt >>= 1) {
+            if (nt != ntile_full && (cout_pad % nt || nt % 16)) break;
+            const int n_t = (cout_pad + nt - 1) / nt;
+            const int cap = g_grid_cap * ((g_light && nt <= 128) ? 2 : 1);
+            const long long rounds = (mt * n_t + cap - 1) / cap;
+            const double cost = (double)rounds * (nt + 48.0);
+            if (cost < best_cost * 0.95) { best_cost = cost; best = nt; }
+        }
+        ntile_full = best;
+    }
     if (!configure(ntile_full)) return EITB_ERR_UNSUPPORTED;
 
     // Configuration = {two CTAs per SM ("light", N <= 128), one} x {halo tile, nine shifted loads} x {weights resident
@@ -606,7 +634,6 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
         light = want_light;
         return true;
     };
-    const bool halo_ok = g_halo && ksize == 3 && stride == 1 && Ho >= 9;
     const bool light_ok = g_light && ntile_full <= 128;
     bool planned = false;
     if (halo_ok && (g_dbg & 256)) {

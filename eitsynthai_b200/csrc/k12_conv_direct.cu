@@ -5,6 +5,8 @@
 //     attention position encoding (9 taps per channel: bandwidth-bound).
 // Reference: the ultralytics modules behind model(...) at kt_service/ai_tools/ai_tools.py:121-122,153.
 #include "common.cuh"
+#include <cuda.h>        // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
+#include <mutex>
 
 namespace {
 
@@ -270,6 +272,128 @@ dwconv3x3_kernel(const __half* __restrict__ x, int x_ctot, int x_coff, const __h
     }
 }
 
+// ---- depthwise 3x3 with the input staged by TMA.
+// A CTA owns a 16 x 8 pixel x 64 channel output tile; its (18 x 10 pixel) input halo arrives as one 4-D TMA box
+// (out-of-range rows / columns zero-filled by the TMA unit = the padding), double-buffered, so the copy of tile i+1
+// runs under the arithmetic of tile i and no thread waits on a global load.  One thread = 8 channels x 4 pixels of a
+// row: 18 conflict-free 16-byte shared-memory reads, 288 FMAs, four 16-byte stores.
+constexpr int DT_W = 16, DT_H = 8, DT_C = 64, DT_HW = DT_W + 2, DT_HH = DT_H + 2;
+constexpr int DT_STAGE = DT_HH * DT_HW * DT_C * 2;               // 23,040 B
+
+__device__ __forceinline__ uint32_t dw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict__ w, const float* __restrict__ bias, int N, int H,
+                     int W, int C, int act, __half* __restrict__ y, int y_ctot, int y_coff, int tiles_x, int tiles_y, int cblocks) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    unsigned char* tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 127) & ~(uintptr_t)127);
+    __shared__ uint64_t full[2];
+    const int tid = threadIdx.x;
+    const int g = tid & 7, xb = (tid >> 3) & 3, rr = tid >> 5;     // channel group (8 ch), block of 4 pixels, row
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&full[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dw_smem_u32(&full[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int total = N * tiles_y * tiles_x * cblocks;
+    auto issue = [&](int tix, int stage) {
+        const int cb = tix % cblocks, t2 = tix / cblocks;
+        const int tx = t2 % tiles_x, ty = (t2 / tiles_x) % tiles_y, n = t2 / (tiles_x * tiles_y);
+        const uint32_t bar = dw_smem_u32(&full[stage]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)DT_STAGE) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(dw_smem_u32(tile + (size_t)stage * DT_STAGE)), "l"(&map_x), "r"(cb * DT_C), "r"(tx * DT_W - 1), "r"(ty * DT_H - 1), "r"(n), "r"(bar)
+            : "memory");
+    };
+    if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+    float wr[9][8], b8[8];
+    int wcb = -1;
+    uint32_t phase[2] = {0u, 0u};
+    int it = 0;
+    for (int tix = blockIdx.x; tix < total; tix += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const int nxt = tix + gridDim.x;
+        if (tid == 0 && nxt < total) issue(nxt, stage ^ 1);         // the other buffer was released by the barrier that ended tile it-1
+        const int cb = tix % cblocks, t2 = tix / cblocks;
+        const int tx = t2 % tiles_x, ty = (t2 / tiles_x) % tiles_y, n = t2 / (tiles_x * tiles_y);
+        if (cb != wcb) {                                           // this channel block's weights and bias (cblocks is 2..8: rarely changes)
+            wcb = cb;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int4 wv = __ldg(reinterpret_cast<const int4*>(w + k * C + cb * DT_C + g * 8));
+                const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(wh[e]); wr[k][2 * e] = f.x; wr[k][2 * e + 1] = f.y; }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) b8[e] = bias ? __ldg(bias + cb * DT_C + g * 8 + e) : 0.f;
+        }
+        {
+            const uint32_t bar = dw_smem_u32(&full[stage]);
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(phase[stage]) : "memory");
+            phase[stage] ^= 1u;
+        }
+        const unsigned char* src = tile + (size_t)stage * DT_STAGE;
+        const int oy = ty * DT_H + rr, ox0 = tx * DT_W + xb * 4;
+        float acc[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j][e] = b8[e];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const int4 v = *reinterpret_cast<const int4*>(src + ((size_t)((rr + r) * DT_HW + xb * 4 + c) * DT_C + g * 8) * 2);
+                float f[8];
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+#pragma unroll
+                for (int sft = 0; sft < 3; ++sft) {
+                    const int j = c - sft;
+                    if (j >= 0 && j < 4) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(f[e], wr[r * 3 + sft][e], acc[j][e]);
+                    }
+                }
+            }
+        if (oy < H) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (ox0 + j >= W) break;
+                int4 o;
+                __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    h[e] = __floats2half2_rn(act ? silu_tanh(acc[j][2 * e]) : acc[j][2 * e], act ? silu_tanh(acc[j][2 * e + 1]) : acc[j][2 * e + 1]);
+                *reinterpret_cast<int4*>(y + ((size_t)(n * H + oy) * W + ox0 + j) * y_ctot + y_coff + cb * DT_C + g * 8) = o;
+            }
+        }
+        __syncthreads();                                           // everyone is done with this stage: it may be refilled
+    }
+}
+
+typedef CUresult (*DwEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+DwEncodeFn dw_encoder() {
+    static DwEncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<DwEncodeFn>(p);
+    });
+    return fn;
+}
+
 }  // namespace
 
 extern "C" int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, const float* w27, const float* bias, int Cout, int act,
@@ -303,6 +427,31 @@ extern "C" int eitb_dwconv3x3_nhwc(const void* x, int N, int H, int W, int x_cto
     if (C % 8 || x_ctot % 8 || x_coff % 8 || y_ctot % 8 || y_coff % 8 || C / 8 > DW_THREADS) return EITB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w9)) & 15) return EITB_ERR_BAD_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (C % DT_C == 0 && dw_encoder() && !(reinterpret_cast<uintptr_t>(x) & 15)) {
+        // TMA-staged kernel: [N,H,W,x_ctot] seen as {C, W, H, N} with a (64 ch, 18 px, 10 rows, 1) box
+        alignas(64) CUtensorMap mx;
+        const char* xb0 = static_cast<const char*>(x) + (size_t)x_coff * 2;
+        const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        const cuuint64_t strides[3] = {(cuuint64_t)x_ctot * 2, (cuuint64_t)W * x_ctot * 2, (cuuint64_t)H * W * x_ctot * 2};
+        const cuuint32_t box[4] = {DT_C, DT_HW, DT_HH, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        if (dw_encoder()(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<char*>(xb0), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            const int tiles_x = eitb_div_up(W, DT_W), tiles_y = eitb_div_up(H, DT_H), cblocks = C / DT_C;
+            const long long tiles = (long long)N * tiles_x * tiles_y * cblocks;
+            if (tiles <= 0x7fffffffLL) {
+                const size_t smem = 2 * (size_t)DT_STAGE + 128;
+                if (cudaFuncSetAttribute(dwconv3x3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                    return EITB_ERR_LAUNCH;
+                const int grid = tiles < 2LL * EITB_NUM_SMS ? (int)tiles : 2 * EITB_NUM_SMS;
+                eitb_prof_begin("dwconv3x3_kernel", s);
+                dwconv3x3_tma_kernel<<<grid, 256, smem, s>>>(mx, (const __half*)w9, bias, N, H, W, C, act, (__half*)y, y_ctot, y_coff, tiles_x,
+                                                             tiles_y, cblocks);
+                EITB_CHECK_LAUNCH();
+                return EITB_OK;
+            }
+        }
+    }
     const int cgs = C / 8;
     int xb = DW_THREADS / (cgs * DW_ROWS);                        // pixel blocks per CTA row
     if (xb < 1) xb = 1;

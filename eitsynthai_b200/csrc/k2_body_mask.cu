@@ -132,11 +132,12 @@ morph5_bits_kernel(const uint32_t* __restrict__ in, long long n_words, int H, in
 // Blocks are anchored at (y, x) = top-left pixel, y in [-1, H-1], x in [-1, W-1].
 __global__ void __launch_bounds__(256)
 area_kernel(const int32_t* __restrict__ lab, int B, int H, int W, int32_t* __restrict__ area2, const int* __restrict__ skip) {
-    // grid (x: block-row chunks, y: block row + 1, z: image); one thread per 2x2 block anchor
-    const int b = blockIdx.z, y = (int)blockIdx.y - 1;
+    // grid (x: block-row chunks, y: block rows (strided), z: image); one thread per 2x2 block anchor
+    const int b = blockIdx.z;
     if (skip && skip[b]) return;
     const int bw = W + 1;
     const int nround = (bw + 31) & ~31;
+    for (int y = (int)blockIdx.y - 1; y < H; y += gridDim.y)
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
         int root = -1, add = 0;
         if (t < bw) {
@@ -399,7 +400,7 @@ labelled:
     if (cudaMemsetAsync(best, 0xff, (size_t)B * 8, s) != cudaSuccess) return EITB_ERR_LAUNCH;  // -1
     eitb_prof_begin("area_kernel", s);
     if (H + 1 > 65535 || B > 65535) return EITB_ERR_UNSUPPORTED;
-    area_kernel<<<dim3(eitb_div_up(W + 1, 256), H + 1, B), 256, 0, s>>>(labB, B, H, W, area2, skip);
+    area_kernel<<<dim3(eitb_div_up(W + 1, 256), H + 1 < 64 ? H + 1 : 64, B), 256, 0, s>>>(labB, B, H, W, area2, skip);
     EITB_CHECK_LAUNCH();
     eitb_prof_begin("best_kernel", s);
     best_kernel<<<dim3(eitb_grid_per_image((long long)H * W, 256, B), B), 256, 0, s>>>(labB, area2, H * W, best, skip);

@@ -133,6 +133,23 @@ def test_depthwise_and_stem():
         assert float((yu.buf.float() - refu).abs().max()) <= 2e-3 * float(refu.abs().max()) + 2e-3
 
 
+@pytest.mark.parametrize("C,H,W,B", [(128, 64, 64, 3), (256, 16, 16, 5), (64, 33, 17, 2), (512, 13, 20, 2), (24, 9, 31, 2)])
+def test_depthwise_tma_tiles_slices_and_fallback(C, H, W, B):
+    """K12 depthwise: the TMA-staged kernel (C % 64 == 0) on tile edges, odd maps and channel slices of wider buffers;
+    other channel counts take the direct kernel."""
+    from eitsynthai_b200.convnet import Act, PackedConv, conv
+    dev = _dev()
+    torch.manual_seed(C + H)
+    xb = torch.randn((B, H, W, C + 16), device=dev).half()
+    w = (torch.randn((C, 1, 3, 3), device=dev) / 3).half()
+    b = torch.randn((C,), device=dev)
+    yb = torch.full((B, H, W, C + 24), 5.0, device=dev).half()
+    conv(Act(xb, 8, C), PackedConv.from_weight(w, b, 1, C, True), out=Act(yb, 16, C))
+    ref = F.silu(F.conv2d(xb[..., 8:8 + C].permute(0, 3, 1, 2).float(), w.float(), b, 1, 1, 1, C)).permute(0, 2, 3, 1)
+    assert float((yb[..., 16:16 + C].float() - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 2e-3
+    assert bool((yb[..., :16] == 5).all()) and bool((yb[..., 16 + C:] == 5).all())
+
+
 @pytest.mark.parametrize("nc,size", [(4, (512, 512)), (4, (256, 256)), (1, (416, 640))])
 def test_network_matches_fp32_pytorch(nc, size):
     """The whole YOLO11s-seg forward on own kernels against the same weights run by PyTorch in fp32."""
