@@ -38,6 +38,7 @@ struct ConvArgs {
     int tmem_cols;
     int dbg;                           // experiments: 1 no TMA store, 2 no staging writes, 8 halo descriptors carry base_offset = tap column
     int halo, WB, HB, halo_bytes, halo_tx, halo_stages;
+    int pair;                          // halo mode: two M tiles (16 x 16 output pixels) share every weight stage
     int res_mode, res_tx, log_tw, log_th;   // 1: residual added after the activation; 2: added before it, read from a half-resolution map (nearest x2)
     int ws, ws_bytes;                  // weights stationary: all taps x K chunks of the (single) N tile stay in shared memory   // halo mode (3x3, stride 1): input tile + 1-pixel frame staged once per K chunk
 };
@@ -137,7 +138,7 @@ __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t* v) {
 // EW = epilogue warps: 8 ("heavy": one CTA per SM, N up to 256, deep ring) or 4 ("light": two CTAs per SM for
 // layers with <= 128 output channels, which are bandwidth-bound: twice the loads in flight and two
 // independent epilogues per SM).
-template <int CT, int EW>
+template <int CT, int EW, int PAIR = 0>
 __global__ void __launch_bounds__((2 + EW) * 32, EW == 8 ? 1 : 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
@@ -206,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     mbar_wait(bar_hempty + 8 * hs, hphase ^ 1);
                     if (el) {
                         mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)p.halo_tx);
-                        tma_load_4d(halo_u + (uint32_t)(hs * p.halo_bytes), &map_x, kc * p.Kc, bx * p.tw - 1, by * p.th - 1, bb,
+                        tma_load_4d(halo_u + (uint32_t)(hs * p.halo_bytes), &map_x, kc * p.Kc, bx * p.tw * (1 + PAIR) - 1, by * p.th - 1, bb,
                                     bar_hfull + 8 * hs);
                     }
                     if (++hs == p.halo_stages) { hs = 0; hphase ^= 1; }
@@ -259,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int acc = local & 1;
             mbar_wait(bar_tempty + 8 * acc, (uint32_t)((local >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t d_tmem = tmem + (uint32_t)(acc * p.ntile);
+            const uint32_t d_tmem = tmem + (uint32_t)(acc * p.ntile * (1 + PAIR));
             if (p.halo) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(bar_hfull + 8 * hs, hphase);
@@ -281,6 +282,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             if (el && !(p.dbg & 4)) {
                                 for (int k = 0; k < ksteps; ++k)
                                     umma_f16(d_tmem, dA + aq + 2 * k, dB + bq + 2 * k, idesc, (uint32_t)((kc | tap | k) != 0));
+                                if (PAIR) {                                // the right-hand M tile: 8 halo pixels further, same weights
+                                    const uint32_t aq2 = aq + 8u * row16;
+                                    for (int k = 0; k < ksteps; ++k)
+                                        umma_f16(d_tmem + (uint32_t)p.ntile, dA + aq2 + 2 * k, dB + bq + 2 * k, idesc, (uint32_t)((kc | tap | k) != 0));
+                                }
                             }
                             if (!p.ws) {
                                 __syncwarp();
@@ -324,9 +330,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
             const int acc = local & 1;
             const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-            const int bx = mt % p.tiles_x, by = (mt / p.tiles_x) % p.tiles_y, bb = mt / (p.tiles_x * p.tiles_y);
+            const int bxs = mt % p.tiles_x, by = (mt / p.tiles_x) % p.tiles_y, bb = mt / (p.tiles_x * p.tiles_y);
             mbar_wait(bar_tfull + 8 * acc, (uint32_t)((local >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int mp = 0; mp <= PAIR; ++mp) {                         // pair mode: left and right M tile of the super tile
+            const int bx = bxs * (1 + PAIR) + mp;
+            const int acc_col = (acc * (1 + PAIR) + mp) * p.ntile;
             for (int sl = 0; sl < p.slabs; ++sl, ++slab_count) {
                 const int buf = slab_count & 1;
                 unsigned char* stg = staging + (size_t)buf * p.slab_bytes;
@@ -356,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll 1
                 for (int half = half0; half < 2; half += kHalfStep) {
                 uint32_t v[CT];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.ntile + sl * p.slabC + half * CT);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_col + sl * p.slabC + half * CT);
                 tmem_ld<CT>(taddr, v);
                 // this thread's CT/8 16-byte chunks of a staging row, swizzled like the TMA store expects
                 uint32_t soff[CT / 8];
@@ -445,6 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
+            }                                                              // mp
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);              // this warp has drained the accumulator
@@ -503,7 +513,7 @@ int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // bit 4 (16) turns halo mode off, bit 5 (32) the two-CTAs-per-SM configuration, bit 6 (64) resident weights,
 // bit 8 (256) tries resident weights + half-N split first on 3x3 layers, bit 9 (512) keeps weights resident whenever they
 // fit (both measured slower, kept for A/B runs), bit 10 (1024) the two-op fp32 SiLU, bit 11 (2048) turns the
-// wave-quantisation choice of the N tile on (measured slower);
+// wave-quantisation choice of the N tile on (measured slower), bit 12 (4096) turns pair mode off;
 // the others are ConvArgs::dbg
 extern "C" int eitb_conv2d_debug(int flags) {
     g_dbg = flags & ~112; g_halo = !(flags & 16); g_light = !(flags & 32); g_ws = !(flags & 64);
@@ -595,13 +605,16 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
     // ring (two halo tiles, or three A stages); a CTA then keeps one N tile, so n_tiles must divide the grid.
     bool light = false;
     size_t smem = 0;
-    auto plan = [&](bool want_light, bool want_halo, bool need_ws) -> bool {
+    auto plan = [&](bool want_light, bool want_halo, bool need_ws, bool want_pair = false) -> bool {
         const int total = (want_light ? 113 : 227) * 1024;
         int avail = total - fixed;
         p.halo = want_halo ? 1 : 0;
+        p.pair = want_pair ? 1 : 0;
         p.halo_stages = 0; p.halo_bytes = 0; p.halo_tx = 0;
+        p.tmem_cols = pow2_ceil(2 * p.ntile * (1 + p.pair)) < 32 ? 32 : pow2_ceil(2 * p.ntile * (1 + p.pair));
+        if (p.tmem_cols > 512) return false;
         if (p.halo) {
-            p.WB = (g_dbg & 128) ? 16 : 10; p.HB = 18;                     // 16 x 8 output pixels + a 1-pixel frame
+            p.WB = want_pair ? 18 : (g_dbg & 128) ? 16 : 10; p.HB = 18;    // 8 (16 in pair mode) x 16 output pixels + a 1-pixel frame
             p.halo_tx = p.WB * p.HB * p.Kc * 2;
             p.halo_bytes = (p.halo_tx + 1023) / 1024 * 1024;
         }
@@ -623,6 +636,7 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
             if (p.halo_stages < 2) return false;
             avail -= p.halo_stages * p.halo_bytes;
         }
+        if (want_pair && (p.ws || want_light)) return false;               // pair mode is for streamed weights, one CTA per SM
         if (p.halo && p.ws) {
             p.stages = 0;
         } else {
@@ -645,7 +659,12 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
     }
     // first that fits: {two CTAs per SM, one} x {halo tile, nine shifted loads}
     if (!planned)
-        planned = (light_ok && halo_ok && plan(true, true, false)) || (halo_ok && plan(false, true, false)) ||
+        planned = (light_ok && halo_ok && plan(true, true, false)) ||
+                  // 3x3 layers that stream their weights (128 -> 128: 295 KB per 128 pixels): two M tiles per weight stage
+                  // (only where the halved tile count still fills the persistent grid many times over: on 16 x 16 maps it does not)
+                  (halo_ok && !(g_dbg & 4096) && (long long)((Wo + 15) / 16) * ((Ho + 15) / 16) * N >= 8LL * EITB_NUM_SMS &&
+                   plan(false, true, false, true)) ||
+                  (halo_ok && plan(false, true, false)) ||
                   (light_ok && plan(true, false, false)) || plan(false, false, false);
     if (!planned) return EITB_ERR_UNSUPPORTED;
     if (p.halo) {                        // row y of the 16 x 8 output tile = 8 consecutive halo pixels = one 8-row group of A
@@ -658,7 +677,8 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
     for (p.log_tw = 0; (1 << p.log_tw) < p.tw; ++p.log_tw) {}
     for (p.log_th = 0; (1 << p.log_th) < p.th; ++p.log_th) {}
     if (p.res_mode == 2 && (p.tw < 2 || p.th < 2)) return EITB_ERR_UNSUPPORTED;
-    p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th; p.tiles_b = (N + p.tn - 1) / p.tn;
+    p.tiles_x = (Wo + p.tw * (1 + p.pair) - 1) / (p.tw * (1 + p.pair));    // pair mode: super tiles of two M tiles side by side
+    p.tiles_y = (Ho + p.th - 1) / p.th; p.tiles_b = (N + p.tn - 1) / p.tn;
     const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
     if (total > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
     p.total_tiles = (int)total;
@@ -716,6 +736,13 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
             case 64: return launch(conv_tc_kernel<32, 4>, 192);
             case 32: return launch(conv_tc_kernel<16, 4>, 192);
             default: return launch(conv_tc_kernel<8, 4>, 192);
+        }
+    }
+    if (p.pair) {
+        switch (p.slabC) {
+            case 64: return launch(conv_tc_kernel<32, 8, 1>, 320);
+            case 32: return launch(conv_tc_kernel<16, 8, 1>, 320);
+            default: return launch(conv_tc_kernel<8, 8, 1>, 320);
         }
     }
     switch (p.slabC) {

@@ -145,18 +145,49 @@ stem_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ w, const
 #pragma unroll
     for (int e = 0; e < 8; ++e) b8[e] = bias ? bias[cgp * 8 + e] : 0.f;
     const int total = N * tiles_y * tiles_x;
+    // The input tile of one output tile is 17 rows x 129 bytes starting one byte before a 128-byte boundary: every thread
+    // fetches (at most) one aligned 16-byte chunk of it -- 17 rows x 10 chunks -- and the fetch for the NEXT tile is in
+    // flight while this tile is computed, so the only global-memory latency a CTA ever waits for is the first one.
+    const int crow = threadIdx.x / 10, cchunk = threadIdx.x - crow * 10;          // chunk row 0..16, chunk 0..9 (170 threads fetch)
+    const bool fetcher = threadIdx.x < ST_IN_H * 10;
+    const bool vec_ok = (W & 15) == 0 && !(reinterpret_cast<uintptr_t>(x) & 15);
+    auto fetch = [&](int tix, uint4& v, bool& ok) {
+        ok = false;
+        v = make_uint4(0u, 0u, 0u, 0u);
+        if (!fetcher || tix >= total || !vec_ok) return;
+        const int tx = tix % tiles_x, ty = (tix / tiles_x) % tiles_y, n = tix / (tiles_x * tiles_y);
+        const int iy = 2 * ty * ST_TO_H - 1 + crow, xs = 2 * tx * ST_TO_W - 16 + cchunk * 16;   // first pixel of the chunk
+        if (iy < 0 || iy >= H || xs < 0 || xs + 16 > W) return;                                 // stays zero: the padding
+        v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)n * H + iy) * W + xs));
+        ok = true;
+    };
+    uint4 pre;
+    bool pre_ok;
+    fetch(blockIdx.x, pre, pre_ok);
     for (int tix = blockIdx.x; tix < total; tix += gridDim.x) {
         const int tx = tix % tiles_x, ty = (tix / tiles_x) % tiles_y, n = tix / (tiles_x * tiles_y);
         const int ox0 = tx * ST_TO_W, oy0 = ty * ST_TO_H;
         const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
-        const uint8_t* img = x + (size_t)n * H * W;
         __syncthreads();                                           // the previous tile is consumed (and the table is written)
-        for (int i = threadIdx.x; i < ST_IN_H * ST_IN_W; i += 256) {
-            const int r = i / ST_IN_W, c = i - r * ST_IN_W;
-            const int iy = iy0 + r, ix = ix0 + c;
-            tile[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? lut[__ldg(img + (size_t)iy * W + ix)] : 0.f;
+        if (vec_ok) {
+            if (fetcher) {
+                const uint32_t wv[4] = {pre.x, pre.y, pre.z, pre.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int c = cchunk * 16 + k - 15;            // tile column of this byte
+                    if (c >= 0 && c < ST_IN_W) tile[crow][c] = pre_ok ? lut[(wv[k >> 2] >> (8 * (k & 3))) & 0xffu] : 0.f;
+                }
+            }
+        } else {
+            const uint8_t* img = x + (size_t)n * H * W;
+            for (int i = threadIdx.x; i < ST_IN_H * ST_IN_W; i += 256) {
+                const int r = i / ST_IN_W, c = i - r * ST_IN_W;
+                const int iy = iy0 + r, ix = ix0 + c;
+                tile[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? lut[__ldg(img + (size_t)iy * W + ix)] : 0.f;
+            }
         }
         __syncthreads();
+        fetch(tix + gridDim.x, pre, pre_ok);                       // in flight during the arithmetic below
         const int ox = ox0 + col;
         if (ox >= Wo) continue;
         float r0[3], r1[3], r2[3];
