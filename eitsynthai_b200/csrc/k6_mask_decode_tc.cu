@@ -7,12 +7,17 @@
 // -> 64 x 48 output pixels.
 //   B operand  [N = 256 pixels][K = 64] fp16, K-major, 128-byte swizzle: the 32 prototype values of a
 //              pixel, twice (for the high and the low half of the coefficients);
-//   A operand  [M = 128 instances][K = 64] fp16: coefficient split hi | lo (c = hi + lo exactly to
+//   A operand  [M = 128 rows][K = 64] fp16: coefficient split hi | lo (c = hi + lo exactly to
 //              22 bits), so fp32 coefficients lose nothing and every product is exact in fp32;
+//              up to 56 live instances per pass, 14 in each 32-lane TMEM quadrant, so that all eight
+//              warps can pull logits out of tensor memory at the same time;
 //   D          [128 lanes][256 columns] fp32 in TMEM: 4 x tcgen05.mma (M128 N256 K16), one commit.
-// Epilogue: the two warps that own a 32-lane quadrant pull its logits out with tcgen05.ld, apply the
-// crop, park them in shared memory, and all 8 warps run the fixed-weight upsample + threshold + OR
-// for those 32 instances.  fp32 masks never leave the SM.
+// Epilogue (round 2): every warp reads its quadrant's half of the columns with tcgen05.ld.x32, applies
+// the crop and parks the logits of ALL live instances in shared memory in one sweep (conflict-free: a lane
+// is an instance, rows are 253 words apart); one barrier; then the fixed-weight upsample + threshold + OR
+// runs over the instances exactly as in the CUDA-core kernel.  Round 1 parked and upsampled one quadrant
+// at a time with two warps reading TMEM and six waiting (33 % of the stall samples on that barrier).
+// 108 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM.  fp32 masks never leave the SM.
 #include "common.cuh"
 
 namespace {
@@ -21,17 +26,19 @@ constexpr int PTX_ = 16, PTY_ = 12;          // prototype pixels per tile
 constexpr int HTX = PTX_ + 2, HTY = PTY_ + 2;
 constexpr int HPT = HTX * HTY;               // 252 halo pixels
 constexpr int NCOL = 256;                    // MMA N, TMEM columns
-constexpr int MROW = 128;                    // MMA M: instances per pass
+constexpr int MROW = 128;                    // MMA M
+constexpr int LPQ = 14;                      // live instances per TMEM lane quadrant
+constexpr int LIVE = 4 * LPQ;                // live instances per pass
 constexpr int KDIM = 64;                     // 32 coefficients, hi | lo
 constexpr int LSTRIDE = 253;                 // odd row stride of the parked logits: conflict-free
 constexpr int kThreads = 256;
 
 constexpr int OFF_B = 0;                                   // 256 x 128 B
 constexpr int OFF_A = OFF_B + NCOL * 128;                  // 128 x 128 B
-constexpr int OFF_LS = OFF_A + MROW * 128;                 // 32 x 253 x 4
-constexpr int OFF_BOX = OFF_LS + 32 * LSTRIDE * 4;         // 128 x 4 f32
-constexpr int OFF_INFO = OFF_BOX + MROW * 16;              // 128 x 2 int
-constexpr int OFF_ACT = OFF_INFO + MROW * 8;               // max_det ints
+constexpr int OFF_LS = OFF_A + MROW * 128;                 // LIVE x 253 x 4
+constexpr int OFF_BOX = OFF_LS + LIVE * LSTRIDE * 4;       // LIVE x 4 f32
+constexpr int OFF_INFO = OFF_BOX + LIVE * 16;              // LIVE x 2 int
+constexpr int OFF_ACT = OFF_INFO + LIVE * 8;               // max_det ints
 // after act: mbarrier (8 B), tmem slot (4 B), counters
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,7 +75,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // byte offset of 16-byte chunk `c` (0..7) of row `r` in the swizzled operand tile
 __device__ __forceinline__ int swz(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n_det, int max_det,
                       const __half* __restrict__ protos, int proto_nhwc, int mh, int mw, int H, int W, int tiles_x,
                       int tiles_per_img, int variant, uint8_t* __restrict__ code, int32_t* __restrict__ inst_area,
@@ -83,8 +90,6 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + OFF_ACT + max_det * 4 + ((8 - (max_det * 4) % 8) % 8));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
     int* s_nact = reinterpret_cast<int*>(tmem_slot + 1);
-    float* colx = reinterpret_cast<float*>(s_nact + 1);                       // [NCOL] prototype x of every halo column
-    float* coly = colx + NCOL;                                                // [NCOL] prototype y (columns >= HPT: -1, never inside a box)
 
     constexpr int nm = 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,11 +102,6 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
     const float rx = (float)((double)mw / (double)W), ry = (float)((double)mh / (double)H);
     const bool int_crop = (variant & 4) && n_det[b] < 50;
 
-    if (tid < NCOL) {
-        const int hy = tid / HTX, hx = tid - hy * HTX;
-        colx[tid] = tid < HPT ? (float)min(max((int)(blockIdx.x - (blockIdx.x / tiles_per_img) * tiles_per_img) % tiles_x * PTX_ - 1 + hx, 0), mw - 1) : -1.f;
-        coly[tid] = tid < HPT ? (float)min(max((int)(blockIdx.x - (blockIdx.x / tiles_per_img) * tiles_per_img) / tiles_x * PTY_ - 1 + hy, 0), mh - 1) : -1.f;
-    }
     if (smem_u32(sB) & 1023u) __trap();                                        // swizzled operand tiles need 1 KiB alignment
     if (tid == 0) {
         *s_nact = 0;
@@ -177,21 +177,25 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
     // instruction descriptor: D fp32, A/B fp16, both K-major, N = 256, M = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(MROW >> 4) << 24);
     uint32_t phase = 0;
+    const int pq = warp & 3;                                                  // the TMEM lane quadrant this warp may read
+    const int pslot = pq * LPQ + lane;                                        // live slot of this lane in that quadrant
 
-    for (int p0 = 0; p0 < nact; p0 += MROW) {
-        const int np = min(MROW, nact - p0);
-        // ---- A operand: coefficients hi | lo; boxes and class codes
-        for (int idx = tid; idx < MROW * 4; idx += kThreads) {                // (instance row, chunk of 8 coefficients)
-            const int i = idx >> 2, j = idx & 3;
+    for (int p0 = 0; p0 < nact; p0 += LIVE) {
+        const int np = min(LIVE, nact - p0);
+        // ---- A operand: row 32*q + l holds live slot q*LPQ + l (l < LPQ), every other row is zero
+        for (int idx = tid; idx < MROW * 4; idx += kThreads) {                // (row, chunk of 8 coefficients)
+            const int row = idx >> 2, j = idx & 3;
+            const int slot = (row >> 5) * LPQ + (row & 31);
+            const bool live = (row & 31) < LPQ && slot < np;
             __align__(16) __half hi[8], lo[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float c = i < np ? dimg[(long long)act[p0 + i] * D + 6 + j * 8 + e] : 0.f;
+                const float c = live ? dimg[(long long)act[p0 + slot] * D + 6 + j * 8 + e] : 0.f;
                 hi[e] = __float2half_rn(c);
                 lo[e] = __float2half_rn(c - __half2float(hi[e]));
             }
-            *reinterpret_cast<int4*>(sA + swz(i, j)) = *reinterpret_cast<const int4*>(hi);
-            *reinterpret_cast<int4*>(sA + swz(i, j + 4)) = *reinterpret_cast<const int4*>(lo);
+            *reinterpret_cast<int4*>(sA + swz(row, j)) = *reinterpret_cast<const int4*>(hi);
+            *reinterpret_cast<int4*>(sA + swz(row, j + 4)) = *reinterpret_cast<const int4*>(lo);
         }
         if (tid < np) {
             const float* d = dimg + (long long)act[p0 + tid] * D;
@@ -228,61 +232,62 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
         }
         asm volatile("tcgen05.fence::after_thread_sync;");
 
-        for (int q = 0; q * 32 < np; ++q) {                                   // one 32-lane quadrant = 32 instances
-            const int ng = min(32, np - q * 32);
-            // ---- the two warps that may touch quadrant q park its cropped logits in shared memory
-            if ((warp & 3) == q) {
-                const int g = lane;                                           // instance within the quadrant
-                const int half_cols = NCOL / 2;
-                const int c_begin = (warp >> 2) * half_cols;
-                const float bx1 = sbox[(q * 32 + g) * 4], by1 = sbox[(q * 32 + g) * 4 + 1];
-                const float bx2 = sbox[(q * 32 + g) * 4 + 2], by2 = sbox[(q * 32 + g) * 4 + 3];
-                for (int c0 = c_begin; c0 < c_begin + half_cols; c0 += 32) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (g < ng) {
-                        const int e_end = min(32, HPT - c0);
+        // ---- all eight warps park the cropped logits of every live instance (lane = instance, 128 columns per warp)
+        {
+            const bool live = lane < LPQ && pslot < np;
+            float bx1 = 0.f, by1 = 0.f, bx2 = 0.f, by2 = 0.f;
+            if (live) { bx1 = sbox[pslot * 4]; by1 = sbox[pslot * 4 + 1]; bx2 = sbox[pslot * 4 + 2]; by2 = sbox[pslot * 4 + 3]; }
+            const int c_begin = (warp >> 2) * (NCOL / 2);
+            const int col_x0 = tx * PTX_ - 1, col_y0 = ty * PTY_ - 1;
+#pragma unroll 1
+            for (int c0 = c_begin; c0 < c_begin + NCOL / 2; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(pq * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (live) {
+                    int hy = c0 / HTX, hx = c0 - hy * HTX;                     // halo position of column c0 (warp-uniform)
+                    float* dst = Ls + pslot * LSTRIDE + c0;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            if (e < e_end) {
-                                const float fx = colx[c0 + e], fy = coly[c0 + e];        // broadcast reads
-                                float val = __uint_as_float(v[e]);
-                                if (variant & 1) val = 1.f / (1.f + expf(-val));
-                                Ls[g * LSTRIDE + c0 + e] = (fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2) ? val : 0.f;
-                            }
+                    for (int e = 0; e < 32; ++e) {
+                        if (c0 + e < HPT) {
+                            const float fx = (float)min(max(col_x0 + hx, 0), mw - 1), fy = (float)min(max(col_y0 + hy, 0), mh - 1);
+                            float val = __uint_as_float(v[e]);
+                            if (variant & 1) val = 1.f / (1.f + expf(-val));
+                            dst[e] = (fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2) ? val : 0.f;
                         }
+                        if (++hx == HTX) { hx = 0; ++hy; }
                     }
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncthreads();
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            // ---- x4 bilinear (align_corners=False) + threshold + OR, all warps, 32 instances
-            if (row_ok) {
-                for (int g = 0; g < ng; ++g) {
-                    if (sbox[(q * 32 + g) * 4 + 3] <= wrow_lo || sbox[(q * 32 + g) * 4 + 1] > wrow_hi) continue;   // warp-uniform
-                    const float* L0 = Ls + g * LSTRIDE + hy0 * HTX + cg * 4;
-                    const float* L1 = L0 + HTX;
-                    float a0[6], a1[6];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        // ---- x4 bilinear (align_corners=False) + threshold + OR over the live instances
+        if (row_ok) {
+            for (int g = 0; g < np; ++g) {
+                if (sbox[g * 4 + 3] <= wrow_lo || sbox[g * 4 + 1] > wrow_hi) continue;   // warp-uniform
+                const float* L0 = Ls + g * LSTRIDE + hy0 * HTX + cg * 4;
+                const float* L1 = L0 + HTX;
+                float a0[6], a1[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) { a0[i] = L0[i]; a1[i] = L1[i]; }
-                    float vmin = fminf(a0[0], a1[0]), vmax = fmaxf(a0[0], a1[0]);
+                for (int i = 0; i < 6; ++i) { a0[i] = L0[i]; a1[i] = L1[i]; }
+                float vmin = fminf(a0[0], a1[0]), vmax = fmaxf(a0[0], a1[0]);
 #pragma unroll
-                    for (int i = 1; i < 6; ++i) { vmin = fminf(vmin, fminf(a0[i], a1[i])); vmax = fmaxf(vmax, fmaxf(a0[i], a1[i])); }
-                    // every output is a convex combination of these 12 logits: all above / none above the threshold
-                    // decides the 16 pixels without interpolating (only mask borders take the slow path)
-                    uint32_t bits = vmin > thr ? 0xffffu : 0u;
-                    if (vmax > thr && !(vmin > thr)) {
+                for (int i = 1; i < 6; ++i) { vmin = fminf(vmin, fminf(a0[i], a1[i])); vmax = fmaxf(vmax, fmaxf(a0[i], a1[i])); }
+                // every output is a convex combination of these 12 logits: all above / none above the threshold
+                // decides the 16 pixels without interpolating (only mask borders take the slow path)
+                uint32_t bits = vmin > thr ? 0xffffu : 0u;
+                if (vmax > thr && !(vmin > thr)) {
                     float V[6];
 #pragma unroll
                     for (int i = 0; i < 6; ++i) V[i] = (1.f - ly) * a0[i] + ly * a1[i];
@@ -295,24 +300,22 @@ mask_decode_tc_kernel(const float* __restrict__ dets, const int32_t* __restrict_
                         const float vv = (1.f - lx) * V[x0] + lx * V[x0 + 1];
                         bits |= (vv > thr ? 1u : 0u) << j;
                     }
-                    }
-                    if (!in_img) bits = 0;
-                    const uint32_t cc = (uint32_t)sinfo[(q * 32 + g) * 2];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)                    // 4 mask bits -> 4 bytes of the class code
-                        codes[k] |= ((((bits >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) * cc;
-                    const int inst = sinfo[(q * 32 + g) * 2 + 1];
-                    if (inst_bits && in_img) {
-                        const long long o = (((long long)b * max_det + inst) * H + oy) * (W >> 3) + (ox0 >> 3);
-                        *reinterpret_cast<uint16_t*>(inst_bits + o) = (uint16_t)bits;
-                    }
-                    if (inst_area && bits) atomicAdd(inst_area + (long long)b * max_det + inst, __popc(bits));
                 }
+                if (!in_img) bits = 0;
+                const uint32_t cc = (uint32_t)sinfo[g * 2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                    // 4 mask bits -> 4 bytes of the class code
+                    codes[k] |= ((((bits >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) * cc;
+                const int inst = sinfo[g * 2 + 1];
+                if (inst_bits && in_img) {
+                    const long long o = (((long long)b * max_det + inst) * H + oy) * (W >> 3) + (ox0 >> 3);
+                    *reinterpret_cast<uint16_t*>(inst_bits + o) = (uint16_t)bits;
+                }
+                if (inst_area && bits) atomicAdd(inst_area + (long long)b * max_det + inst, __popc(bits));
             }
-            __syncthreads();
         }
         asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();                                                      // TMEM and A are free for the next pass
+        __syncthreads();                                                      // TMEM, A and the parked logits are free for the next pass
         asm volatile("tcgen05.fence::after_thread_sync;");
     }
     if (in_img)
@@ -330,7 +333,7 @@ int eitb_mask_decode_tc(const float* dets, const int32_t* n_det, int max_det, co
                         int mw, int H, int W, int variant, uint8_t* code, int32_t* inst_area, uint8_t* inst_bits,
                         cudaStream_t s) {
     const int tiles_x = eitb_div_up(mw, PTX_), tiles_y = eitb_div_up(mh, PTY_);
-    const size_t smem = (size_t)OFF_ACT + (size_t)max_det * 4 + 64 + 2 * NCOL * sizeof(float);
+    const size_t smem = (size_t)OFF_ACT + (size_t)max_det * 4 + 64;
     if (cudaFuncSetAttribute(mask_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     const long long grid = (long long)B * tiles_x * tiles_y;
