@@ -5,8 +5,9 @@ not installed here) and then copies all pixels twice (``np.stack(axis=-1)``, uti
 module is the first row of SURVEY §8(f): a minimal reader for the two *uncompressed* little-endian
 transfer syntaxes CT scanners export (Implicit VR 1.2.840.10008.1.2 and Explicit VR
 1.2.840.10008.1.2.1) that hands the PixelData bytes straight to a pinned buffer, one copy, ready for
-the host->device stream.  Compressed syntaxes raise ``UnsupportedTransferSyntax`` (pydicom is used
-for those when it is importable).  ``write_dicom`` produces files for the synthetic series of the
+the host->device stream.  Deflated Explicit VR, RLE Lossless and JPEG Lossless (process 14) files are decoded
+too (zlib; libeitb200's host codecs, csrc/codec_host.cu); the remaining compressed syntaxes (JPEG-LS, JPEG 2000,
+lossy JPEG) raise ``UnsupportedTransferSyntax`` (pydicom is used for those when it is importable).  ``write_dicom`` produces files for the synthetic series of the
 tests; PARITY UNPINNED against pydicom itself (not available offline) -- the reader is checked on
 files it did not write only through the DICOM standard's layout (PS3.5 §7.1, §7.5, PS3.10 §7.1).
 """
@@ -20,6 +21,9 @@ import numpy as np
 
 IMPLICIT_LE = "1.2.840.10008.1.2"
 EXPLICIT_LE = "1.2.840.10008.1.2.1"
+DEFLATED_LE = "1.2.840.10008.1.2.1.99"                     # the data set is one raw-deflate stream
+RLE_LOSSLESS = "1.2.840.10008.1.2.5"
+JPEG_LOSSLESS = ("1.2.840.10008.1.2.4.57", "1.2.840.10008.1.2.4.70")   # process 14, any selection value / SV1
 _LONG_VR = {b"OB", b"OW", b"OF", b"SQ", b"UT", b"UN", b"OD", b"OL", b"UC", b"UR", b"OV", b"SV", b"UV"}
 #: the tags the hot path reads (utils.py:46-105, 621-656; ai_tools.py:337) -> VR for implicit files
 _WANTED = {
@@ -138,7 +142,7 @@ def _next_element(buf: bytes, pos: int, explicit: bool, skip_only: bool = False)
         vrs = _WANTED.get(tag, "UN")
     if ln == 0xFFFFFFFF:
         if tag == (0x7FE0, 0x0010):
-            raise UnsupportedTransferSyntax("encapsulated (compressed) PixelData")
+            return voff, tag, vrs, (voff, -1)                # encapsulated: fragments follow (read_dicom decodes them)
         return _skip_undefined(buf, voff, explicit), tag, vrs, (voff, 0)
     return voff + ln, tag, vrs, (voff, ln)
 
@@ -155,20 +159,76 @@ def read_dicom(data: bytes) -> Dataset:
             pos, tag, vr, (voff, ln) = _next_element(buf, pos, True)
             if tag == (0x0002, 0x0010):
                 syntax = bytes(buf[voff:voff + ln]).decode("latin-1").rstrip(" \x00")
-    if syntax not in (IMPLICIT_LE, EXPLICIT_LE):
-        raise UnsupportedTransferSyntax(syntax)
-    explicit = syntax == EXPLICIT_LE
+    if syntax not in (IMPLICIT_LE, EXPLICIT_LE, DEFLATED_LE, RLE_LOSSLESS) + JPEG_LOSSLESS:
+        raise UnsupportedTransferSyntax(syntax)                    # JPEG-LS, JPEG 2000, lossy JPEG, big endian: pydicom's job
+    if syntax == DEFLATED_LE:
+        import zlib
+        buf = bytes(buf[:pos]) + zlib.decompress(bytes(buf[pos:]), -15)
+    explicit = syntax != IMPLICIT_LE
     ds._tags[(0x0002, 0x0010)] = syntax
     while pos + 8 <= len(buf):
         pos, tag, vr, (voff, ln) = _next_element(buf, pos, explicit)
         if tag == (0x7FE0, 0x0010):
-            ds._pixel_bytes, ds._pixel_off, ds._pixel_len = buf, voff, ln
+            if ln < 0:                                             # encapsulated pixel data
+                if syntax != RLE_LOSSLESS and syntax not in JPEG_LOSSLESS:
+                    raise UnsupportedTransferSyntax(f"encapsulated PixelData in {syntax}")
+                px = _decode_encapsulated(buf, voff, syntax, ds)
+                ds._pixel_bytes, ds._pixel_off, ds._pixel_len = px, 0, len(px)
+            else:
+                ds._pixel_bytes, ds._pixel_off, ds._pixel_len = buf, voff, ln
             break
         if tag in _WANTED:
             ds._tags[tag] = _convert(_WANTED[tag] if not explicit else vr, bytes(buf[voff:voff + ln]))
     if ds._pixel_bytes is None:
         raise ValueError("no PixelData element")
     return ds
+
+
+def _fragments(buf, pos: int):
+    """Items of an encapsulated PixelData element (PS3.5 A.4): the basic offset table, then the fragments."""
+    frags, first = [], True
+    while pos + 8 <= len(buf):
+        g, e, ln = struct.unpack_from("<HHI", buf, pos)
+        pos += 8
+        if (g, e) == (0xFFFE, 0xE0DD):
+            break
+        if (g, e) != (0xFFFE, 0xE000) or ln == 0xFFFFFFFF:
+            raise ValueError("malformed encapsulated PixelData")
+        if first:
+            first = False                                         # basic offset table (possibly empty)
+        else:
+            frags.append((pos, ln))
+        pos += ln
+    return frags
+
+
+def _decode_encapsulated(buf, pos: int, syntax: str, ds: "Dataset") -> bytes:
+    """One frame of RLE Lossless or JPEG Lossless pixel data -> little-endian stored values, decoded by
+    libeitb200's host codecs (csrc/codec_host.cu; the reference leaves this to pydicom + pylibjpeg)."""
+    import ctypes as C
+
+    from ... import cabi
+    lib = cabi.load()
+    h, w = ds.shape
+    bps = (int(ds._tags.get((0x0028, 0x0100), 16)) + 7) // 8
+    frags = _fragments(buf, pos)
+    if not frags:
+        raise ValueError("no pixel data fragment")
+    raw = bytes(buf)
+    if syntax == RLE_LOSSLESS:
+        off, ln = frags[0]                                        # one fragment per frame
+        out = (C.c_uint8 * (h * w * bps))()
+        rc = lib.eitb_rle_decode_frame(raw[off:off + ln], ln, h, w, bps, out)
+        if rc != 0:
+            raise ValueError(f"RLE frame: {cabi.strerror(rc)}")
+        return bytes(out)
+    stream = b"".join(raw[o:o + n] for o, n in frags)             # a JPEG stream may be split over fragments
+    rows, cols, prec = C.c_int(0), C.c_int(0), C.c_int(0)
+    out = (C.c_uint16 * (h * w))()
+    rc = lib.eitb_jpeg_lossless_decode(stream, len(stream), C.byref(rows), C.byref(cols), C.byref(prec), out, h * w)
+    if rc != 0 or (rows.value, cols.value) != (h, w):
+        raise ValueError(f"JPEG lossless frame: {cabi.strerror(rc) if rc else 'size mismatch'}")
+    return bytes(out)
 
 
 # ------------------------------------------------------------------------------------------ writer

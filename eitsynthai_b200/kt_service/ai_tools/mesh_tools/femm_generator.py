@@ -64,13 +64,25 @@ def label_triangles(nodes_xy, triangles, contours, outer_contour_class=4, device
     return out.cpu().numpy()
 
 
-def export_mesh_for_femm(filename, nodes_xy, triangles, classes, isSaveToFile=False):
+#: class ids as the segmentation writes them (utils.py:498-505: the polygon strings' first field) ...
+LABEL_CLASS_NAMES = {0: "bone", 1: "muscles", 2: "lung", 3: "adipose", 4: "skin"}
+#: ... and as the FEMM model generator reads them (femm_tools/model_generator.py:13).  Ids 2 and 3 are swapped between
+#: the two tables in the reference; ``export_mesh_for_femm`` keeps the reference's behaviour (ids pass through
+#: unchanged) unless ``femm_class_order=True`` asks for the ids the consumer's table means.
+FEMM_CLASS_NAMES = {0: "bone", 1: "muscles", 2: "fat", 3: "lung", 4: "skin"}
+
+
+def export_mesh_for_femm(filename, nodes_xy, triangles, classes, isSaveToFile=False, femm_class_order=False):
     """femm_generator.py:187-265: used-node compaction (sorted tags -> 0-based) and the CLASS vector,
-    without the O(T^2) tag search."""
+    without the O(T^2) tag search.  ``femm_class_order``: translate lung / adipose (2 / 3 of utils.py:498-505) to
+    the ids femm_tools/model_generator.py:13 gives them (3 / 2); off by default, like the reference."""
     tri = np.asarray(triangles, np.int64)
     used = np.unique(tri)
     remap = np.full(int(used.max()) + 1 if used.size else 0, -1, np.int64)
     remap[used] = np.arange(used.size)
+    if femm_class_order:
+        swap = {2: 3, 3: 2}
+        classes = [swap.get(int(c), int(c)) for c in classes]
     data = {"NODES": np.asarray(nodes_xy, np.float64)[used].tolist(), "TRIANGLES": remap[tri].tolist(),
             "CLASS": [int(c) for c in classes]}
     if isSaveToFile is True and filename:

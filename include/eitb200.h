@@ -330,6 +330,17 @@ int eitb_polygons_for_mesh(const int32_t* n_polys, const int32_t* poly_cls, cons
                            double* out_xy, int32_t* out_off, int32_t* out_cls, int32_t* out_n,
                            void* ws, size_t ws_bytes, eitb_stream_t stream);
 
+/* ---- host codecs for compressed DICOM pixel data (ingest) -------------------------
+ * Replace what pydicom + pylibjpeg do behind pydicom.dcmread(...).pixel_array (utils.py:52-60, 98;
+ * requirements.txt:9-13) for the two lossless syntaxes of CT exports.  Host pointers, no CUDA.
+ *   eitb_rle_decode_frame: one RLE Lossless frame (PS3.5 Annex G) -> rows*cols samples, little endian
+ *   eitb_jpeg_lossless_decode: a JPEG lossless (SOF3, one component, 2-16 bits, any predictor, restart
+ *   intervals) stream -> out[rows*cols] uint16; out == NULL only reports rows / cols / precision */
+int eitb_rle_decode_frame(const uint8_t* frag, size_t frag_len, int rows, int cols, int bytes_per_sample,
+                          uint8_t* out);
+int eitb_jpeg_lossless_decode(const uint8_t* data, size_t len, int* rows, int* cols, int* precision,
+                              uint16_t* out, size_t out_capacity);
+
 #ifdef __cplusplus
 }
 #endif

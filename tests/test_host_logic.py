@@ -118,3 +118,43 @@ def test_tri_label_oracle_against_exact_rational_arithmetic_on_the_most_delicate
     tri = np.array([[0, 1, 2], [3, 4, 5]], np.int64)
     args = (nodes, tri, sq, np.array([0, 5], np.int32), np.array([2], np.int32))
     assert TL.label_triangles_exact(*args).tolist() == [4, 2] == TL.label_triangles(*args).tolist()
+
+
+def test_export_mesh_for_femm_matches_the_reference_statement(tmp_path):
+    """export_mesh_for_femm of the mirror against a literal restatement of femm_generator.py:187-265 working on
+    Gmsh-style arrays (1-based node tags with unused nodes, element tags, class groups and its O(T^2) tag search):
+    same dictionary, same file bytes."""
+    from eitsynthai_b200.kt_service.ai_tools.mesh_tools import femm_generator as FG
+    rng = np.random.default_rng(3)
+    n_nodes, T = 40, 55
+    coords = rng.uniform(0, 100, (n_nodes, 2))
+    tri = rng.integers(0, n_nodes - 5, (T, 3))                    # the last five nodes stay unused
+    cls = rng.integers(0, 5, T)
+    # --- the reference's procedure, on gmsh-like inputs
+    node_tags = np.arange(1, n_nodes + 1)
+    node_dict = {int(t): (coords[i, 0], coords[i, 1]) for i, t in enumerate(node_tags)}
+    elem_tags = np.arange(101, 101 + T)
+    class_groups = {}
+    for e, c in zip(elem_tags, cls):
+        class_groups.setdefault(int(c), []).append(int(e))
+    triangle_data, used = [], set()
+    for i in range(T):
+        n1, n2, n3 = (int(v) + 1 for v in tri[i])
+        used.update([n1, n2, n3])
+        cid = next(c for c, tags in class_groups.items() if int(elem_tags[i]) in tags)
+        triangle_data.append((n1, n2, n3, cid))
+    tag_to_index = {t: i + 1 for i, t in enumerate(sorted(used))}
+    want = {"NODES": [[float(node_dict[t][0]), float(node_dict[t][1])] for t in sorted(used)],
+            "TRIANGLES": [[tag_to_index[a] - 1, tag_to_index[b] - 1, tag_to_index[c] - 1] for a, b, c, _ in triangle_data],
+            "CLASS": [int(float(c)) for *_, c in triangle_data]}
+    lines = ["# NODES\n"] + [f"{tag_to_index[t]} {node_dict[t][0]:.12f} {node_dict[t][1]:.12f}\n" for t in sorted(used)]
+    lines += ["\n# TRIANGLES\n"] + [f"{tag_to_index[a]} {tag_to_index[b]} {tag_to_index[c]} {k}\n" for a, b, c, k in triangle_data]
+    # --- the mirror
+    path = tmp_path / "mesh.txt"
+    got = FG.export_mesh_for_femm(str(path), coords, tri, cls, True)
+    assert got == want
+    assert path.read_text() == "".join(lines)
+    # the lung / fat id swap between utils.py:498-505 and femm_tools/model_generator.py:13 is explicit, off by default
+    swapped = FG.export_mesh_for_femm(None, coords, tri, cls, False, femm_class_order=True)["CLASS"]
+    assert swapped == [{2: 3, 3: 2}.get(int(c), int(c)) for c in cls]
+    assert FG.LABEL_CLASS_NAMES[2] == "lung" and FG.FEMM_CLASS_NAMES[2] == "fat"
