@@ -230,7 +230,15 @@ class ConvNet:
         blocks = []
         for blk in m.m:
             a = blk.attn
-            blocks.append((P(a.qkv), P(a.pe), P(a.proj), P(blk.ffn[0]), P(blk.ffn[1]), a.num_heads, a.key_dim, a.head_dim, a.scale))
+            # qkv output channels regrouped from [head][q | k | v] to [q of all heads | k of all heads | v of all heads]:
+            # V (and the attention output) then is a contiguous channel slice [head][d] of the buffer -- the layout the
+            # position-encoding depthwise conv and proj expect -- and needs no gather copy
+            per = 2 * a.key_dim + a.head_dim
+            idx = [h * per + off + i for off, n in ((0, a.key_dim), (a.key_dim, a.key_dim), (2 * a.key_dim, a.head_dim))
+                   for h in range(a.num_heads) for i in range(n)]
+            idx = torch.tensor(idx, device=a.qkv.conv.weight.device)
+            qkv = PackedConv.from_weight(a.qkv.conv.weight.detach()[idx], a.qkv.fused_bias[idx], 1, 1, a.qkv.has_act)
+            blocks.append((qkv, P(a.pe), P(a.proj), P(blk.ffn[0]), P(blk.ffn[1]), a.num_heads, a.key_dim, a.head_dim, a.scale))
         return (cv1, P(m.cv2), blocks, m.c)
 
     # ------------------------------------------------------------------ block executors
@@ -274,15 +282,16 @@ class ConvNet:
         conv(x, cv1, out=buf)
         b = buf.slice(c, c)
         for qkv_l, pe_l, proj_l, f0, f1, heads, kd, hd, scale in blocks:
-            qkv = conv(b, qkv_l).buf.view(B, H * W, heads, 2 * kd + hd)
-            q = qkv[..., :kd].permute(0, 2, 1, 3)                   # [B, heads, N, kd]
-            k = qkv[..., kd:2 * kd].permute(0, 2, 3, 1)             # [B, heads, kd, N]
-            v = qkv[..., 2 * kd:].permute(0, 2, 1, 3)               # [B, heads, N, hd]
-            attn = torch.softmax((q @ k) * scale, dim=-1)
-            o = (attn @ v).permute(0, 2, 1, 3).reshape(B, H, W, heads * hd)
-            vimg = Act(qkv[..., 2 * kd:].reshape(B, H, W, heads * hd).contiguous())
-            o = Act((o + conv(vimg, pe_l).buf).contiguous())
-            x1 = conv(o, proj_l, res=b)
+            qkv = conv(b, qkv_l)                                    # [B, H, W, q | k | v], each [head][d]
+            N = H * W
+            flat = qkv.buf.view(B, N, -1)
+            q = flat[..., :heads * kd].view(B, N, heads, kd).transpose(1, 2)                  # [B, heads, N, kd] (strided views)
+            k = flat[..., heads * kd:2 * heads * kd].view(B, N, heads, kd).transpose(1, 2)
+            v = flat[..., 2 * heads * kd:].view(B, N, heads, hd).transpose(1, 2)              # [B, heads, N, hd]
+            att = torch.nn.functional.scaled_dot_product_attention(q, k, v, scale=scale)      # the one PyTorch-owned op of the network
+            pe = conv(qkv.slice(2 * heads * kd, heads * hd), pe_l)  # depthwise position encoding straight from the V slice
+            pe.buf.view(B, N, heads, hd).add_(att.transpose(1, 2))  # o = attention + pe(v), in the NHWC buffer
+            x1 = conv(pe, proj_l, res=b)
             conv(conv(x1, f0), f1, out=b, res=x1)
         return conv(buf, cv2, out=out)
 

@@ -173,7 +173,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = threadIdx.x; i < p.n_tiles * p.ntile; i += kThreads) sbias[i] = (bias && i < p.Cout) ? bias[i] : 0.f;
+    const bool fast_silu = p.act && !(p.dbg & (1024 | 8192));              // then sbias holds bias / 2 (see the epilogue)
+    for (int i = threadIdx.x; i < p.n_tiles * p.ntile; i += kThreads)
+        sbias[i] = (bias && i < p.Cout) ? (fast_silu ? 0.5f * bias[i] : bias[i]) : 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -381,8 +383,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     roff[j] = byte ^ (((byte >> 7) & (uint32_t)p.swz_out) << 4);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float x[CT];
                 const float4* bs = reinterpret_cast<const float4*>(sbias + c_slab + half * CT);
+                if (fast_silu) {
+                    // SiLU(x) = h + h * tanh(h), h = x / 2: sbias holds bias / 2, so h is one FFMA per output; one
+                    // tanh.approx.f16x2 and one HFMA2 per output pair, and the half2 result is what gets stored -- about
+                    // 3 instructions per output instead of 6.5 (the epilogue warps of the wide 1x1 layers are bound by
+                    // their own dependent instruction chains: 2 warps per scheduler, IPC 1.3 of 4 in ncu).  The two-op
+                    // fp32 form costs 2 MUFU per output: at 16 per clock and SM that alone is the time budget of a
+                    // bandwidth-bound layer (measured +60 % on 192 -> 256 at 64 x 64).  Absolute error <= |x| / 2 * 2^-11,
+                    // the size of the fp16 rounding of the stored output.
+                    // phase by phase over all CT outputs (16 independent chains per phase hide the MUFU latency; a
+                    // per-chunk ordering measured 10 % slower on the two-CTA configuration)
+                    uint32_t hh[CT / 2], th[CT / 2];
+#pragma unroll
+                    for (int j = 0; j < CT / 8; ++j) {
+                        int4 rv = make_int4(0, 0, 0, 0);
+                        if (p.res_mode == 2) rv = *reinterpret_cast<const int4*>(rsrc + roff[j]);
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                        const float4 b0 = bs[2 * j], b1 = bs[2 * j + 1];   // same address in every lane: broadcast
+                        const float hb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t0 = __uint_as_float(v[8 * j + 2 * e]), t1 = __uint_as_float(v[8 * j + 2 * e + 1]);
+                            if (p.res_mode == 2) { const float2 rf = __half22float2(rh[e]); t0 += rf.x; t1 += rf.y; }
+                            const __half2 h2 = __floats2half2_rn(fmaf(t0, 0.5f, hb[2 * e]), fmaf(t1, 0.5f, hb[2 * e + 1]));
+                            hh[4 * j + e] = *reinterpret_cast<const uint32_t*>(&h2);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < CT / 2; ++i) asm("tanh.approx.f16x2 %0, %1;" : "=r"(th[i]) : "r"(hh[i]));
+#pragma unroll
+                    for (int i = 0; i < CT / 2; ++i) {
+                        const __half2 h2 = *reinterpret_cast<const __half2*>(&hh[i]);
+                        const __half2 y = __hfma2(h2, *reinterpret_cast<const __half2*>(&th[i]), h2);
+                        hh[i] = *reinterpret_cast<const uint32_t*>(&y);
+                    }
+#pragma unroll
+                    for (int j = 0; j < CT / 8; ++j) {
+                        int4 o = make_int4((int)hh[4 * j], (int)hh[4 * j + 1], (int)hh[4 * j + 2], (int)hh[4 * j + 3]);
+                        if (p.res_mode == 1) {                             // Bottleneck shortcut: added in fp32, rounded once
+                            const int4 rv = *reinterpret_cast<const int4*>(stg + soff[j]);
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 yf = __half22float2(oh[e]), rf = __half22float2(rh[e]);
+                                oh[e] = __floats2half2_rn(yf.x + rf.x, yf.y + rf.y);
+                            }
+                        }
+                        if (!(p.dbg & 2)) *reinterpret_cast<int4*>(stg + soff[j]) = o;
+                    }
+                } else {
+                float x[CT];
 #pragma unroll
                 for (int i = 0; i < CT / 4; ++i) {
                     const float4 b4 = bs[i];                               // same address in every lane: broadcast
@@ -401,20 +453,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         }
                     }
                 }
-                if (p.act && (p.dbg & 1024)) {
-#pragma unroll
-                    for (int i = 0; i < CT; ++i) {                         // SiLU: x * 1/(1 + 2^(-x log2 e)), 32 independent chains
-                        float e;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x[i] * -1.4426950408889634f));
-                        float rcp;
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(1.f + e));
-                        x[i] *= rcp;
-                    }
-                } else if (p.act) {
-                    // SiLU = h + h * tanh(h), h = x / 2, two outputs per special-function op (tanh.approx.f16x2): the
-                    // two-op fp32 form above costs 2 MUFU per output, and at 16 per clock and SM that alone is the
-                    // whole time budget of a bandwidth-bound 1x1 layer (measured: +60 % on 192 -> 256 at 64 x 64).
-                    // Absolute error <= |x| / 2 * 2^-11, the size of the fp16 rounding of the stored output.
+                if (p.act && (p.dbg & 8192)) {                             // A/B: tanh form on the fp32 values, converted back
 #pragma unroll
                     for (int i = 0; i < CT; i += 2) {
                         const __half2 hh = __floats2half2_rn(0.5f * x[i], 0.5f * x[i + 1]);
@@ -422,6 +461,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&hh)));
                         const float2 y = __half22float2(__hfma2(hh, *reinterpret_cast<const __half2*>(&t), hh));
                         x[i] = y.x; x[i + 1] = y.y;
+                    }
+                } else if (p.act) {
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) {                         // SiLU: x * 1/(1 + 2^(-x log2 e)), 32 independent chains
+                        float e;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x[i] * -1.4426950408889634f));
+                        float rcp;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(1.f + e));
+                        x[i] *= rcp;
                     }
                 }
                 if (p.res_mode == 1) {
@@ -446,6 +494,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         *reinterpret_cast<int4*>(stg + soff[j]) = o;
                     }
                 }
+                }                                                          // fast_silu
                 }                                                          // half
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA store reads
                 asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");

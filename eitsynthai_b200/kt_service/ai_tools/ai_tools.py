@@ -25,6 +25,7 @@ from .. import config, kt_service_config
 from ...pipeline import ImagingPipeline, SeriesMeta
 from . import utils
 from .mesh_tools.femm_generator import create_mesh
+from ...ops import u8_to_nchw as ops_u8_to_nchw
 
 logging.basicConfig(level=logging.INFO)
 logger = logging.getLogger(__name__)
@@ -116,16 +117,14 @@ class DICOMabc(abc.ABC):
         return front, px, i_slices, custom
 
     def _ribs_predict(self, front_slice):
-        """ai_tools.py:107-127 -> object with .xyxy / .confidence / .class_id (sv.Detections' fields)."""
-        class _Det:
-            xyxy = np.zeros((0, 4), np.float32); confidence = np.zeros(0, np.float32); class_id = np.zeros(0, int)
-        det = _Det()
+        """ai_tools.py:107-127 -> ``results.Detections`` (the fields of sv.Detections the reference reads)."""
+        from .results import Detections
+        det = Detections.empty()
         try:
             front = torch.from_numpy(np.ascontiguousarray(front_slice)).to(self.device)
             sel, boxes, k = self.pipeline.rib_select(front[None])
             n = int(k[0])
-            det.xyxy = boxes[0, :n].cpu().numpy()
-            det.class_id = np.zeros(n, int)
+            det = Detections(boxes[0, :n].cpu().numpy())
             self._sel = sel[0].cpu().tolist()
         except Exception as e:
             logger.error(f"_ribs_predict failed: {e}")
@@ -156,6 +155,23 @@ class DICOMabc(abc.ABC):
             self._dev_last = (code[0], None)
         out = code[0].cpu().numpy()
         return out, body, int(n[0]), round(time.time() - t1, 3)
+
+    def predict_results(self, axial_slice):
+        """The reference's ``_axial_slice_predict`` return value (ai_tools.py:129-158): ``(results, segmentation_time)``
+        with ``results.masks.data`` / ``results.boxes`` / ``results.orig_shape`` as ``utils.create_segmentations_masks``
+        reads them (``results.Results``).  ``axial_slice``: the normalised, body-masked u8 slice (2-D, or 3 equal
+        channels).  The service itself uses the fused ``_axial_slice_predict`` above; this is the per-function path."""
+        from .results import Boxes, Masks, Results
+        t1 = time.time()
+        img = np.asarray(axial_slice)
+        if img.ndim == 3:
+            img = img[..., 0]
+        u8 = torch.from_numpy(np.ascontiguousarray(img, np.uint8)[None]).to(self.device)
+        x = u8 if self.pipeline.fused_input else ops_u8_to_nchw(u8, self.pipeline.dtype)
+        (dets, masks), = self.pipeline.predict_instances(x)
+        res = Results(img.shape[:2], Boxes(dets[:, :4], dets[:, 4], dets[:, 5]), Masks(masks) if len(dets) else None,
+                      {0: "bone", 1: "muscles", 2: "lung", 3: "adipose"})
+        return res, round(time.time() - t1, 3)
 
     def _finish(self, code, body, pixel_spacing, n_det, seg_time, mesh=None, extra=None):
         """create_answer (utils.py:1019-1058): the reference's seven keys -- ``image`` (base64 PNG; here the colour

@@ -178,6 +178,25 @@ class ImagingPipeline:
         """jpg_png route (ai_tools.py:365-400): [B,S,S] u8, no windowing, no body mask."""
         return self._segment_nchw(gray.contiguous() if self.fused_input else ops.u8_to_nchw(gray, self.dtype), None)
 
+    @torch.no_grad()
+    def predict_instances(self, x: torch.Tensor, drop_empty: bool = True):
+        """What ``model(img, conf=0.3, imgsz=S)[0]`` holds in the reference (ai_tools.py:153), per image: the kept boxes
+        (xyxy, conf, cls) and the per-instance binary masks [n, S, S] u8 -- K5 -> K6 with the per-instance bit masks
+        kept.  ``x``: network input as for ``_segment_nchw``.  Returns a list of (dets [n, 6], masks [n, S, S])."""
+        S = x.shape[-1]
+        model = self.axial_model_256 if S == 256 else self.axial_model_512
+        head, protos = self._net(model, x if x.dtype == torch.uint8 else x.contiguous(memory_format=torch.channels_last))
+        dets, _, n = ops.nms(head.contiguous(), 4, CONF, IOU, MAX_DET, want_idx=False)
+        _, area, bits = ops.mask_decode(dets, n, protos, self.mask_variant, want_area=True, want_bits=True)
+        shifts = torch.arange(8, device=bits.device, dtype=torch.uint8)
+        out = []
+        for b in range(x.shape[0]):
+            k = int(n[b])
+            m = ((bits[b, :k, :, :, None] >> shifts) & 1).reshape(k, bits.shape[2], bits.shape[3] * 8)
+            keep = area[b, :k] > 0 if drop_empty else torch.ones(k, dtype=torch.bool, device=bits.device)
+            out.append((dets[b, :k, :6][keep], m[keep]))
+        return out
+
     def _segment_nchw(self, x: torch.Tensor, body):
         """``x``: the normalised [B,3,S,S] network input, or (fused path) the u8 image [B,S,S] it is made from."""
         S = x.shape[-1]

@@ -320,3 +320,25 @@ def test_fastapi_routes(pipe):
         zf.writestr("vol.nii.gz", N.write_nifti(hu))
     r = c.post("/uploadNII", files={"file": ("n.zip", buf.getvalue(), "application/zip")})
     assert r.status_code == 200 and len(r.json()["mesh_classes"]) > 100
+
+
+def test_results_objects_carry_the_reference_fields_and_rebuild_the_fused_label_image():
+    """``predict_results`` returns what the reference's ``_axial_slice_predict`` returns (ai_tools.py:129-158): an object
+    with ``masks.data`` / ``boxes.cls`` / ``orig_shape``; the per-function path create_segmentations_masks ->
+    create_color_output on it gives the label image of the fused K5 -> K6 -> K7 path, and ``Detections.from_ultralytics``
+    exposes the fields search_number_axial_slice reads."""
+    from eitsynthai_b200.kt_service.ai_tools import ai_tools as A
+    from eitsynthai_b200.kt_service.ai_tools import utils as U
+    from eitsynthai_b200.kt_service.ai_tools.results import Detections
+    from oracle import imaging as OI
+    svc = A.ImageToMask()
+    px = synth.phantom_slice(2)
+    u8 = OI.apply_mask(OI.classic_norm(px), OI.body_mask(px, -1024, 1))
+    res, t = svc.predict_results(u8)
+    assert res.orig_shape == (512, 512) and len(res) == len(res.boxes) > 0
+    assert tuple(res.masks.data.shape) == (len(res), 512, 512) and tuple(res.boxes.data.shape) == (len(res), 6)
+    det = Detections.from_ultralytics(res)
+    assert det.xyxy.shape == (len(res), 4) and det.mask.dtype == bool and det.class_id.dtype.kind == "i"
+    color = U.create_color_output(U.create_segmentations_masks(res))            # per-function path, no body mask
+    code, _, n = svc.pipeline.segment_u8(torch.from_numpy(u8[None]).to(svc.device))
+    assert np.array_equal(color, OI.code_to_bgr(code[0].cpu().numpy()))
