@@ -291,7 +291,16 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # the exchange is 0.3 MB of coronal rows per step: one NCCL CTA moves it, and more would take SMs away from the
+        # persistent one-CTA-per-SM convolution kernels that run concurrently on the main stream
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = 1
+            opts.config.min_ctas = 1
+        except Exception:
+            opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     torch.backends.cudnn.benchmark = True
 
     peaks = {}

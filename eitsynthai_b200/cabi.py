@@ -63,8 +63,8 @@ SIGNATURES = {
     "eitb_conv2d_debug": (_i, [_i]),
     "eitb_stem_conv3x3s2_nhwc": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _p]),
     "eitb_dwconv3x3_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p]),
-    "eitb_tri_label_workspace_bytes": (_sz, [_i]),
-    "eitb_tri_label": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _p, _p, _sz, _p]),
+    "eitb_tri_label_workspace_bytes": (_sz, [_i, _i]),
+    "eitb_tri_label": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "eitb_tri_label_raster": (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _p, _p]),
     "eitb_rle_decode_frame": (_i, [C.c_char_p, _sz, _i, _i, _i, _p]),
     "eitb_jpeg_lossless_decode": (_i, [C.c_char_p, _sz, _p, _p, _p, _p, _sz]),

@@ -7,8 +7,8 @@
 //   area(tri ∩ poly) > best so far (> 0)      -> remember the class          (:179-181)
 //   nothing                                   -> outer class                 (:162)
 //
-// One warp per triangle; lanes stride over polygon edges.  Candidate polygons are found 32 at
-// a time by bounding-box ballot.  The intersection area needs no clipped-polygon storage: by
+// One thread per triangle over y-slab lists of every polygon's edges (see below).  The intersection area needs no
+// clipped-polygon storage: by
 // Green's theorem about the centroid O the boundary of (T ∩ P) splits into
 //   * the pieces of P's edges inside T  (Cyrus-Beck parameter interval [t0,t1] per edge):
 //         (t1 - t0) * cross(u - O, v - O), signed by P's orientation, and
@@ -17,13 +17,18 @@
 //     with wn the signed winding number of P about the edge's end point -- so rings that touch
 //     or retrace themselves (1-px whiskers from findContours) integrate exactly like the
 //     signed area of a clipped ring,
-// all of which are sums over P's edges and reduce with warp shuffles in a fixed order
-// (deterministic results).
+// all of which are sums over P's edges, accumulated in a fixed order (deterministic results).
 #include "common.cuh"
 
 namespace {
 
 constexpr double kAreaNoiseFloor = 1e-9;   // relative to the triangle's area
+// Every polygon's edges are binned by y into kBuckets equal slabs of its bounding box (an edge is listed in every slab
+// its y-span touches, in edge order).  Only edges whose y-span meets the triangle's can contribute to any of the sums
+// -- the crossing tests need an edge that straddles the query point's y, Cyrus-Beck an edge that meets the triangle's
+// box -- so a triangle walks the few slabs it touches instead of the whole ring: the body-sized rings of the reference's
+// polygon sets (5,000 vertices) cost a 1-2 pixel triangle tens of edges, not thousands.
+constexpr int kBuckets = 64;
 
 struct D2 { double x, y; };
 __device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) {
@@ -69,6 +74,46 @@ __global__ void poly_prep_kernel(const double* __restrict__ poly_xy, const int32
     }
 }
 
+__device__ __forceinline__ int y_bucket(double y, double miny, double inv_h) {
+    const double f = __dmul_rn(__dsub_rn(y, miny), inv_h);                // monotone in y: overlapping spans share a bucket
+    return f <= 0.0 ? 0 : f >= (double)(kBuckets - 1) ? kBuckets - 1 : (int)f;
+}
+__device__ __forceinline__ double inv_bucket_height(double miny, double maxy) {
+    return maxy > miny ? __ddiv_rn((double)kBuckets, __dsub_rn(maxy, miny)) : 0.0;
+}
+
+// one CTA of kBuckets threads per polygon; thread b lists, in edge order, the edges whose y-span touches slab b
+// boff [P][kBuckets + 1] offsets relative to the polygon's region, entries: region of polygon p starts at (kBuckets + 2) * poly_off[p]
+__global__ void __launch_bounds__(kBuckets)
+poly_bucket_kernel(const double* __restrict__ poly_xy, const int32_t* __restrict__ poly_off, const double* __restrict__ bbox,
+                   int32_t* __restrict__ boff, int32_t* __restrict__ entries) {
+    __shared__ int cnt[kBuckets + 1];
+    const int p = blockIdx.x, b = threadIdx.x;
+    const int o0 = poly_off[p], o1 = poly_off[p + 1] - 1;
+    const double miny = bbox[p * 4 + 1], inv_h = inv_bucket_height(bbox[p * 4 + 1], bbox[p * 4 + 3]);
+    int n = 0;
+    for (int i = o0; i < o1; ++i) {
+        const double y0 = __ldg(poly_xy + 2 * (size_t)i + 1), y1 = __ldg(poly_xy + 2 * (size_t)i + 3);
+        n += (y_bucket(fmin(y0, y1), miny, inv_h) <= b && b <= y_bucket(fmax(y0, y1), miny, inv_h)) ? 1 : 0;
+    }
+    cnt[b] = n;
+    __syncthreads();
+    if (b == 0) {
+        int acc = 0;
+        for (int k = 0; k < kBuckets; ++k) { const int c = cnt[k]; cnt[k] = acc; acc += c; }
+        cnt[kBuckets] = acc;
+    }
+    __syncthreads();
+    int32_t* bo = boff + (size_t)p * (kBuckets + 1);
+    bo[b] = cnt[b];
+    if (b == 0) bo[kBuckets] = cnt[kBuckets];
+    int32_t* dst = entries + (size_t)(kBuckets + 2) * o0 + cnt[b];
+    for (int i = o0; i < o1; ++i) {
+        const double y0 = __ldg(poly_xy + 2 * (size_t)i + 1), y1 = __ldg(poly_xy + 2 * (size_t)i + 3);
+        if (y_bucket(fmin(y0, y1), miny, inv_h) <= b && b <= y_bucket(fmax(y0, y1), miny, inv_h)) *dst++ = i;
+    }
+}
+
 // crossing-number test of q against edge (u, v), boundary cases left to the half-open rule
 __device__ __forceinline__ int pip_edge(const D2& q, const D2& u, const D2& v) {
     if ((u.y > q.y) != (v.y > q.y)) {
@@ -78,15 +123,31 @@ __device__ __forceinline__ int pip_edge(const D2& q, const D2& u, const D2& v) {
     return 0;
 }
 
-__global__ void __launch_bounds__(256)
+// One THREAD per triangle (round 2; round 1 used a warp per triangle with lanes over the ring's edges).  With the y-slab
+// lists a triangle meets a handful of edges per candidate polygon, so a warp per triangle left 28 lanes idle and spent
+// its time on dependent global loads and shuffle reductions; a thread per triangle keeps 32 independent triangles in
+// flight per warp and sums every integral sequentially in list order (deterministic).  The per-polygon records
+// (bounding box, class, orientation) are staged in shared memory.
+constexpr int kMaxSmemPolys = 1024;
+
+__global__ void __launch_bounds__(128)
 tri_label_kernel(const double* __restrict__ nodes, const int64_t* __restrict__ tri, long long T,
                  const double* __restrict__ poly_xy, const int32_t* __restrict__ poly_off,
                  const int32_t* __restrict__ poly_cls, int P, int outer_cls, const double* __restrict__ bbox,
-                 const double* __restrict__ orient, int32_t* __restrict__ cls_out) {
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long t = warp0; t < T; t += nwarps) {
+                 const double* __restrict__ orient, const int32_t* __restrict__ boff, const int32_t* __restrict__ entries,
+                 int32_t* __restrict__ cls_out) {
+    extern __shared__ __align__(16) unsigned char k8sm[];
+    double* sbox = reinterpret_cast<double*>(k8sm);                      // [Ps][4]
+    double* sori = sbox + (size_t)min(P, kMaxSmemPolys) * 4;             // [Ps]
+    int* scls = reinterpret_cast<int*>(sori + min(P, kMaxSmemPolys));    // [Ps]
+    int* soff = scls + min(P, kMaxSmemPolys);                            // [Ps]
+    const int Ps = min(P, kMaxSmemPolys);
+    for (int i = threadIdx.x; i < Ps; i += blockDim.x) {
+        sbox[i * 4] = bbox[i * 4]; sbox[i * 4 + 1] = bbox[i * 4 + 1]; sbox[i * 4 + 2] = bbox[i * 4 + 2]; sbox[i * 4 + 3] = bbox[i * 4 + 3];
+        sori[i] = orient[i]; scls[i] = poly_cls[i]; soff[i] = poly_off[i];
+    }
+    __syncthreads();
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (long long)gridDim.x * blockDim.x) {
         D2 a = ld_pt(nodes, tri[t * 3]), b = ld_pt(nodes, tri[t * 3 + 1]), c = ld_pt(nodes, tri[t * 3 + 2]);
         double area2 = cross2(__dsub_rn(b.x, a.x), __dsub_rn(b.y, a.y), __dsub_rn(c.x, a.x), __dsub_rn(c.y, a.y));
         if (area2 < 0.0) { const D2 tmp = b; b = c; c = tmp; area2 = -area2; }       // make T ccw
@@ -98,91 +159,95 @@ tri_label_kernel(const double* __restrict__ nodes, const int64_t* __restrict__ t
 
         int best = outer_cls;
         double max_inter = 0.0;
-        bool done = false;
-        for (int p0 = 0; p0 < P && !done; p0 += 32) {
-            const int pl = p0 + lane;
-            bool cand = false, cin = false;
-            if (pl < P && poly_cls[pl] != outer_cls) {
-                const double bx0 = bbox[pl * 4], by0 = bbox[pl * 4 + 1], bx1 = bbox[pl * 4 + 2], by1 = bbox[pl * 4 + 3];
-                cin = O.x >= bx0 && O.x <= bx1 && O.y >= by0 && O.y <= by1;
-                cand = cin || (tri_area > 0.0 && tmaxx >= bx0 && tminx <= bx1 && tmaxy >= by0 && tminy <= by1);
+        for (int p = 0; p < P; ++p) {
+            const bool sm = p < Ps;
+            const int pc = sm ? scls[p] : poly_cls[p];
+            if (pc == outer_cls) continue;
+            const double bx0 = sm ? sbox[p * 4] : bbox[p * 4], by0 = sm ? sbox[p * 4 + 1] : bbox[p * 4 + 1];
+            const double bx1 = sm ? sbox[p * 4 + 2] : bbox[p * 4 + 2], by1 = sm ? sbox[p * 4 + 3] : bbox[p * 4 + 3];
+            const bool cin = O.x >= bx0 && O.x <= bx1 && O.y >= by0 && O.y <= by1;
+            const bool cand = cin || (tri_area > 0.0 && tmaxx >= bx0 && tminx <= bx1 && tmaxy >= by0 && tminy <= by1);
+            if (!cand) continue;
+            const int o0 = sm ? soff[p] : poly_off[p];
+            const double inv_h = inv_bucket_height(by0, by1);
+            const int32_t* bo = boff + (size_t)p * (kBuckets + 1);
+            const int32_t* ent = entries + (size_t)(kBuckets + 2) * o0;
+            // ---- pass 1: centroid strictly inside?  (only edges whose y-span holds O.y can cross its ray)
+            if (cin) {
+                int par = 0;
+                const int bq = y_bucket(O.y, by0, inv_h);
+                for (int k = bo[bq]; k < bo[bq + 1]; ++k) {
+                    const int i = ent[k];
+                    par ^= pip_edge(O, ld_pt(poly_xy, i), ld_pt(poly_xy, i + 1));
+                }
+                if (par) { best = pc; break; }
             }
-            unsigned m = __ballot_sync(0xffffffffu, cand);
-            const unsigned mc = __ballot_sync(0xffffffffu, cin);
-            while (m && !done) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                const int p = p0 + l;
-                const int o0 = poly_off[p], o1 = poly_off[p + 1] - 1;       // edges i -> i+1, i in [o0, o1)
-                const int pc = poly_cls[p];
-                // ---- pass 1: centroid strictly inside?
-                if ((mc >> l) & 1u) {
-                    int par = 0;
-                    for (int i = o0 + lane; i < o1; i += 32) par ^= pip_edge(O, ld_pt(poly_xy, i), ld_pt(poly_xy, i + 1));
-                    if (__popc(__ballot_sync(0xffffffffu, par)) & 1) { best = pc; done = true; break; }
-                }
-                if (!(tri_area > 0.0)) continue;
-                // ---- pass 2: intersection area
-                double sum_p = 0.0;            // pieces of P's edges inside T
-                double len[3] = {0.0, 0.0, 0.0};
-                int wn[3] = {0, 0, 0};         // signed winding number of P about b_e (ccw positive)
-                for (int i = o0 + lane; i < o1; i += 32) {
-                    const D2 u = ld_pt(poly_xy, i), v = ld_pt(poly_xy, i + 1);
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        const D2 q = tv[(e + 1) % 3];
-                        if (pip_edge(q, u, v)) wn[e] += v.y > q.y ? 1 : -1;
-                    }
-                    if (fmax(u.x, v.x) < tminx || fmin(u.x, v.x) > tmaxx || fmax(u.y, v.y) < tminy || fmin(u.y, v.y) > tmaxy)
-                        continue;
-                    const double wx = __dsub_rn(v.x, u.x), wy = __dsub_rn(v.y, u.y);
-                    double t0 = 0.0, t1 = 1.0;
-                    bool rej = false;
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        const D2 ea = tv[e], eb = tv[(e + 1) % 3];
-                        const double dx = __dsub_rn(eb.x, ea.x), dy = __dsub_rn(eb.y, ea.y);
-                        const double su = cross2(dx, dy, __dsub_rn(u.x, ea.x), __dsub_rn(u.y, ea.y));   // side of u
-                        const double sv = cross2(dx, dy, __dsub_rn(v.x, ea.x), __dsub_rn(v.y, ea.y));   // side of v
-                        const double dn = cross2(dx, dy, wx, wy);
-                        // Cyrus-Beck against the half-plane left of ea->eb
-                        if (dn == 0.0) {
-                            if (su < 0.0) rej = true;
-                        } else {
-                            const double ts = __ddiv_rn(-su, dn);
-                            if (dn > 0.0) t0 = fmax(t0, ts); else t1 = fmin(t1, ts);
-                        }
-                        // crossing of the T edge with this P edge (half-open on P's parameter)
-                        if ((su > 0.0) != (sv > 0.0)) {
-                            const double s = __ddiv_rn(cross2(__dsub_rn(u.x, ea.x), __dsub_rn(u.y, ea.y), wx, wy), dn);
-                            if (s >= 0.0 && s <= 1.0) {
-                                // moving along ea->eb we enter P (ccw) when cross(w, d) > 0, i.e. dn < 0
-                                len[e] = dn < 0.0 ? __dsub_rn(len[e], s) : __dadd_rn(len[e], s);
-                            }
-                        }
-                    }
-                    if (!rej && t0 < t1)
-                        sum_p = __dadd_rn(sum_p, __dmul_rn(__dsub_rn(t1, t0),
-                                                          cross2(__dsub_rn(u.x, O.x), __dsub_rn(u.y, O.y),
-                                                                 __dsub_rn(v.x, O.x), __dsub_rn(v.y, O.y))));
-                }
-                double total = warp_sum_d(sum_p);
+            if (!(tri_area > 0.0)) continue;
+            // ---- pass 2: intersection area
+            double sum_p = 0.0;            // pieces of P's edges inside T
+            double len[3] = {0.0, 0.0, 0.0};
+            int wn[3] = {0, 0, 0};         // signed winding number of P about b_e (ccw positive)
+            const int bb0 = y_bucket(tminy, by0, inv_h), bb1 = y_bucket(tmaxy, by0, inv_h);
+            for (int bk = bb0; bk <= bb1; ++bk)
+            for (int k = bo[bk]; k < bo[bk + 1]; ++k) {
+                const int i = ent[k];
+                const D2 u = ld_pt(poly_xy, i), v = ld_pt(poly_xy, i + 1);
+                // an edge listed in several of these slabs is taken in the first one
+                if (bk > bb0 && y_bucket(fmin(u.y, v.y), by0, inv_h) < bk) continue;
 #pragma unroll
                 for (int e = 0; e < 3; ++e) {
-                    const double le = __dadd_rn(warp_sum_d(len[e]), (double)warp_sum(wn[e]));
-                    const D2 ea = tv[e], eb = tv[(e + 1) % 3];
-                    total = __dadd_rn(total, __dmul_rn(le, cross2(__dsub_rn(ea.x, O.x), __dsub_rn(ea.y, O.y),
-                                                                   __dsub_rn(eb.x, O.x), __dsub_rn(eb.y, O.y))));
+                    const D2 q = tv[(e + 1) % 3];
+                    if (pip_edge(q, u, v)) wn[e] += v.y > q.y ? 1 : -1;
                 }
-                double inter = __dmul_rn(__dmul_rn(orient[p], total), 0.5);
-                // lower-dimensional overlaps (zero-width whiskers, touching edges) have area exactly 0
-                // in GEOS; fp64 sums leave ~1e-12 px^2 of noise, which must not win "inter > 0"
-                if (!(inter > __dmul_rn(kAreaNoiseFloor, tri_area))) inter = 0.0;
-                if (__ddiv_rn(inter, tri_area) > 0.5) { best = pc; done = true; break; }
-                if (inter > max_inter) { max_inter = inter; best = pc; }
+                if (fmax(u.x, v.x) < tminx || fmin(u.x, v.x) > tmaxx || fmax(u.y, v.y) < tminy || fmin(u.y, v.y) > tmaxy)
+                    continue;
+                const double wx = __dsub_rn(v.x, u.x), wy = __dsub_rn(v.y, u.y);
+                double t0 = 0.0, t1 = 1.0;
+                bool rej = false;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const D2 ea = tv[e], eb = tv[(e + 1) % 3];
+                    const double dx = __dsub_rn(eb.x, ea.x), dy = __dsub_rn(eb.y, ea.y);
+                    const double su = cross2(dx, dy, __dsub_rn(u.x, ea.x), __dsub_rn(u.y, ea.y));   // side of u
+                    const double sv = cross2(dx, dy, __dsub_rn(v.x, ea.x), __dsub_rn(v.y, ea.y));   // side of v
+                    const double dn = cross2(dx, dy, wx, wy);
+                    // Cyrus-Beck against the half-plane left of ea->eb
+                    if (dn == 0.0) {
+                        if (su < 0.0) rej = true;
+                    } else {
+                        const double ts = __ddiv_rn(-su, dn);
+                        if (dn > 0.0) t0 = fmax(t0, ts); else t1 = fmin(t1, ts);
+                    }
+                    // crossing of the T edge with this P edge (half-open on P's parameter)
+                    if ((su > 0.0) != (sv > 0.0)) {
+                        const double sc = __ddiv_rn(cross2(__dsub_rn(u.x, ea.x), __dsub_rn(u.y, ea.y), wx, wy), dn);
+                        if (sc >= 0.0 && sc <= 1.0) {
+                            // moving along ea->eb we enter P (ccw) when cross(w, d) > 0, i.e. dn < 0
+                            len[e] = dn < 0.0 ? __dsub_rn(len[e], sc) : __dadd_rn(len[e], sc);
+                        }
+                    }
+                }
+                if (!rej && t0 < t1)
+                    sum_p = __dadd_rn(sum_p, __dmul_rn(__dsub_rn(t1, t0),
+                                                      cross2(__dsub_rn(u.x, O.x), __dsub_rn(u.y, O.y),
+                                                             __dsub_rn(v.x, O.x), __dsub_rn(v.y, O.y))));
             }
+            double total = sum_p;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const double le = __dadd_rn(len[e], (double)wn[e]);
+                const D2 ea = tv[e], eb = tv[(e + 1) % 3];
+                total = __dadd_rn(total, __dmul_rn(le, cross2(__dsub_rn(ea.x, O.x), __dsub_rn(ea.y, O.y),
+                                                               __dsub_rn(eb.x, O.x), __dsub_rn(eb.y, O.y))));
+            }
+            double inter = __dmul_rn(__dmul_rn(sm ? sori[p] : orient[p], total), 0.5);
+            // lower-dimensional overlaps (zero-width whiskers, touching edges) have area exactly 0
+            // in GEOS; fp64 sums leave ~1e-12 px^2 of noise, which must not win "inter > 0"
+            if (!(inter > __dmul_rn(kAreaNoiseFloor, tri_area))) inter = 0.0;
+            if (__ddiv_rn(inter, tri_area) > 0.5) { best = pc; break; }
+            if (inter > max_inter) { max_inter = inter; best = pc; }
         }
-        if (lane == 0) cls_out[t] = best;
+        cls_out[t] = best;
     }
 }
 
@@ -204,27 +269,39 @@ tri_label_raster_kernel(const double* __restrict__ nodes, const int64_t* __restr
 
 }  // namespace
 
-extern "C" size_t eitb_tri_label_workspace_bytes(int P) { return (size_t)(P > 0 ? P : 0) * 5 * sizeof(double); }
+// per-polygon bounding boxes and orientation (5 doubles), slab offsets (kBuckets + 1 ints) and the slab lists: an edge is
+// listed at most kBuckets times, so (kBuckets + 2) ints per vertex bound every polygon's region
+extern "C" size_t eitb_tri_label_workspace_bytes(int P, int V) {
+    const size_t p = (size_t)(P > 0 ? P : 0), v = (size_t)(V > 0 ? V : 0);
+    return p * 5 * sizeof(double) + (p * (kBuckets + 1) + v * (kBuckets + 2)) * sizeof(int32_t) + 64;
+}
 
 extern "C" int eitb_tri_label(const double* nodes_xy, int64_t n_nodes, const int64_t* tri, int64_t T,
                               const double* poly_xy, const int32_t* poly_off, const int32_t* poly_cls, int P,
-                              int outer_cls, int32_t* cls_out, void* ws, size_t ws_bytes, eitb_stream_t stream) {
-    if (T < 0 || P < 0 || n_nodes < 0) return EITB_ERR_BAD_ARG;
+                              int V, int outer_cls, int32_t* cls_out, void* ws, size_t ws_bytes, eitb_stream_t stream) {
+    if (T < 0 || P < 0 || n_nodes < 0 || V < 0) return EITB_ERR_BAD_ARG;
     if (T == 0) return EITB_OK;
     if (!nodes_xy || !tri || !cls_out || (P > 0 && (!poly_xy || !poly_off || !poly_cls))) return EITB_ERR_BAD_ARG;
-    if (ws_bytes < eitb_tri_label_workspace_bytes(P) || (P > 0 && !ws)) return EITB_ERR_WORKSPACE;
+    if (ws_bytes < eitb_tri_label_workspace_bytes(P, V) || (P > 0 && !ws)) return EITB_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(nodes_xy) & 15) || (reinterpret_cast<uintptr_t>(poly_xy) & 15)) return EITB_ERR_BAD_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     double* bbox = reinterpret_cast<double*>(ws);
     double* orient = bbox + (size_t)P * 4;
+    int32_t* boff = reinterpret_cast<int32_t*>(orient + P);
+    int32_t* entries = boff + (size_t)P * (kBuckets + 1);
     if (P > 0) {
         eitb_prof_begin("poly_prep_kernel", s);
         poly_prep_kernel<<<eitb_div_up(P, 4), 128, 0, s>>>(poly_xy, poly_off, P, bbox, orient);
         EITB_CHECK_LAUNCH();
+        eitb_prof_begin("poly_bucket_kernel", s);
+        poly_bucket_kernel<<<P, kBuckets, 0, s>>>(poly_xy, poly_off, bbox, boff, entries);
+        EITB_CHECK_LAUNCH();
     }
-    const int grid = eitb_grid(T * 32, 256, 8);
+    const int Ps = P < kMaxSmemPolys ? P : kMaxSmemPolys;
+    const size_t smem = (size_t)Ps * (5 * sizeof(double) + 2 * sizeof(int)) + 16;
+    const int grid = eitb_grid(T, 128, 12);
     eitb_prof_begin("tri_label_kernel", s);
-    tri_label_kernel<<<grid, 256, 0, s>>>(nodes_xy, tri, T, poly_xy, poly_off, poly_cls, P, outer_cls, bbox, orient, cls_out);
+    tri_label_kernel<<<grid, 128, smem, s>>>(nodes_xy, tri, T, poly_xy, poly_off, poly_cls, P, outer_cls, bbox, orient, boff, entries, cls_out);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }

@@ -403,13 +403,13 @@ def tri_label(nodes_xy: torch.Tensor, tri: torch.Tensor, poly_xy: torch.Tensor, 
     _chk(poly_xy, torch.float64, "poly_xy")
     _chk(poly_off, torch.int32, "poly_off")
     _chk(poly_cls, torch.int32, "poly_cls")
-    T, P = tri.shape[0], poly_cls.shape[0]
+    T, P, V = tri.shape[0], poly_cls.shape[0], poly_xy.shape[0]
     out = torch.empty((T,), dtype=torch.int32, device=tri.device)
-    nbytes = cabi.load().eitb_tri_label_workspace_bytes(P)
+    nbytes = cabi.load().eitb_tri_label_workspace_bytes(P, V)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=tri.device)
     with torch.cuda.device(tri.device):
         cabi.call("eitb_tri_label", nodes_xy.data_ptr(), nodes_xy.shape[0], tri.data_ptr(), T, poly_xy.data_ptr(),
-                  poly_off.data_ptr(), poly_cls.data_ptr(), P, outer_cls, out.data_ptr(), ws.data_ptr(), nbytes,
+                  poly_off.data_ptr(), poly_cls.data_ptr(), P, V, outer_cls, out.data_ptr(), ws.data_ptr(), nbytes,
                   _stream(tri))
     return out
 

@@ -285,11 +285,13 @@ int eitb_dwconv3x3_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_co
  *   poly_xy  [V,2] f64 closed rings back to back; poly_off [P+1] int32 vertex offsets;
  *   poly_cls [P] int32; polygons already sorted by ascending area (host mirror does it)
  *   cls_out  [T] int32
- *   ws       eitb_tri_label_workspace_bytes(P) bytes (per-polygon bounding boxes, orientation)
+ *   V        number of polygon vertices (poly_off[P])
+ *   ws       eitb_tri_label_workspace_bytes(P, V) bytes (per-polygon bounding boxes, orientation, and the
+ *            y-slab edge lists that let a triangle visit only the edges near it)
  * nodes_xy and poly_xy must be 16-byte aligned. */
-size_t eitb_tri_label_workspace_bytes(int P);
+size_t eitb_tri_label_workspace_bytes(int P, int V);
 int eitb_tri_label(const double* nodes_xy, int64_t n_nodes, const int64_t* tri, int64_t T,
-                   const double* poly_xy, const int32_t* poly_off, const int32_t* poly_cls, int P,
+                   const double* poly_xy, const int32_t* poly_off, const int32_t* poly_cls, int P, int V,
                    int outer_cls, int32_t* cls_out, void* ws, size_t ws_bytes, eitb_stream_t stream);
 
 /* Raster mode named by the north star: class of the label-map pixel under the centroid

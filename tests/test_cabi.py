@@ -55,7 +55,7 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     from eitsynthai_b200 import cabi
     assert lib.eitb_hu_window_nchw(0, 1, 512, 512, -160, 240, 1, 0, 0, 0, 0, 0, 0) == cabi.ERR_BAD_ARG
     assert lib.eitb_nms(0, 0, 1, 4, 32, 5376, 0.3, 0.7, 300, 7680.0, 0, 0, 0, 0, 0, 0) == cabi.ERR_BAD_ARG
-    assert lib.eitb_tri_label(0, 0, 0, -1, 0, 0, 0, 0, 4, 0, 0, 0, 0) == cabi.ERR_BAD_ARG
+    assert lib.eitb_tri_label(0, 0, 0, -1, 0, 0, 0, 0, 0, 4, 0, 0, 0, 0) == cabi.ERR_BAD_ARG
     assert lib.eitb_mask_decode(0, 0, 300, 0, 0, 0, 1, 32, 128, 128, 512, 512, 0, 0, 0, 0, 0, 0, 0) == cabi.ERR_BAD_ARG
     with pytest.raises(cabi.EitbError):
         cabi.call("eitb_minmax_u8", 0, 10, 0, 0, 0)
