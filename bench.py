@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-mesh", action="store_true", help="skip the configs[4] mesh element classification measurement")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip isolated kernels, latency, teacher heads, strong scaling, config3")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-overlap", action="store_true", help="one graph per chunk on one stream, steps joined one by one "
+                    "(default: K2 / K5-K7 graphs on side streams beside the CNN graphs, host passes two deep)")
     return ap.parse_args()
 
 
@@ -329,19 +331,23 @@ def run_b200(args):
                 v, i = vols[s % distinct], insts[s % distinct]
             vols.append(v); insts.append(i)
         px_host = torch.from_numpy(np.stack(vols)).pin_memory()    # [S, nl, H, W]
-        labels_host = torch.empty((S, z1 - z0, SIZE, SIZE), dtype=torch.uint8).pin_memory()
+        # two label buffers: the host path keeps two passes in flight (submit_host / wait_host)
+        labels_host = [torch.empty((S, z1 - z0, SIZE, SIZE), dtype=torch.uint8).pin_memory() for _ in range(2)]
         total = S * (z1 - z0)
         headline = S == (args.series or world) and nslices == args.slices
         runner = SeriesBatchRunner(pipe, [SeriesMeta(i) for i in insts], nslices, SIZE, min(chunk, total), use_graphs=not args.no_graphs,
-                                   timer=timer, first_chunk=args.first_chunk if headline else 0,
+                                   timer=timer, first_chunk=args.first_chunk if headline else 0, overlap=not args.no_overlap,
                                    chunk_sizes=[int(c) for c in args.chunks.split(",")] if args.chunks and headline else None)
         runner.load(px_host)
         runner.capture()
         return runner, px_host, labels_host
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, finish=None):
+        """``finish`` closes what ``fn`` leaves in flight (side streams, the last host pass); it runs inside the timed region."""
         for _ in range(warmup):
             fn()
+        if finish is not None:
+            finish()
         cabi.profile_enable(profiling["on"])                       # drops what the warm-up recorded
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -354,6 +360,9 @@ def run_b200(args):
         a.record()
         for _ in range(steps):
             out = fn()
+        if finish is not None:
+            last = finish()
+            out = out if last is None else last
         b.record()
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
@@ -374,7 +383,31 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, sel, _ = timed(runner.step_device, args.steps, max(args.warmup, 3))
+    def dev_pass(r):
+        """Device-resident passes back to back; the runner's side streams are joined once, inside the timed region."""
+        return (lambda: r.step_device(join=False)), r.join
+
+    def host_pass(r, ph, lh):
+        """Passes from pinned host memory, two in flight: pass i+1 is submitted before the host waits for pass i, so its
+        host->device copies run under pass i's kernels; every pass still copies its own pixels in and its own label maps
+        and selected-slice table out, and the last pass is waited for inside the timed region."""
+        state = {"pending": None, "k": 0}
+
+        def fn():
+            h = r.submit_host(ph, lh[state["k"] & 1])
+            state["k"] += 1
+            prev, state["pending"] = state["pending"], h
+            return r.wait_host(prev) if prev is not None else None
+
+        def finish():
+            prev, state["pending"] = state["pending"], None
+            out = r.wait_host(prev) if prev is not None else None
+            r.join()
+            return out
+        return fn, finish
+
+    fn_d, fin_d = dev_pass(runner)
+    ms_dev, sel, _ = timed(fn_d, args.steps, max(args.warmup, 3), fin_d)
     clocks = sampler.stop() if rank == 0 else None
     # eager pass with per-stage and per-kernel CUDA events (same work, no graphs)
     profiling["on"] = True
@@ -393,10 +426,14 @@ def run_b200(args):
     value = total_slices / (ms_dev / 1e3)
     e2e = None
     if not args.no_e2e:
-        ms_e2e, _, _ = timed(lambda: runner.step_host(px_host, labels_host), args.steps, max(args.warmup, 3))
+        fn_h, fin_h = host_pass(runner, px_host, labels_host)
+        ms_e2e, _, _ = timed(fn_h, args.steps, max(args.warmup, 3), fin_h)
+        ms_sync, _, _ = timed(lambda: runner.step_host(px_host, labels_host[0]), args.steps, 3)
         h2d = int(px_host.numel() * 2 + runner.rows_dev.numel() * 2)
         e2e = {"value": total_slices / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(labels_host.numel() + S * 16), "h2d_gbs_per_rank": h2d / (ms_e2e / 1e3) / 1e9}
+               "d2h_bytes_per_step": int(labels_host[0].numel() + S * 16), "h2d_gbs_per_rank": h2d / (ms_e2e / 1e3) / 1e9,
+               "passes_in_flight": 2, "one_pass_at_a_time": {"value": total_slices / (ms_sync / 1e3), "ms_per_step": ms_sync},
+               "api": "SeriesBatchRunner.submit_host / wait_host (step_host = both, one pass at a time)"}
 
     # ---------------------------------------------------------------- roofline: every own kernel of the step
     px = SIZE * SIZE
@@ -627,8 +664,10 @@ def run_b200(args):
             del runner
             torch.cuda.empty_cache()
             r1, ph1, lh1 = make_runner(1, nslices, args.chunk)
-            ms1, _, _ = timed(r1.step_device, max(args.steps, 10), 3)
-            ms1h, _, _ = timed(lambda: r1.step_host(ph1, lh1), max(args.steps, 10), 3)
+            fn1, fin1 = dev_pass(r1)
+            ms1, _, _ = timed(fn1, max(args.steps, 10), 3, fin1)
+            fn1, fin1 = host_pass(r1, ph1, lh1)
+            ms1h, _, _ = timed(fn1, max(args.steps, 10), 3, fin1)
             extras["strong_scaling"] = {"workload": config(world, 1, nslices)["workload"], "slices_per_gpu": r1.nl, "ms_per_step": ms1,
                                         "slices_per_sec": nslices / (ms1 / 1e3), "e2e_ms_per_step": ms1h,
                                         "e2e_slices_per_sec": nslices / (ms1h / 1e3)}
@@ -639,8 +678,10 @@ def run_b200(args):
         if world == 8:
             try:
                 r3, ph3, lh3 = make_runner(64, nslices, args.chunk)
-                ms3, _, _ = timed(r3.step_device, 5, 2)
-                ms3h, _, _ = timed(lambda: r3.step_host(ph3, lh3), 5, 2)
+                fn3, fin3 = dev_pass(r3)
+                ms3, _, _ = timed(fn3, 5, 2, fin3)
+                fn3, fin3 = host_pass(r3, ph3, lh3)
+                ms3h, _, _ = timed(fn3, 5, 2, fin3)
                 extras["config3"] = {"workload": config(world, 64, nslices)["workload"], "slices_per_gpu_per_step": 64 * r3.nl,
                                      "ms_per_step": ms3, "slices_per_sec": 64 * nslices / (ms3 / 1e3), "e2e_ms_per_step": ms3h,
                                      "e2e_slices_per_sec": 64 * nslices / (ms3h / 1e3)}

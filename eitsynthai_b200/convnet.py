@@ -297,8 +297,10 @@ class ConvNet:
 
     # ------------------------------------------------------------------ whole network
     @torch.no_grad()
-    def __call__(self, x: torch.Tensor, gray: bool = False):
-        """``gray``: the three channels of ``x`` are equal (K1 / letterbox output) -- lets the stem read one."""
+    def __call__(self, x: torch.Tensor, gray: bool = False, out=None):
+        """``gray``: the three channels of ``x`` are equal (K1 / letterbox output) -- lets the stem read one.
+        ``out`` = (head [B, 4+nc+nm, A] fp16, protos [B, H/4, W/4, nm] fp16 NHWC): buffers the last two kernels write
+        into instead of fresh allocations (hand-over buffers of CUDA graphs that replay on different streams)."""
         p = self.p
         dev = x.device
         if x.dtype == torch.uint8:                                  # the u8 window image [B, H, W]: preprocess fused into the stem
@@ -326,9 +328,9 @@ class ConvNet:
         n4 = self._c3k2(cat19, p["l19"])
         conv(n4, p["l20"], out=cat22.slice(0, 256))
         n5 = self._c3k2(cat22, p["l22"])
-        return self._head((n3, n4, n5))
+        return self._head((n3, n4, n5), out)
 
-    def _head(self, feats):
+    def _head(self, feats, out=None):
         p = self.p
         cv1, ups, cv2, cv3 = p["proto"]
         t = conv(feats[0], cv1)
@@ -337,7 +339,7 @@ class ConvNet:
         for dy in range(2):
             for dx in range(2):
                 conv(t, ups[dy][dx], out=up, up=(2, dy, dx))
-        protos = conv(conv(up, cv2), cv3)
+        protos = conv(conv(up, cv2), cv3, out=Act(out[1]) if out is not None else None)
         box, cls, mc = [], [], []
         for i, f in enumerate(feats):
             b = p["box"][i]
@@ -347,5 +349,6 @@ class ConvNet:
             cls.append(cl.buf.permute(0, 3, 1, 2))                  # padded to 8 channels per pixel
             m = p["mc"][i]
             mc.append(conv(conv(conv(f, m[0]), m[1]), m[2]).nchw())
-        head = ops.yolo_head_decode(box, cls, mc, self.stride, self.nc, self.nm, self.head_bias, cls_cstride=cls[0].shape[1])
+        head = ops.yolo_head_decode(box, cls, mc, self.stride, self.nc, self.nm, self.head_bias, cls_cstride=cls[0].shape[1],
+                                    out=out[0] if out is not None else None)
         return head, protos.nchw()

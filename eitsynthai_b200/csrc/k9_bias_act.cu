@@ -102,7 +102,7 @@ extern "C" int eitb_bias_act_nhwc(void* x, int dtype, long long n_pixels, int C,
 }
 
 // ---------------------------------------------------------------------------------------------
-// General conv epilogue: y = act(src + bias [+ residual]); y goes to `out` (may alias src: in
+// General conv epilogue: y = act(src + bias) [+ residual] (the Bottleneck shortcut is added AFTER the activation); y goes to `out` (may alias src: in
 // place) and/or into a channel slice of a wider channels-last tensor `out2` -- the concat buffer
 // of a C3k2 / C3k block, so that torch.cat and the residual add never run as separate passes.
 namespace {

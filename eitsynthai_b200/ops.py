@@ -61,11 +61,16 @@ def u8_to_nchw(gray: torch.Tensor, dtype: torch.dtype = torch.float16) -> torch.
 
 
 # ------------------------------------------------------------------------------------ K2
-def body_mask(px: torch.Tensor, slope: int = 1, intercept: int = -1024, flipud: bool = True) -> torch.Tensor:
-    """[B,H,W] int16 -> [B,H,W] u8 {0,255}: get_axial_slice_body_mask(_nii)."""
+def body_mask(px: torch.Tensor, slope: int = 1, intercept: int = -1024, flipud: bool = True,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B,H,W] int16 -> [B,H,W] u8 {0,255}: get_axial_slice_body_mask(_nii).  ``out``: write into this buffer."""
     _chk(px, torch.int16, "px")
     B, H, W = px.shape
-    out = torch.empty((B, H, W), dtype=torch.uint8, device=px.device)
+    if out is None:
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=px.device)
+    else:
+        _chk(out, torch.uint8, "out")
+        assert out.shape == px.shape
     lib = cabi.load()
     nbytes = lib.eitb_body_mask_workspace_bytes(B, H, W)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=px.device)
@@ -201,9 +206,10 @@ def scale_boxes(dets: torch.Tensor, n: torch.Tensor, gain: float, pad_x: float, 
 
 # ------------------------------------------------------------------------------------ K6
 def mask_decode(dets: torch.Tensor, n_det: torch.Tensor, protos: torch.Tensor, variant: int = 0,
-                want_area: bool = False, want_bits: bool = False):
+                want_area: bool = False, want_bits: bool = False, code_out: torch.Tensor | None = None):
     """dets/n from ``nms`` + protos [B,nm,mh,mw] -> overlay code image [B,4mh,4mw] u8
-    (+ per-instance areas [B,max_det] i32, + per-instance bit masks [B,max_det,H,W/8] u8)."""
+    (+ per-instance areas [B,max_det] i32, + per-instance bit masks [B,max_det,H,W/8] u8).
+    ``code_out``: write the code image into this buffer."""
     _chk(dets, torch.float32, "dets")
     _chk(n_det, torch.int32, "n_det")
     if not protos.is_cuda:
@@ -218,7 +224,12 @@ def mask_decode(dets: torch.Tensor, n_det: torch.Tensor, protos: torch.Tensor, v
     max_det = dets.shape[1]
     assert dets.shape[2] == 6 + nm and dets.shape[0] == B
     H, W = 4 * mh, 4 * mw
-    code = torch.empty((B, H, W), dtype=torch.uint8, device=dets.device)
+    if code_out is None:
+        code = torch.empty((B, H, W), dtype=torch.uint8, device=dets.device)
+    else:
+        _chk(code_out, torch.uint8, "code_out")
+        assert tuple(code_out.shape) == (B, H, W)
+        code = code_out
     area = torch.empty((B, max_det), dtype=torch.int32, device=dets.device) if want_area else None
     bits = torch.empty((B, max_det, H, W // 8), dtype=torch.uint8, device=dets.device) if want_bits else None
     with torch.cuda.device(dets.device):
@@ -325,7 +336,7 @@ def bias_act_(x: torch.Tensor, bias: torch.Tensor | None, silu: bool = True) -> 
 
 def conv_epilogue(src: torch.Tensor, bias: torch.Tensor | None, silu: bool, residual: torch.Tensor | None = None,
                   inplace: bool = True, out2: torch.Tensor | None = None, out2_off: int = 0):
-    """y = act(src + bias [+ residual]) for a channels-last half tensor; y replaces ``src`` (``inplace``)
+    """y = act(src + bias) [+ residual] (shortcut added after the activation) for a channels-last half tensor; y replaces ``src`` (``inplace``)
     and/or lands in channels [out2_off, out2_off + C) of the channels-last tensor ``out2``."""
     cl = torch.channels_last
     if not src.is_cuda or src.dim() != 4 or not src.is_contiguous(memory_format=cl):
@@ -357,7 +368,8 @@ def upsample2x_concat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------ K10
-def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int, biases=None, cls_cstride: int = 0) -> torch.Tensor:
+def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int, biases=None, cls_cstride: int = 0,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
     """Lists of the 3 per-level branch outputs (channels-last fp16 [B,64|nc|nm,h,w]) -> head [B,4+nc+nm,A].
     ``biases`` = (box, cls, mc) lists of per-level float32 bias vectors folded into the decode."""
     import ctypes as C
@@ -371,7 +383,12 @@ def yolo_head_decode(box, cls, mc, strides, nc: int, nm: int, biases=None, cls_c
     st = (C.c_int * 3)(*strides)
     arr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
     A = sum(t.shape[2] * t.shape[3] for t in box)
-    head = torch.empty((B, 4 + nc + nm, A), dtype=torch.float16, device=box[0].device)
+    if out is None:
+        head = torch.empty((B, 4 + nc + nm, A), dtype=torch.float16, device=box[0].device)
+    else:
+        _chk(out, torch.float16, "out")
+        assert tuple(out.shape) == (B, 4 + nc + nm, A)
+        head = out
     bb = cb = mb = None
     if biases is not None:
         for group in biases:

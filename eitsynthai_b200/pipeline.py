@@ -82,10 +82,17 @@ class ImagingPipeline:
         if calibrate:
             self._calibrate()
 
-    def _net(self, model, x):
+    def _net(self, model, x, out=None):
         """Run a network on a replicated gray image (every input of the service is one): lets the own-kernel
-        engine read a single input channel in the stem."""
-        return model(x, gray=True) if self.fused_input else model(x)
+        engine read a single input channel in the stem.  ``out`` = (head, NHWC prototypes) buffers to write into."""
+        if self.engine == "eitb" and self.dtype == torch.float16:
+            return model(x, gray=True) if out is None else model(x, gray=True, out=out)
+        head, protos = model(x)
+        if out is not None:
+            out[0].copy_(head)
+            out[1].copy_(protos.permute(0, 2, 3, 1))
+            head, protos = out[0], out[1].permute(0, 3, 1, 2)
+        return head, protos
 
     @property
     def fused_input(self) -> bool:
@@ -305,7 +312,7 @@ class SeriesBatchRunner:
     """
 
     def __init__(self, pipe: ImagingPipeline, metas, n_slices: int, size: int = 512, chunk: int = 160,
-                 use_graphs: bool = True, timer=None, first_chunk: int = 0, chunk_sizes=None):
+                 use_graphs: bool = True, timer=None, first_chunk: int = 0, chunk_sizes=None, overlap: bool = True):
         from . import sharded
         self.pipe, self.sharded = pipe, sharded
         self.dev = pipe.device
@@ -349,35 +356,66 @@ class SeriesBatchRunner:
         self.side = torch.cuda.Stream(dev)                      # the per-series decision runs beside the slice chunks
         self.graphs, self.outs, self.rib_graph, self.sel_static = [], [], None, None
         self.use_graphs = use_graphs
+        # Overlapped replay (graphs only): a chunk is three graphs -- K2 on ``pre_s``, K1 + CNN on the caller's stream,
+        # K5/K6/K7 on ``post_s`` -- so the latency-bound label kernels of chunk c (a handful of busy warps per image)
+        # run in the tails and launch gaps of chunk c+1's persistent convolution kernels instead of after them, also
+        # across steps.  Buffers are guarded by events (previous reader -> next writer), never by stream joins.
+        self.overlap = bool(overlap and use_graphs)
+        self.pre_s, self.post_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.pre_graphs, self.cnn_graphs, self.post_graphs = [], [], []
+        nch = len(self.bounds)
+        self.ev_cnn, self.ev_post, self.ev_d2h = [None] * nch, [None] * nch, [None] * nch
+        self._sel_ring = [torch.empty((self.S, 4), dtype=torch.int32).pin_memory() for _ in range(4)] if torch.cuda.is_available() else []
+        self._submitted = 0
 
     # ---------------------------------------------------------------- stages
     @torch.no_grad()
-    def slice_stage(self, px_chunk, a: int = 0, b: int | None = None):
-        """K2 .. K7 for the slices [a, b) of the flattened [S * n_local] batch."""
-        t, pipe = self.timer, self.pipe
-        with t("K2_body_mask"):
+    def pre_stage(self, px_chunk, a: int = 0, b: int | None = None, out=None):
+        """K2 for the slices [a, b) of the flattened [S * n_local] batch.  ``out`` (here and in the next two stages): the
+        hand-over buffers the stage writes its results into."""
+        with self.timer("K2_body_mask"):
             if self.uniform_rescale:
-                body = ops.body_mask(px_chunk, self.rescale[0][0], self.rescale[0][1], True)
+                body = ops.body_mask(px_chunk, self.rescale[0][0], self.rescale[0][1], True, out=out)
             else:                                               # per-series RescaleSlope / RescaleIntercept
-                body = torch.empty(px_chunk.shape, dtype=torch.uint8, device=self.dev)
+                body = torch.empty(px_chunk.shape, dtype=torch.uint8, device=self.dev) if out is None else out
                 b = a + px_chunk.shape[0] if b is None else b
                 s0 = a // self.nl
                 while s0 * self.nl < b:
                     lo, hi = max(a, s0 * self.nl) - a, min(b, (s0 + 1) * self.nl) - a
                     body[lo:hi] = ops.body_mask(px_chunk[lo:hi], self.rescale[s0][0], self.rescale[s0][1], True)
                     s0 += 1
+        return body
+
+    @torch.no_grad()
+    def cnn_stage(self, px_chunk, body, out=None):
+        """K1 + the axial network."""
+        t, pipe = self.timer, self.pipe
         with t("K1_hu_window_nchw"):
             x = pipe.window_input(px_chunk, body)
         with t("CNN_axial"):
-            head, protos = pipe._net(pipe.axial_model_256 if self.size == 256 else pipe.axial_model_512, x)
+            head, protos = pipe._net(pipe.axial_model_256 if self.size == 256 else pipe.axial_model_512, x, out=out)
             head = head.contiguous()
+        return head, protos
+
+    @torch.no_grad()
+    def post_stage(self, head, protos, body, out=None):
+        """K5 -> K6 -> K7."""
+        t, pipe = self.timer, self.pipe
         with t("K5_nms"):
             dets, _, n = ops.nms(head, 4, CONF, IOU, MAX_DET, want_idx=False)
+            if out is not None:
+                n = out[1].copy_(n)
         with t("K6_mask_decode"):
-            code, _, _ = ops.mask_decode(dets, n, protos, pipe.mask_variant)
+            code, _, _ = ops.mask_decode(dets, n, protos, pipe.mask_variant, code_out=None if out is None else out[0])
         with t("K7_label_cleanup"):
             ops.label_cleanup(code, body)
         return code, n
+
+    def slice_stage(self, px_chunk, a: int = 0, b: int | None = None):
+        """K2 .. K7 for the slices [a, b) of the flattened [S * n_local] batch."""
+        body = self.pre_stage(px_chunk, a, b)
+        head, protos = self.cnn_stage(px_chunk, body)
+        return self.post_stage(head, protos, body)
 
     def rib_rows(self, px, row0: bool = False):
         """One launch for the whole batch: the coronal row of every local slice of every series + per-series
@@ -432,23 +470,61 @@ class SeriesBatchRunner:
         return sel
 
     def capture(self, warm: int = 2):
-        """cuDNN autotune / lazy loading eagerly, then one CUDA graph per chunk and one for the rib decision."""
+        """cuDNN autotune / lazy loading eagerly, then the CUDA graphs of every chunk and one for the rib decision."""
         for _ in range(warm):
             self.step_eager()
         torch.cuda.synchronize(self.dev)
         if not self.use_graphs:
             return
-        pool = torch.cuda.graph_pool_handle()
-        for a, b in self.bounds:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                o = self.slice_stage(self.flat[a:b], a, b)
-            self.graphs.append(g)
-            self.outs.append(o)
+        if self.overlap:
+            # Hand-over buffers (body mask, head, prototypes, label image, counts) live OUTSIDE the graph pools: inside a
+            # shared pool the outputs of chunk 1's graph may sit where chunk 0's graph keeps its intermediates, which is
+            # only safe while nothing reads them beside a later replay of chunk 0 -- exactly what the overlap does.
+            hand = []
+            with torch.no_grad():
+                for a, b in self.bounds:
+                    body = self.pre_stage(self.flat[a:b], a, b)
+                    head, protos = self.cnn_stage(self.flat[a:b], body)
+                    code, n = self.post_stage(head, protos, body)
+                    hand.append(dict(body=torch.empty_like(body), head=torch.empty_like(head),
+                                     protos=torch.empty((protos.shape[0], protos.shape[2], protos.shape[3], protos.shape[1]),
+                                                        dtype=protos.dtype, device=self.dev),      # NHWC
+                                     code=torch.empty_like(code), n=torch.empty_like(n)))
+                    del body, head, protos, code, n
+            torch.cuda.synchronize(self.dev)
+            # three memory pools: graphs of one kind replay in order on one stream, graphs of different kinds side by side
+            pools = [torch.cuda.graph_pool_handle() for _ in range(3)]
+            for ci, (a, b) in enumerate(self.bounds):
+                h = hand[ci]
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pools[0]):
+                    self.pre_stage(self.flat[a:b], a, b, out=h["body"])
+                self.pre_graphs.append(g)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pools[1]):
+                    head, protos = self.cnn_stage(self.flat[a:b], h["body"], out=(h["head"], h["protos"]))
+                assert head.data_ptr() == h["head"].data_ptr() and protos.data_ptr() == h["protos"].data_ptr()
+                self.cnn_graphs.append(g)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pools[2]):
+                    code, n = self.post_stage(h["head"], h["protos"].permute(0, 3, 1, 2), h["body"], out=(h["code"], h["n"]))
+                assert code.data_ptr() == h["code"].data_ptr()
+                self.post_graphs.append(g)
+                self.outs.append((h["code"], h["n"]))
+            self._static = hand
+        else:
+            pool = torch.cuda.graph_pool_handle()
+            for a, b in self.bounds:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    o = self.slice_stage(self.flat[a:b], a, b)
+                self.graphs.append(g)
+                self.outs.append(o)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):                                 # own memory pool: it replays beside the chunk graphs
             self.sel_static = self.rib_decide(self.rows_static, self.mm_static)
         self.rib_graph = g
+        torch.cuda.synchronize(self.dev)
 
     def run_chunk(self, ci):
         if self.graphs:
@@ -457,31 +533,82 @@ class SeriesBatchRunner:
         a, b = self.bounds[ci]
         return self.slice_stage(self.flat[a:b], a, b)
 
-    def _rib_on_side(self, px, row0=False):
+    def _event(self, stream):
+        e = torch.cuda.Event()
+        e.record(stream)
+        return e
+
+    def _chunk_overlapped(self, ci, main, ready=None):
+        """pre (K2) -> cnn (K1 + network) -> post (K5, K6, K7) of chunk ``ci`` on three streams.  Waits: the chunk's pixels
+        (``ready``), and whoever still reads a buffer this replay overwrites -- the previous step's post graph reads body /
+        head / prototypes, its device->host copy reads the label image."""
+        with torch.cuda.stream(self.pre_s):
+            if ready is not None:
+                self.pre_s.wait_event(ready)
+            if self.ev_post[ci] is not None:
+                self.pre_s.wait_event(self.ev_post[ci])
+            self.pre_graphs[ci].replay()
+            ev_pre = self._event(self.pre_s)
+        main.wait_event(ev_pre)
+        if self.ev_post[ci] is not None:
+            main.wait_event(self.ev_post[ci])
+        self.cnn_graphs[ci].replay()
+        self.ev_cnn[ci] = self._event(main)
+        with torch.cuda.stream(self.post_s):
+            self.post_s.wait_event(self.ev_cnn[ci])
+            if self.ev_d2h[ci] is not None:
+                self.post_s.wait_event(self.ev_d2h[ci])
+            self.post_graphs[ci].replay()
+            self.ev_post[ci] = self._event(self.post_s)
+        return self.outs[ci]
+
+    def join(self):
+        """Make the caller's stream wait for everything the runner has in flight on its own streams."""
+        main = torch.cuda.current_stream(self.dev)
+        for st in (self.pre_s, self.post_s, self.copy_out, self.side):
+            main.wait_stream(st)
+
+    def _rib_on_side(self, px, row0=False, after=None):
         """The coronal decision is independent of the per-slice path and tiny (one image per series): run it
         on a side stream so its ~300 small launches hide under the chunk graphs."""
         main = torch.cuda.current_stream(self.dev)
-        self.side.wait_stream(main)
+        if after is None:
+            self.side.wait_stream(main)
+        else:
+            self.side.wait_event(after)                           # host path: the coronal rows have landed
         with torch.cuda.stream(self.side):
             sel = self.rib_stage(px, graphed=True, row0=row0)
         sel.record_stream(main)
         return sel
 
-    def step_device(self):
+    def step_device(self, join: bool = True):
+        """One pass over the resident batch (``load`` is its only writer and synchronises).  ``join=False`` leaves the
+        label kernels of the last chunk running beside the next step's first chunk; call ``join()`` before reading
+        ``outs``."""
         main = torch.cuda.current_stream(self.dev)
         sel = self._rib_on_side(self.px)
         for ci in range(len(self.chunks)):
-            self.run_chunk(ci)
+            if self.overlap:
+                self._chunk_overlapped(ci, main)
+            else:
+                self.run_chunk(ci)
         main.wait_stream(self.side)
+        if join and self.overlap:
+            self.join()
         return sel
 
-    def step_host(self, px_host: torch.Tensor, labels_host: torch.Tensor):
-        """px_host [S, n_local, H, W] int16 pinned, labels_host [S, n_local, H, W] u8 pinned (file order).
-        Returns the selected-slice table [S, 4] on the host (the one synchronisation of the step)."""
+    def submit_host(self, px_host: torch.Tensor, labels_host: torch.Tensor):
+        """Enqueue one pass from pinned host memory and return a handle for ``wait_host``; nothing blocks the host, so
+        a caller that keeps two passes in flight (two ``labels_host`` buffers) overlaps the copies of one pass with
+        the kernels of the other.  px_host [S, n_local, H, W] int16 pinned, labels_host [S, n_local, H, W] u8 pinned
+        (file order)."""
         main = torch.cuda.current_stream(self.dev)
         flat_host = px_host.view(self.S * self.nl, self.size, self.size)
         flat_out = labels_host.view(self.S * self.nl, self.size, self.size)
-        self.copy_in.wait_stream(main)
+        if self.overlap:
+            self.copy_in.wait_stream(self.side)                   # the previous pass's rib stage has read rows_dev
+        else:
+            self.copy_in.wait_stream(main)
         evs = []
         with torch.cuda.stream(self.copy_in):
             # strided DMA of the coronal rows straight from the pinned series: no CPU gather, no staging buffer
@@ -490,24 +617,50 @@ class SeriesBatchRunner:
             else:
                 for s_ in range(self.S):
                     ops.rows_h2d(px_host[s_], self.rows_of[s_], self.rows_dev[s_].view(self.nl, self.size))
-            ev_rows = torch.cuda.Event()
-            ev_rows.record(self.copy_in)
-            for a, b in self.bounds:
+            ev_rows = self._event(self.copy_in)
+            for ci, (a, b) in enumerate(self.bounds):
+                if self.overlap and self.ev_cnn[ci] is not None:
+                    self.copy_in.wait_event(self.ev_cnn[ci])      # K2 / K1 of the previous pass have read these pixels
                 self.flat[a:b].copy_(flat_host[a:b], non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(self.copy_in)
-                evs.append(e)
-        main.wait_event(ev_rows)
-        sel = self._rib_on_side(self.rows_dev, row0=True)
+                evs.append(self._event(self.copy_in))
+        if self.overlap:
+            sel = self._rib_on_side(self.rows_dev, row0=True, after=ev_rows)
+        else:
+            main.wait_event(ev_rows)
+            sel = self._rib_on_side(self.rows_dev, row0=True)
         for ci, (a, b) in enumerate(self.bounds):
-            main.wait_event(evs[ci])
-            code, _ = self.run_chunk(ci)
-            e = torch.cuda.Event()
-            e.record(main)
-            self.copy_out.wait_event(e)
+            if self.overlap:
+                code, _ = self._chunk_overlapped(ci, main, evs[ci])
+                self.copy_out.wait_event(self.ev_post[ci])
+            else:
+                main.wait_event(evs[ci])
+                code, _ = self.run_chunk(ci)
+                self.copy_out.wait_event(self._event(main))
             with torch.cuda.stream(self.copy_out):
                 flat_out[a:b].copy_(code, non_blocking=True)
+                self.ev_d2h[ci] = self._event(self.copy_out)
             code.record_stream(self.copy_out)
-        main.wait_stream(self.copy_out)
-        main.wait_stream(self.side)
-        return sel.cpu()
+        # the selected-slice table travels last on the copy-out stream: its event closes the pass
+        sel_host = self._sel_ring[self._submitted % len(self._sel_ring)]
+        self._submitted += 1
+        self.copy_out.wait_stream(self.side)
+        with torch.cuda.stream(self.copy_out):
+            sel_host.copy_(sel, non_blocking=True)
+            done = self._event(self.copy_out)
+        sel.record_stream(self.copy_out)
+        if not self.overlap:
+            main.wait_stream(self.copy_out)
+            main.wait_stream(self.side)
+        return sel_host, done
+
+    @staticmethod
+    def wait_host(handle):
+        """Block until the pass behind ``handle`` has delivered its label maps; returns the selected-slice table [S, 4]."""
+        sel_host, done = handle
+        done.synchronize()
+        return sel_host.clone()
+
+    def step_host(self, px_host: torch.Tensor, labels_host: torch.Tensor):
+        """One pass from pinned host memory, synchronously: returns the selected-slice table [S, 4] on the host once
+        the label maps are in ``labels_host``."""
+        return self.wait_host(self.submit_host(px_host, labels_host))

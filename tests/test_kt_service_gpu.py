@@ -201,6 +201,63 @@ def test_series_batch_runner_graphs_match_eager(pipe):
     assert torch.equal(sel_ref.cpu(), sel_dev)
 
 
+def test_series_batch_runner_overlapped_passes(pipe):
+    """The overlapped replay (K2 / K5-K7 graphs on side streams, passes joined only by buffer events) and the two-deep host
+    path deliver, pass after pass, exactly what the single-stream runner delivers -- also when the pixels change between
+    passes (a stale or early read of a hand-over buffer would show up as another pass's labels)."""
+    from eitsynthai_b200.pipeline import SeriesBatchRunner, SeriesMeta
+    base = synth.phantom_series(48, seed=31)[0]
+    # shifted copies: the body outline (hence the label image) must differ between the passes
+    vols = [base, np.roll(base, 37, axis=2).copy(), np.roll(base, -53, axis=1).copy()]
+    inst = synth.phantom_series(48, seed=31)[1]
+    plain = SeriesBatchRunner(pipe, [SeriesMeta(inst)], 48, 512, chunk=16, overlap=False)
+    fast = SeriesBatchRunner(pipe, [SeriesMeta(inst)], 48, 512, chunk=16, overlap=True)
+    assert fast.overlap and not plain.overlap
+    hosts = [torch.from_numpy(v[None]).pin_memory() for v in vols]
+
+    def input_sensitive(r):
+        """The random-init network's label image barely depends on its input, which would hide a stale hand-over buffer:
+        flip the sign of every prototype of a slice by two probe pixels of that slice (inside the captured graphs)."""
+        plain_stage = r.cnn_stage
+
+        def stage(px_chunk, body, out=None):
+            head, protos = plain_stage(px_chunk, body, out=out)
+            flip = (px_chunk[:, 256, 110] > 900) ^ (px_chunk[:, 256, 256] > 900)
+            protos.mul_(torch.where(flip, 1.0, -1.0).to(protos.dtype)[:, None, None, None])
+            return head, protos
+        r.cnn_stage = stage
+    for r in (plain, fast):
+        input_sensitive(r)
+        r.load(hosts[0])
+        r.capture(warm=1)
+    want, want_sel = [], []
+    for h in hosts:
+        out = torch.zeros((1, 48, 512, 512), dtype=torch.uint8).pin_memory()
+        want_sel.append(plain.step_host(h, out))
+        want.append(out)
+    assert not torch.equal(want[0], want[1]) and not torch.equal(want[0], want[2])
+    # device-resident passes without a join in between, then one join
+    fast.load(hosts[0])
+    for _ in range(3):
+        sel = fast.step_device(join=False)
+    fast.join()
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([o[0] for o in fast.outs]).cpu(), want[0][0])
+    assert torch.equal(sel.cpu(), want_sel[0])
+    # host passes, two in flight, different pixels every pass, two rounds over the three series
+    outs = [torch.zeros((1, 48, 512, 512), dtype=torch.uint8).pin_memory() for _ in range(6)]
+    handles = []
+    for k in range(6):
+        handles.append(fast.submit_host(hosts[k % 3], outs[k]))
+        if k >= 1:
+            got_sel = fast.wait_host(handles[k - 1])
+            assert torch.equal(got_sel, want_sel[(k - 1) % 3])
+            assert torch.equal(outs[k - 1], want[(k - 1) % 3]), f"pass {k - 1}"
+    assert torch.equal(fast.wait_host(handles[5]), want_sel[2]) and torch.equal(outs[5], want[2])
+    fast.join()
+    torch.cuda.synchronize()
+
+
 def test_zip_of_dicom_files_end_to_end(pipe):
     """Real wire format: a zip of (uncompressed) DICOM files through the reference-named entry points."""
     from eitsynthai_b200.kt_service.ai_tools import ai_tools as A
