@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunk", type=int, default=160, help="slices per CNN batch / CUDA graph")
+    ap.add_argument("--chunk", type=int, default=320, help="slices per CNN batch / CUDA graph")
     ap.add_argument("--first-chunk", type=int, default=0, help="size of a smaller first chunk (0: all chunks equal)")
     ap.add_argument("--chunks", default="", help="explicit comma-separated chunk sizes (must add up to the local slice count)")
     ap.add_argument("--slices", type=int, default=N_SLICES)
@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-mesh", action="store_true", help="skip the configs[4] mesh element classification measurement")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip isolated kernels, latency, teacher heads, strong scaling, config3")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--label-fan", type=int, default=1, help="parallel graph branches of the K2 / K5-K7 chains per chunk")
     ap.add_argument("--no-overlap", action="store_true", help="one graph per chunk on one stream, steps joined one by one "
                     "(default: K2 / K5-K7 graphs on side streams beside the CNN graphs, host passes two deep)")
     return ap.parse_args()
@@ -336,7 +337,7 @@ def run_b200(args):
         total = S * (z1 - z0)
         headline = S == (args.series or world) and nslices == args.slices
         runner = SeriesBatchRunner(pipe, [SeriesMeta(i) for i in insts], nslices, SIZE, min(chunk, total), use_graphs=not args.no_graphs,
-                                   timer=timer, first_chunk=args.first_chunk if headline else 0, overlap=not args.no_overlap,
+                                   timer=timer, first_chunk=args.first_chunk if headline else 0, overlap=not args.no_overlap, label_fan=args.label_fan,
                                    chunk_sizes=[int(c) for c in args.chunks.split(",")] if args.chunks and headline else None)
         runner.load(px_host)
         runner.capture()
@@ -380,6 +381,7 @@ def run_b200(args):
     nslices = args.slices
     runner, px_host, labels_host = make_runner(S, nslices, args.chunk)
     nl = runner.nl
+    runner_overlap = bool(runner.overlap)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -700,7 +702,8 @@ def run_b200(args):
                 "scaling": "strong" if (args.series and args.series < world) else "weak",
                 "vs_baseline": None, "dtype": "f16 (CNN, fp32 accumulate) / int16,u8,f32,f64 (kernels)", "data": "synthetic",
                 "config": dict(config(world, S, nslices), chunk=args.chunk, engine=args.engine, class_bias_shift=pipe.bias_shift,
-                               mean_detections_per_slice=ndet_mean, cuda_graphs=not args.no_graphs),
+                               mean_detections_per_slice=ndet_mean, cuda_graphs=not args.no_graphs,
+                               overlap=runner_overlap, label_fan=args.label_fan),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roof, "cpu_baseline": cpu,
                 "roofline_kernels": kroof, "conv_work_per_step": {k: v for k, v in conv_stats.items() if k != "by_kind"},
                 "eager_profiled_ms_per_step": ms_eager,

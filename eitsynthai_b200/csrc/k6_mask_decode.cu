@@ -61,7 +61,7 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
     extern __shared__ __align__(16) float smem[];
     float* P = smem;                         // [nm][HP]
     float* Ls = P + nm * HP;                 // [G][HP]
-    float* sc = Ls + G * HP;                 // [G][nm]
+    float* sc = Ls + G * HP;                 // [nm][G]: the G coefficients of one prototype channel are two 16-byte words
     float* sbox = sc + G * nm;               // [G][4]  crop box in prototype pixels
     int* sinfo = reinterpret_cast<int*>(sbox + G * 4);   // [G][2]  code, instance index
     int* act = sinfo + G * 2;                // [max_det]
@@ -134,7 +134,7 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
         const int ng = min(G, nact - c0);
         for (int i = tid; i < ng * nm; i += kThreads) {
             const int g = i / nm, k = i - g * nm;
-            sc[g * nm + k] = dimg[(long long)act[c0 + g] * D + 6 + k];
+            sc[k * G + g] = dimg[(long long)act[c0 + g] * D + 6 + k];
         }
         if (tid < ng) {
             const float* d = dimg + (long long)act[c0 + tid] * D;
@@ -149,10 +149,15 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
             float acc[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) acc[g] = 0.f;
+            // per channel: one prototype value + two broadcast 16-byte coefficient loads feed 8 FMAs (coefficients of
+            // slots >= ng are stale, their sums are never used)
+            const float4* sc4 = reinterpret_cast<const float4*>(sc);
+#pragma unroll 4
             for (int k = 0; k < nm; ++k) {
                 const float p = P[k * HP + h];
-#pragma unroll
-                for (int g = 0; g < G; ++g) acc[g] = fmaf(sc[g * nm + k], p, acc[g]);
+                const float4 c0 = sc4[2 * k], c1 = sc4[2 * k + 1];
+                acc[0] = fmaf(c0.x, p, acc[0]); acc[1] = fmaf(c0.y, p, acc[1]); acc[2] = fmaf(c0.z, p, acc[2]); acc[3] = fmaf(c0.w, p, acc[3]);
+                acc[4] = fmaf(c1.x, p, acc[4]); acc[5] = fmaf(c1.y, p, acc[5]); acc[6] = fmaf(c1.z, p, acc[6]); acc[7] = fmaf(c1.w, p, acc[7]);
             }
             const int hy = h / HT, hx = h - hy * HT;
             const float fy = (float)min(max(ty * PT - 1 + hy, 0), mh - 1);

@@ -32,19 +32,30 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------ K1
 def hu_window(px: torch.Tensor, lo: int = -160, hi: int = 240, rot180: bool = True,
               body_mask: torch.Tensor | None = None, want_u8: bool = True,
-              nchw_dtype: torch.dtype | None = torch.float16, channels_last: bool = False):
+              nchw_dtype: torch.dtype | None = torch.float16, channels_last: bool = False,
+              u8_out: torch.Tensor | None = None, nchw_out: torch.Tensor | None = None):
     """[B,H,W] int16 -> (u8 [B,H,W] or None, NCHW [B,3,H,W] or None).  classic_norm + mask + /255.
-    ``channels_last`` returns the same logical tensor in torch.channels_last memory format."""
+    ``channels_last`` returns the same logical tensor in torch.channels_last memory format; ``u8_out`` / ``nchw_out``:
+    buffers to write into instead of fresh allocations."""
     _chk(px, torch.int16, "px")
     B, H, W = px.shape
     if body_mask is not None:
         _chk(body_mask, torch.uint8, "body_mask")
         assert body_mask.shape == px.shape
-    u8 = torch.empty((B, H, W), dtype=torch.uint8, device=px.device) if want_u8 else None
+    u8 = None
+    if want_u8:
+        u8 = torch.empty((B, H, W), dtype=torch.uint8, device=px.device) if u8_out is None else u8_out
+        _chk(u8, torch.uint8, "u8_out")
+        assert u8.shape == px.shape
     nchw = None
     if nchw_dtype is not None:
-        nchw = torch.empty((B, 3, H, W), dtype=nchw_dtype, device=px.device,
-                           memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        if nchw_out is None:
+            nchw = torch.empty((B, 3, H, W), dtype=nchw_dtype, device=px.device,
+                               memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        else:
+            nchw = nchw_out
+            assert nchw.dtype == nchw_dtype and tuple(nchw.shape) == (B, 3, H, W) and nchw.is_cuda
+            assert nchw.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     with torch.cuda.device(px.device):
         cabi.call("eitb_hu_window_nchw", px.data_ptr(), B, H, W, lo, hi, int(rot180), _ptr(body_mask),
                   _ptr(u8), _ptr(nchw), _DT.get(nchw_dtype, cabi.F32), int(channels_last), _stream(px))

@@ -100,12 +100,14 @@ class ImagingPipeline:
         preprocess itself, so the normalised [B,3,H,W] tensor is never written."""
         return self.engine == "eitb" and self.dtype == torch.float16
 
-    def window_input(self, px, body, rot180: bool = True):
-        """K1 for the axial networks: the u8 window image on the fused path, the normalised NCHW tensor otherwise."""
+    def window_input(self, px, body, rot180: bool = True, out=None):
+        """K1 for the axial networks: the u8 window image on the fused path, the normalised NCHW tensor otherwise
+        (written into ``out`` when given)."""
         if self.fused_input:
-            u8, _ = ops.hu_window(px, body_mask=body, want_u8=True, nchw_dtype=None, rot180=rot180)
+            u8, _ = ops.hu_window(px, body_mask=body, want_u8=True, nchw_dtype=None, rot180=rot180, u8_out=out)
             return u8
-        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype, rot180=rot180, channels_last=True)
+        _, x = ops.hu_window(px, body_mask=body, want_u8=False, nchw_dtype=self.dtype, rot180=rot180, channels_last=True,
+                             nchw_out=out)
         return x
 
     def _bind_engine(self):
@@ -312,7 +314,7 @@ class SeriesBatchRunner:
     """
 
     def __init__(self, pipe: ImagingPipeline, metas, n_slices: int, size: int = 512, chunk: int = 160,
-                 use_graphs: bool = True, timer=None, first_chunk: int = 0, chunk_sizes=None, overlap: bool = True):
+                 use_graphs: bool = True, timer=None, first_chunk: int = 0, chunk_sizes=None, overlap: bool = True, label_fan: int = 1):
         from . import sharded
         self.pipe, self.sharded = pipe, sharded
         self.dev = pipe.device
@@ -354,7 +356,7 @@ class SeriesBatchRunner:
         self.rows_dev = torch.empty((self.S, self.nl, 1, size), dtype=torch.int16, device=dev)
         self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.side = torch.cuda.Stream(dev)                      # the per-series decision runs beside the slice chunks
-        self.graphs, self.outs, self.rib_graph, self.sel_static = [], [], None, None
+        self.graphs, self._outs, self.rib_graph, self.sel_static = [], [], None, None
         self.use_graphs = use_graphs
         # Overlapped replay (graphs only): a chunk is three graphs -- K2 on ``pre_s``, K1 + CNN on the caller's stream,
         # K5/K6/K7 on ``post_s`` -- so the latency-bound label kernels of chunk c (a handful of busy warps per image)
@@ -362,37 +364,71 @@ class SeriesBatchRunner:
         # across steps.  Buffers are guarded by events (previous reader -> next writer), never by stream joins.
         self.overlap = bool(overlap and use_graphs)
         self.pre_s, self.post_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self.pre_graphs, self.cnn_graphs, self.post_graphs = [], [], []
+        # K2 and K7 are chains of latency-bound kernels (one CTA per image, a few busy warps): inside their graphs a chunk is
+        # cut into ``label_fan`` groups of images whose chains run on parallel branches, so that several stages are
+        # resident at once (and the instruction-bound K6 of one group runs beside the K7 of another)
+        self.label_fan = max(1, int(label_fan)) if self.overlap else 1
+        self.fan_s = [torch.cuda.Stream(dev) for _ in range(self.label_fan - 1)]
+        # two sets of hand-over buffers and graphs, used by alternate passes: the K2 / K1 graph of pass k+1 does not have
+        # to wait for the label kernels of pass k (which still read pass k's body mask), so with one chunk per pass the
+        # three stages of consecutive passes still run side by side
+        self.n_sets = 2 if self.overlap else 1
+        self.pre_graphs, self.cnn_graphs, self.post_graphs = [[], []], [[], []], [[], []]
         nch = len(self.bounds)
-        self.ev_cnn, self.ev_post, self.ev_d2h = [None] * nch, [None] * nch, [None] * nch
+        self.ev_px = [None] * nch                                 # K2 / K1 have read the chunk's pixels (guards the next copy-in)
+        self.ev_post = [[None] * nch for _ in range(2)]           # per set: the label kernels have read body / head / prototypes
+        self.ev_d2h = [[None] * nch for _ in range(2)]            # per set: the copy-out has read the label image
+        self._passes, self._last_set = 0, 0
         self._sel_ring = [torch.empty((self.S, 4), dtype=torch.int32).pin_memory() for _ in range(4)] if torch.cuda.is_available() else []
         self._submitted = 0
 
     # ---------------------------------------------------------------- stages
+    def _fan(self, n: int, fn, enabled: bool):
+        """``fn(lo, hi)`` over ``label_fan`` contiguous groups of ``n`` images, group 0 on the current stream and the others
+        on the fan streams (forked from and joined to it, so a stream capture records parallel branches)."""
+        k = min(self.label_fan, n) if enabled else 1
+        if k <= 1:
+            fn(0, n)
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        edges = [n * i // k for i in range(k + 1)]
+        for i in range(1, k):
+            st = self.fan_s[i - 1]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                fn(edges[i], edges[i + 1])
+        fn(edges[0], edges[1])
+        for i in range(1, k):
+            cur.wait_stream(self.fan_s[i - 1])
+
     @torch.no_grad()
     def pre_stage(self, px_chunk, a: int = 0, b: int | None = None, out=None):
-        """K2 for the slices [a, b) of the flattened [S * n_local] batch.  ``out`` (here and in the next two stages): the
-        hand-over buffers the stage writes its results into."""
+        """K2 + K1 for the slices [a, b) of the flattened [S * n_local] batch: (body mask, network input) -- the two stages
+        that read the pixels.  ``out`` (here and in the next two stages): the hand-over buffers to write the results into."""
         with self.timer("K2_body_mask"):
-            if self.uniform_rescale:
-                body = ops.body_mask(px_chunk, self.rescale[0][0], self.rescale[0][1], True, out=out)
+            if self.uniform_rescale and out is not None:
+                body = out[0]
+                self._fan(px_chunk.shape[0], lambda lo, hi: ops.body_mask(px_chunk[lo:hi], self.rescale[0][0], self.rescale[0][1],
+                                                                           True, out=body[lo:hi]), True)
+            elif self.uniform_rescale:
+                body = ops.body_mask(px_chunk, self.rescale[0][0], self.rescale[0][1], True)
             else:                                               # per-series RescaleSlope / RescaleIntercept
-                body = torch.empty(px_chunk.shape, dtype=torch.uint8, device=self.dev) if out is None else out
+                body = torch.empty(px_chunk.shape, dtype=torch.uint8, device=self.dev) if out is None else out[0]
                 b = a + px_chunk.shape[0] if b is None else b
                 s0 = a // self.nl
                 while s0 * self.nl < b:
                     lo, hi = max(a, s0 * self.nl) - a, min(b, (s0 + 1) * self.nl) - a
                     body[lo:hi] = ops.body_mask(px_chunk[lo:hi], self.rescale[s0][0], self.rescale[s0][1], True)
                     s0 += 1
-        return body
+        with self.timer("K1_hu_window_nchw"):
+            x = self.pipe.window_input(px_chunk, body, out=None if out is None else out[1])
+        return body, x
 
     @torch.no_grad()
-    def cnn_stage(self, px_chunk, body, out=None):
-        """K1 + the axial network."""
-        t, pipe = self.timer, self.pipe
-        with t("K1_hu_window_nchw"):
-            x = pipe.window_input(px_chunk, body)
-        with t("CNN_axial"):
+    def cnn_stage(self, x, out=None):
+        """The axial network on K1's output."""
+        pipe = self.pipe
+        with self.timer("CNN_axial"):
             head, protos = pipe._net(pipe.axial_model_256 if self.size == 256 else pipe.axial_model_512, x, out=out)
             head = head.contiguous()
         return head, protos
@@ -401,20 +437,27 @@ class SeriesBatchRunner:
     def post_stage(self, head, protos, body, out=None):
         """K5 -> K6 -> K7."""
         t, pipe = self.timer, self.pipe
+        if out is not None:                                       # graph capture: groups of images on parallel branches
+
+            def group(lo, hi):
+                dets, _, n = ops.nms(head[lo:hi], 4, CONF, IOU, MAX_DET, want_idx=False)
+                out[1][lo:hi].copy_(n)
+                ops.mask_decode(dets, n, protos[lo:hi], pipe.mask_variant, code_out=out[0][lo:hi])
+                ops.label_cleanup(out[0][lo:hi], body[lo:hi])
+            self._fan(head.shape[0], group, True)
+            return out[0], out[1]
         with t("K5_nms"):
             dets, _, n = ops.nms(head, 4, CONF, IOU, MAX_DET, want_idx=False)
-            if out is not None:
-                n = out[1].copy_(n)
         with t("K6_mask_decode"):
-            code, _, _ = ops.mask_decode(dets, n, protos, pipe.mask_variant, code_out=None if out is None else out[0])
+            code, _, _ = ops.mask_decode(dets, n, protos, pipe.mask_variant)
         with t("K7_label_cleanup"):
             ops.label_cleanup(code, body)
         return code, n
 
     def slice_stage(self, px_chunk, a: int = 0, b: int | None = None):
         """K2 .. K7 for the slices [a, b) of the flattened [S * n_local] batch."""
-        body = self.pre_stage(px_chunk, a, b)
-        head, protos = self.cnn_stage(px_chunk, body)
+        body, x = self.pre_stage(px_chunk, a, b)
+        head, protos = self.cnn_stage(x)
         return self.post_stage(head, protos, body)
 
     def rib_rows(self, px, row0: bool = False):
@@ -480,37 +523,42 @@ class SeriesBatchRunner:
             # Hand-over buffers (body mask, head, prototypes, label image, counts) live OUTSIDE the graph pools: inside a
             # shared pool the outputs of chunk 1's graph may sit where chunk 0's graph keeps its intermediates, which is
             # only safe while nothing reads them beside a later replay of chunk 0 -- exactly what the overlap does.
-            hand = []
+            shapes = []
             with torch.no_grad():
                 for a, b in self.bounds:
-                    body = self.pre_stage(self.flat[a:b], a, b)
-                    head, protos = self.cnn_stage(self.flat[a:b], body)
+                    body, x = self.pre_stage(self.flat[a:b], a, b)
+                    head, protos = self.cnn_stage(x)
                     code, n = self.post_stage(head, protos, body)
-                    hand.append(dict(body=torch.empty_like(body), head=torch.empty_like(head),
-                                     protos=torch.empty((protos.shape[0], protos.shape[2], protos.shape[3], protos.shape[1]),
-                                                        dtype=protos.dtype, device=self.dev),      # NHWC
-                                     code=torch.empty_like(code), n=torch.empty_like(n)))
-                    del body, head, protos, code, n
+                    shapes.append((body, x, head, protos, code, n))
+            hand = [[dict(body=torch.empty_like(body), x=torch.empty_like(x), head=torch.empty_like(head),
+                          protos=torch.empty((protos.shape[0], protos.shape[2], protos.shape[3], protos.shape[1]),
+                                             dtype=protos.dtype, device=self.dev),      # NHWC
+                          code=torch.empty_like(code), n=torch.empty_like(n))
+                     for body, x, head, protos, code, n in shapes] for _ in range(self.n_sets)]
+            del shapes, body, x, head, protos, code, n
             torch.cuda.synchronize(self.dev)
             # three memory pools: graphs of one kind replay in order on one stream, graphs of different kinds side by side
             pools = [torch.cuda.graph_pool_handle() for _ in range(3)]
-            for ci, (a, b) in enumerate(self.bounds):
-                h = hand[ci]
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pools[0]):
-                    self.pre_stage(self.flat[a:b], a, b, out=h["body"])
-                self.pre_graphs.append(g)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pools[1]):
-                    head, protos = self.cnn_stage(self.flat[a:b], h["body"], out=(h["head"], h["protos"]))
-                assert head.data_ptr() == h["head"].data_ptr() and protos.data_ptr() == h["protos"].data_ptr()
-                self.cnn_graphs.append(g)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pools[2]):
-                    code, n = self.post_stage(h["head"], h["protos"].permute(0, 3, 1, 2), h["body"], out=(h["code"], h["n"]))
-                assert code.data_ptr() == h["code"].data_ptr()
-                self.post_graphs.append(g)
-                self.outs.append((h["code"], h["n"]))
+            self._outs = [[], []]
+            for st in range(self.n_sets):
+                for ci, (a, b) in enumerate(self.bounds):
+                    h = hand[st][ci]
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pools[0]):
+                        _, x = self.pre_stage(self.flat[a:b], a, b, out=(h["body"], h["x"]))
+                    assert x.data_ptr() == h["x"].data_ptr()
+                    self.pre_graphs[st].append(g)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pools[1]):
+                        head, protos = self.cnn_stage(h["x"], out=(h["head"], h["protos"]))
+                    assert head.data_ptr() == h["head"].data_ptr() and protos.data_ptr() == h["protos"].data_ptr()
+                    self.cnn_graphs[st].append(g)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pools[2]):
+                        code, n = self.post_stage(h["head"], h["protos"].permute(0, 3, 1, 2), h["body"], out=(h["code"], h["n"]))
+                    assert code.data_ptr() == h["code"].data_ptr()
+                    self.post_graphs[st].append(g)
+                    self._outs[st].append((h["code"], h["n"]))
             self._static = hand
         else:
             pool = torch.cuda.graph_pool_handle()
@@ -519,17 +567,22 @@ class SeriesBatchRunner:
                 with torch.cuda.graph(g, pool=pool):
                     o = self.slice_stage(self.flat[a:b], a, b)
                 self.graphs.append(g)
-                self.outs.append(o)
+                self._outs.append(o)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):                                 # own memory pool: it replays beside the chunk graphs
             self.sel_static = self.rib_decide(self.rows_static, self.mm_static)
         self.rib_graph = g
         torch.cuda.synchronize(self.dev)
 
+    @property
+    def outs(self):
+        """(label image, detection count) of every chunk of the latest pass (after ``join()`` in overlapped mode)."""
+        return self._outs[self._last_set] if self.overlap and self._outs else self._outs
+
     def run_chunk(self, ci):
         if self.graphs:
             self.graphs[ci].replay()
-            return self.outs[ci]
+            return self._outs[ci]
         a, b = self.bounds[ci]
         return self.slice_stage(self.flat[a:b], a, b)
 
@@ -538,29 +591,33 @@ class SeriesBatchRunner:
         e.record(stream)
         return e
 
-    def _chunk_overlapped(self, ci, main, ready=None):
-        """pre (K2) -> cnn (K1 + network) -> post (K5, K6, K7) of chunk ``ci`` on three streams.  Waits: the chunk's pixels
-        (``ready``), and whoever still reads a buffer this replay overwrites -- the previous step's post graph reads body /
-        head / prototypes, its device->host copy reads the label image."""
+    def _begin_pass(self):
+        self._last_set = self._passes % self.n_sets
+        self._passes += 1
+        return self._last_set
+
+    def _chunk_overlapped(self, st, ci, main, ready=None):
+        """pre (K2, K1) -> cnn (network) -> post (K5, K6, K7) of chunk ``ci`` with buffer set ``st`` on three streams.
+        Waits: the chunk's pixels (``ready``), and whoever still reads a buffer this replay overwrites -- the post graph of
+        the pass that last used the set reads body / head / prototypes, its device->host copy reads the label image."""
         with torch.cuda.stream(self.pre_s):
             if ready is not None:
                 self.pre_s.wait_event(ready)
-            if self.ev_post[ci] is not None:
-                self.pre_s.wait_event(self.ev_post[ci])
-            self.pre_graphs[ci].replay()
+            if self.ev_post[st][ci] is not None:
+                self.pre_s.wait_event(self.ev_post[st][ci])
+            self.pre_graphs[st][ci].replay()
             ev_pre = self._event(self.pre_s)
+        self.ev_px[ci] = ev_pre
         main.wait_event(ev_pre)
-        if self.ev_post[ci] is not None:
-            main.wait_event(self.ev_post[ci])
-        self.cnn_graphs[ci].replay()
-        self.ev_cnn[ci] = self._event(main)
+        self.cnn_graphs[st][ci].replay()
+        ev_cnn = self._event(main)
         with torch.cuda.stream(self.post_s):
-            self.post_s.wait_event(self.ev_cnn[ci])
-            if self.ev_d2h[ci] is not None:
-                self.post_s.wait_event(self.ev_d2h[ci])
-            self.post_graphs[ci].replay()
-            self.ev_post[ci] = self._event(self.post_s)
-        return self.outs[ci]
+            self.post_s.wait_event(ev_cnn)
+            if self.ev_d2h[st][ci] is not None:
+                self.post_s.wait_event(self.ev_d2h[st][ci])
+            self.post_graphs[st][ci].replay()
+            self.ev_post[st][ci] = self._event(self.post_s)
+        return self._outs[st][ci]
 
     def join(self):
         """Make the caller's stream wait for everything the runner has in flight on its own streams."""
@@ -568,14 +625,15 @@ class SeriesBatchRunner:
         for st in (self.pre_s, self.post_s, self.copy_out, self.side):
             main.wait_stream(st)
 
-    def _rib_on_side(self, px, row0=False, after=None):
+    def _rib_on_side(self, px, row0=False, after=None, free_running=False):
         """The coronal decision is independent of the per-slice path and tiny (one image per series): run it
-        on a side stream so its ~300 small launches hide under the chunk graphs."""
+        on a side stream so its ~300 small launches hide under the chunk graphs.  ``free_running``: the side stream
+        neither waits for the caller's stream nor is waited for (resident pixels; the caller joins later)."""
         main = torch.cuda.current_stream(self.dev)
-        if after is None:
-            self.side.wait_stream(main)
-        else:
+        if after is not None:
             self.side.wait_event(after)                           # host path: the coronal rows have landed
+        elif not free_running:
+            self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             sel = self.rib_stage(px, graphed=True, row0=row0)
         sel.record_stream(main)
@@ -583,16 +641,19 @@ class SeriesBatchRunner:
 
     def step_device(self, join: bool = True):
         """One pass over the resident batch (``load`` is its only writer and synchronises).  ``join=False`` leaves the
-        label kernels of the last chunk running beside the next step's first chunk; call ``join()`` before reading
-        ``outs``."""
+        per-series decision and the label kernels of the last chunk running beside the next pass; call ``join()``
+        before reading ``outs`` or the returned table."""
         main = torch.cuda.current_stream(self.dev)
-        sel = self._rib_on_side(self.px)
+        free = self.overlap and not join
+        sel = self._rib_on_side(self.px, free_running=free)
+        st = self._begin_pass()
         for ci in range(len(self.chunks)):
             if self.overlap:
-                self._chunk_overlapped(ci, main)
+                self._chunk_overlapped(st, ci, main)
             else:
                 self.run_chunk(ci)
-        main.wait_stream(self.side)
+        if not free:
+            main.wait_stream(self.side)
         if join and self.overlap:
             self.join()
         return sel
@@ -619,8 +680,8 @@ class SeriesBatchRunner:
                     ops.rows_h2d(px_host[s_], self.rows_of[s_], self.rows_dev[s_].view(self.nl, self.size))
             ev_rows = self._event(self.copy_in)
             for ci, (a, b) in enumerate(self.bounds):
-                if self.overlap and self.ev_cnn[ci] is not None:
-                    self.copy_in.wait_event(self.ev_cnn[ci])      # K2 / K1 of the previous pass have read these pixels
+                if self.overlap and self.ev_px[ci] is not None:
+                    self.copy_in.wait_event(self.ev_px[ci])       # K2 / K1 of the previous pass have read these pixels
                 self.flat[a:b].copy_(flat_host[a:b], non_blocking=True)
                 evs.append(self._event(self.copy_in))
         if self.overlap:
@@ -628,17 +689,18 @@ class SeriesBatchRunner:
         else:
             main.wait_event(ev_rows)
             sel = self._rib_on_side(self.rows_dev, row0=True)
+        st = self._begin_pass()
         for ci, (a, b) in enumerate(self.bounds):
             if self.overlap:
-                code, _ = self._chunk_overlapped(ci, main, evs[ci])
-                self.copy_out.wait_event(self.ev_post[ci])
+                code, _ = self._chunk_overlapped(st, ci, main, evs[ci])
+                self.copy_out.wait_event(self.ev_post[st][ci])
             else:
                 main.wait_event(evs[ci])
                 code, _ = self.run_chunk(ci)
                 self.copy_out.wait_event(self._event(main))
             with torch.cuda.stream(self.copy_out):
                 flat_out[a:b].copy_(code, non_blocking=True)
-                self.ev_d2h[ci] = self._event(self.copy_out)
+                self.ev_d2h[st][ci] = self._event(self.copy_out)
             code.record_stream(self.copy_out)
         # the selected-slice table travels last on the copy-out stream: its event closes the pass
         sel_host = self._sel_ring[self._submitted % len(self._sel_ring)]

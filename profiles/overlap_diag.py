@@ -17,9 +17,9 @@ plain = SeriesBatchRunner(pipe, [SeriesMeta(inst)], N, 512, chunk=CH, overlap=Fa
 fast = SeriesBatchRunner(pipe, [SeriesMeta(inst)], N, 512, chunk=CH, overlap=True)
 def input_sensitive(r):
     plain_stage = r.cnn_stage
-    def stage(px_chunk, body, out=None):
-        head, protos = plain_stage(px_chunk, body, out=out)
-        flip = (px_chunk[:, 256, 110] > 900) ^ (px_chunk[:, 256, 256] > 900)
+    def stage(x, out=None):
+        head, protos = plain_stage(x, out=out)
+        flip = (x.reshape(x.shape[0], -1)[:, ::997].sum(1, dtype=torch.int64) & 1) == 1   # parity of a strided checksum
         protos.mul_(torch.where(flip, 1.0, -1.0).to(protos.dtype)[:, None, None, None])
         return head, protos
     r.cnn_stage = stage
