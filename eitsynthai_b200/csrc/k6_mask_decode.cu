@@ -13,7 +13,13 @@
 // thread interpolates its own 16 output pixels (fixed weights .125/.375/.625/.875) and ORs the
 // class code into registers.  Per-instance fp32 masks never exist in HBM: traffic is the
 // prototype read + one u8 code per pixel.
+//
+// MMA = true (fp16 NHWC prototypes with 32 channels, what the network emits): the halo tile is staged as fp16 rows
+// (straight 16-byte copies) and the logits of a chunk are one warp-level tensor-core contraction per 16 halo pixels
+// (mma.sync m16n8k16, fp32 accumulate; coefficients split into fp16 hi + lo so fp32 coefficients lose nothing) instead
+// of 8 x 32 scalar FMAs per pixel; the crop / upsample / threshold / overlay part is the same code.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -23,6 +29,16 @@ constexpr int HP = HT * HT;     // 324
 constexpr int G = 8;            // instances per chunk
 constexpr int kThreads = 256;
 constexpr int kMaxDet = 1024;
+constexpr int kNm = 32;                      // MMA path: prototype channels
+constexpr int kKS = 40;                      // MMA path: halfs per staged row (32 + 8 of padding: conflict-free fragment loads)
+constexpr int kMTiles = (HP + 15) / 16;      // 21 tiles of 16 halo pixels
+constexpr int kMRows = kMTiles * 16;         // 336 staged rows (the last 12 are zero)
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
 template <typename T> __device__ __forceinline__ float ld_f32(const T* p);
 template <> __device__ __forceinline__ float ld_f32<float>(const float* p) { return __ldg(p); }
@@ -52,16 +68,17 @@ __device__ __forceinline__ float4 eitb_crop_box(const float* d, float rx, float 
     return b;
 }
 
-template <typename T>
+template <typename T, bool MMA>
 __global__ void __launch_bounds__(kThreads)
 mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n_det, int max_det,
                    const T* __restrict__ protos, int proto_nhwc, int nm, int mh, int mw, int H, int W, int tiles_x,
                    int tiles_per_img, int variant, uint8_t* __restrict__ code, int32_t* __restrict__ inst_area,
                    uint8_t* __restrict__ inst_bits) {
     extern __shared__ __align__(16) float smem[];
-    float* P = smem;                         // [nm][HP]
-    float* Ls = P + nm * HP;                 // [G][HP]
+    float* P = smem;                         // [nm][HP] fp32                       | MMA: [kMRows][kKS] fp16
+    float* Ls = MMA ? smem + kMRows * kKS / 2 : P + nm * HP;                 // [G][HP]
     float* sc = Ls + G * HP;                 // [nm][G]: the G coefficients of one prototype channel are two 16-byte words
+                                             // MMA: [2][G][nm] fp16 (hi, lo), the same number of bytes
     float* sbox = sc + G * nm;               // [G][4]  crop box in prototype pixels
     int* sinfo = reinterpret_cast<int*>(sbox + G * 4);   // [G][2]  code, instance index
     int* act = sinfo + G * 2;                // [max_det]
@@ -82,7 +99,20 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
     // ---- stage the prototype tile (halo replicated at the frame)
     {
         const T* pimg = protos + (long long)b * nm * mh * mw;
-        if (proto_nhwc) {                                  // [mh][mw][nm]: the nm values of a pixel are contiguous
+        if (MMA) {                                         // a pixel's 32 halfs = four 16-byte words, copied as they are
+            __half* P16 = reinterpret_cast<__half*>(P);
+            for (int idx = tid; idx < kMRows * 4; idx += kThreads) {
+                const int h = idx >> 2, q = idx & 3;
+                int4 v = make_int4(0, 0, 0, 0);
+                if (h < HP) {
+                    const int hy = h / HT, hx = h - hy * HT;
+                    const int py = min(max(ty * PT - 1 + hy, 0), mh - 1);
+                    const int px = min(max(tx * PT - 1 + hx, 0), mw - 1);
+                    v = __ldg(reinterpret_cast<const int4*>(pimg + ((long long)py * mw + px) * kNm) + q);
+                }
+                *reinterpret_cast<int4*>(P16 + h * kKS + q * 8) = v;
+            }
+        } else if (proto_nhwc) {                                  // [mh][mw][nm]: the nm values of a pixel are contiguous
             for (int idx = tid; idx < nm * HP; idx += kThreads) {
                 const int h = idx / nm, k = idx - h * nm;
                 const int hy = h / HT, hx = h - hy * HT;
@@ -132,9 +162,20 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
 
     for (int c0 = 0; c0 < nact; c0 += G) {
         const int ng = min(G, nact - c0);
+        if (MMA) {
+            __half* sch = reinterpret_cast<__half*>(sc);   // [G][nm] hi, then [G][nm] lo; unused slots are zero
+            for (int i = tid; i < G * kNm; i += kThreads) {
+                const int g = i >> 5, k = i & 31;
+                const float c = g < ng ? dimg[(long long)act[c0 + g] * D + 6 + k] : 0.f;
+                const __half hi = __float2half_rn(c);
+                sch[i] = hi;
+                sch[G * kNm + i] = __float2half_rn(c - __half2float(hi));
+            }
+        } else {
         for (int i = tid; i < ng * nm; i += kThreads) {
             const int g = i / nm, k = i - g * nm;
             sc[k * G + g] = dimg[(long long)act[c0 + g] * D + 6 + k];
+        }
         }
         if (tid < ng) {
             const float* d = dimg + (long long)act[c0 + tid] * D;
@@ -145,6 +186,50 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
         }
         __syncthreads();
         // logits of the halo tile for the chunk, cropped to each instance's box
+        if (MMA) {
+            const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+            const __half* P16 = reinterpret_cast<const __half*>(P);
+            const __half* sch = reinterpret_cast<const __half*>(sc);
+            uint32_t bh[2][2], bl[2][2];                   // B fragments: instance gid, channels 16 s + 2 tig (+ 8)
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                bh[s2][0] = *reinterpret_cast<const uint32_t*>(sch + gid * kNm + 16 * s2 + 2 * tig);
+                bh[s2][1] = *reinterpret_cast<const uint32_t*>(sch + gid * kNm + 16 * s2 + 2 * tig + 8);
+                bl[s2][0] = *reinterpret_cast<const uint32_t*>(sch + G * kNm + gid * kNm + 16 * s2 + 2 * tig);
+                bl[s2][1] = *reinterpret_cast<const uint32_t*>(sch + G * kNm + gid * kNm + 16 * s2 + 2 * tig + 8);
+            }
+            for (int mt = warp; mt < kMTiles; mt += kThreads / 32) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};         // rows gid / gid + 8 of the tile x instances 2 tig / 2 tig + 1
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const __half* ab = P16 + (mt * 16 + gid) * kKS + 16 * s2 + 2 * tig;
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ab);
+                    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(ab + 8 * kKS);
+                    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(ab + 8);
+                    const uint32_t a3 = *reinterpret_cast<const uint32_t*>(ab + 8 * kKS + 8);
+                    mma_16816(c, a0, a1, a2, a3, bl[s2][0], bl[s2][1]);
+                    mma_16816(c, a0, a1, a2, a3, bh[s2][0], bh[s2][1]);
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int h = mt * 16 + gid + 8 * rr;
+                    if (h >= HP) continue;
+                    const int hy = h / HT, hx = h - hy * HT;
+                    const float fy = (float)min(max(ty * PT - 1 + hy, 0), mh - 1);
+                    const float fx = (float)min(max(tx * PT - 1 + hx, 0), mw - 1);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int g = 2 * tig + j;
+                        if (g < ng) {
+                            const bool in = fx >= sbox[g * 4] && fx < sbox[g * 4 + 2] && fy >= sbox[g * 4 + 1] && fy < sbox[g * 4 + 3];
+                            float v = c[rr * 2 + j];
+                            if (variant == 1) v = 1.f / (1.f + expf(-v));
+                            Ls[g * HP + h] = in ? v : 0.f;
+                        }
+                    }
+                }
+            }
+        } else
         for (int h = tid; h < HP; h += kThreads) {
             float acc[G];
 #pragma unroll
@@ -222,25 +307,26 @@ mask_decode_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n
                        make_int4((int)codes[0], (int)codes[1], (int)codes[2], (int)codes[3]));
 }
 
-size_t decode_smem(int nm, int max_det) {
-    return (size_t)(nm * HP + G * HP + G * nm + G * 4) * 4 + G * 2 * 4 + (size_t)max_det * 4;
+size_t decode_smem(int nm, int max_det, bool mma) {
+    const size_t tile = mma ? (size_t)kMRows * kKS * 2 : (size_t)nm * HP * 4;
+    return tile + (size_t)(G * HP + G * nm + G * 4) * 4 + G * 2 * 4 + (size_t)max_det * 4;
 }
 
-template <typename T>
+template <typename T, bool MMA = false>
 int launch_decode(const float* dets, const int32_t* n_det, int max_det, const void* protos, int nhwc, int B, int nm, int mh,
                   int mw, int H, int W, int variant, uint8_t* code, int32_t* inst_area, uint8_t* inst_bits,
                   cudaStream_t s) {
     const int tiles_x = eitb_div_up(mw, PT), tiles_y = eitb_div_up(mh, PT);
-    const size_t smem = decode_smem(nm, max_det);
+    const size_t smem = decode_smem(nm, max_det, MMA);
     if (smem > 200 * 1024) return EITB_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(mask_decode_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(mask_decode_kernel<T, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return EITB_ERR_LAUNCH;
     const long long grid = (long long)B * tiles_x * tiles_y;
     if (grid > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
     eitb_prof_begin("mask_decode_kernel", s);
-    mask_decode_kernel<T><<<(unsigned)grid, kThreads, smem, s>>>(dets, n_det, max_det, (const T*)protos, nhwc, nm, mh, mw, H, W,
-                                                                 tiles_x, tiles_x * tiles_y, variant, code, inst_area,
-                                                                 inst_bits);
+    mask_decode_kernel<T, MMA><<<(unsigned)grid, kThreads, smem, s>>>(dets, n_det, max_det, (const T*)protos, nhwc, nm, mh, mw, H, W,
+                                                                      tiles_x, tiles_x * tiles_y, variant, code, inst_area,
+                                                                      inst_bits);
     EITB_CHECK_LAUNCH();
     return EITB_OK;
 }
@@ -275,6 +361,9 @@ extern "C" int eitb_mask_decode(const float* dets, const int32_t* n_det, int max
     if (proto_dtype == EITB_F16 && nm == 32 && (variant & 0x20) && !(variant & 0x10) && !(reinterpret_cast<uintptr_t>(protos) & 15))
         return eitb_mask_decode_tc(dets, n_det, max_det, protos, proto_channels_last, B, mh, mw, H, W, variant & 5, code,
                                    inst_area, inst_bits, s);
+    // the same prototypes stored NHWC, unless bit 4 asks for the scalar kernel: warp-level MMA for the logits
+    if (proto_dtype == EITB_F16 && nm == kNm && proto_channels_last && !(variant & 0x10) && !(reinterpret_cast<uintptr_t>(protos) & 15))
+        return launch_decode<__half, true>(dets, n_det, max_det, protos, 1, B, nm, mh, mw, H, W, variant & 5, code, inst_area, inst_bits, s);
     variant &= 5;
     switch (proto_dtype) {
         case EITB_F32: return launch_decode<float>(dets, n_det, max_det, protos, proto_channels_last, B, nm, mh, mw, H, W, variant, code, inst_area, inst_bits, s);

@@ -180,7 +180,11 @@ int eitb_scale_boxes(const float* dets, const int32_t* n, int B, int max_det, in
  *             bit 5 (0x20) -- fp16 prototypes with nm == 32: contraction as tcgen05.mma with the accumulator in
  *             tensor memory (same semantics).  Not the default: the contraction is K = 32 per pixel and the kernel
  *             is bound by the crop / upsample / threshold epilogue, where the CUDA-core kernel is 1.3-1.6x faster
- *             (bench.py kernels_isolated).  bit 4 (0x10) forces the CUDA-core kernel.
+ *             (bench.py kernels_isolated).
+ *             bit 4 (0x10) -- the CUDA-core kernel with scalar fp32 FMAs for the contraction.  Without bits 4 and 5, fp16
+ *             NHWC prototypes with nm == 32 (the network's own output) take the same kernel with the contraction as
+ *             warp-level mma.sync m16n8k16 (fp32 accumulate, coefficients as fp16 hi + lo): same semantics, another
+ *             summation order (<= 1e-5 of the mask pixels differ from the scalar kernel).
  *   code      [B,H,W] u8 out: overlay codes
  *   inst_area [B,max_det] int32 out or NULL: mask pixel count (the empty-mask filter)
  *   inst_bits [B,max_det,H,W/8] u8 out or NULL: per-instance bit masks (LSB = lowest x)

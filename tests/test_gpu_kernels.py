@@ -291,7 +291,50 @@ def test_mask_decode_batch_and_half_protos(ops):
     code16ref, _, _ = ops.mask_decode(dets, n, ph.float().to(DEV))
     assert torch.equal(code16, code16ref)          # fp16 protos are widened exactly
     cl = ph.to(DEV).contiguous(memory_format=torch.channels_last)     # NHWC storage, same result
-    assert torch.equal(ops.mask_decode(dets, n, cl)[0], code16)
+    assert torch.equal(ops.mask_decode(dets, n, cl, 0x10)[0], code16)
+    # NHWC fp16 is what the network emits: by default its logits come from warp-level MMAs (other summation order)
+    assert (ops.mask_decode(dets, n, cl)[0] != code16).float().mean().item() <= 1e-4
+
+
+@pytest.mark.parametrize("variant", [0, 1, 4])
+@pytest.mark.parametrize("case", ["teacher", "random50", "random300", "empty", "fewbox", "size256"])
+def test_mask_decode_warp_mma_path(ops, case, variant):
+    """Default path for fp16 NHWC prototypes with 32 channels (the network's output): logits by mma.sync with fp16 hi + lo
+    coefficients.  Against the scalar kernel (variant bit 4) and the CPU restatement, masks / areas / codes, every variant,
+    partial tiles (256-pixel size) and fp32 heads whose coefficients are not fp16 numbers."""
+    size = 512
+    if case == "teacher":
+        head, protos = synth.teacher_heads(seed=5)
+        head, protos = head[None], protos[None]
+    elif case == "fewbox":
+        head, protos = _few_box_heads(2, 30)
+        head, protos = head[None], protos[None]
+    elif case == "size256":
+        size = 256
+        head, protos = synth.random_heads(3, 60, seed=13, size=256)
+    else:
+        head, protos = synth.random_heads(2, {"random50": 50, "random300": 300, "empty": 0}[case], seed=41)
+    ph = torch.from_numpy(protos).half()
+    cl = ph.to(DEV).contiguous(memory_format=torch.channels_last)
+    dets, idx, n = ops.nms(dev(head), 4)
+    mm, area_mm, bits_mm = ops.mask_decode(dets, n, cl, variant, want_area=True, want_bits=True)
+    cc, area_cc, bits_cc = ops.mask_decode(dets, n, cl, variant | 0x10, want_area=True, want_bits=True)
+    total = bits_cc.numel() * 8
+    diff = int((np.unpackbits(bits_mm.cpu().numpy()) != np.unpackbits(bits_cc.cpu().numpy())).sum())
+    assert diff <= 1e-5 * max(total, 1), (diff, total)
+    assert (mm != cc).float().mean().item() <= 1e-4
+    got_bits = bits_mm.cpu().numpy()
+    for b in range(head.shape[0]):
+        nn = int(n[b])
+        got = _unpack_bits(got_bits[b, :nn], size)
+        assert np.array_equal(area_mm[b, :nn].cpu().numpy(), got.reshape(nn, size * size).sum(1))
+        r = Y.postprocess(torch.from_numpy(head[b]), ph[b].float(), 4, (size, size), (size, size),
+                          variant="logit" if not (variant & 1) else "sigmoid", drop_empty=False,
+                          crop="cpu" if variant & 4 else "float")
+        want = r["masks"].numpy()
+        assert int((got != want).sum()) <= 1e-4 * max(want.size, 1)
+        wcode = O.overlay_codes(O.class_union_masks(want, r["cls"].numpy().astype(int), size))
+        assert (wcode != mm[b].cpu().numpy()).mean() <= 1e-4
 
 
 @pytest.mark.parametrize("variant", [0, 1])
