@@ -190,9 +190,13 @@ class ConvNet:
         up_b = getattr(pr, "up_bias", None)
         if up_b is None and pr.upsample.bias is not None:
             up_b = pr.upsample.bias.detach().float()
+        # ConvTranspose2d(k 2, s 2) = four 1x1 convolutions, one per output phase (dy, dx); the two dx phases of a row are
+        # neighbouring pixels of the NHWC output, i.e. one 2C-channel "pixel" at stride 2: one launch per dy with the
+        # two taps' output channels side by side reads the input twice instead of four times
         self.p["proto"] = (P(pr.cv1),
-                           [[PackedConv.from_weight(up_w[:, :, dy, dx].t().contiguous()[:, :, None, None], up_b, 1, 1, False)
-                             for dx in range(2)] for dy in range(2)],
+                           [PackedConv.from_weight(torch.cat([up_w[:, :, dy, 0].t(), up_w[:, :, dy, 1].t()], 0).contiguous()[:, :, None, None],
+                                                   None if up_b is None else torch.cat([up_b, up_b]), 1, 1, False)
+                            for dy in range(2)],
                            P(pr.cv2), P(pr.cv3))
         self.stride, self.nm = h.stride, h.nm
 
@@ -335,10 +339,9 @@ class ConvNet:
         cv1, ups, cv2, cv3 = p["proto"]
         t = conv(feats[0], cv1)
         B, H, W = t.bhw
-        up = _new(B, 2 * H, 2 * W, ups[0][0].cout, t.buf.device)
+        up = _new(B, 2 * H, 2 * W, ups[0].cout // 2, t.buf.device)
         for dy in range(2):
-            for dx in range(2):
-                conv(t, ups[dy][dx], out=up, up=(2, dy, dx))
+            conv(t, ups[dy], out=up, up=(2, dy, 0))
         protos = conv(conv(up, cv2), cv3, out=Act(out[1]) if out is not None else None)
         box, cls, mc = [], [], []
         for i, f in enumerate(feats):

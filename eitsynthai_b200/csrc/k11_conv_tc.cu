@@ -18,6 +18,10 @@
 // tile -> TMA store).  Two accumulator stages in TMEM let the MMAs of tile i+1 run under the
 // epilogue of tile i; the shared-memory ring is 3..8 stages deep.
 #include "common.cuh"
+#include <cstdio>
+#include <mutex>
+#include <set>
+#include <string>
 #include <cuda.h>        // CUtensorMap and its enums only; the encoder is fetched from the driver at run time
 #include <mutex>
 
@@ -783,7 +787,11 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
         // the output map sees (Wo x Ho) pixels placed on every y_up-th pixel of a (Wo*y_up x Ho*y_up) map, offset (dy, dx)
         const int Wy = Wo * y_up, Hy = Ho * y_up;
         char* yb = static_cast<char*>(y) + ((size_t)(y_dy * Wy + y_dx) * y_ctot + y_coff) * 2;
-        const int cvis = Cout < y_ctot - y_coff ? Cout : y_ctot - y_coff;
+        // With y_up == 2 a map "pixel" is y_up physical pixels wide, so a launch with y_dx == 0 may write more than y_ctot
+        // channels per pixel: channels [y_ctot, 2 y_ctot) land in the next physical pixel -- both dx taps of a 2x2
+        // transposed convolution as ONE launch with the taps' output channels side by side.
+        const int cmax = (y_up - y_dx) * y_ctot - y_coff;
+        const int cvis = Cout < cmax ? Cout : cmax;
         if (!encode_act(&my, yb, cvis, Wo, Ho, N, y_ctot, (long long)Wy * y_up, (long long)Hy * Wy, y_up, p.slabC, p.tw, p.th, p.tn, 1))
             return EITB_ERR_BAD_ARG;
     }
@@ -805,7 +813,18 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
     }
     auto launch = [&](auto kernel, int threads) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EITB_ERR_LAUNCH;
-        eitb_prof_begin("conv_tc_kernel", s);
+        const char* prof_name = "conv_tc_kernel";
+        if (g_dbg & (1 << 20)) {                                           // launch profiler: one entry per layer shape and configuration
+            static std::mutex mu;
+            static std::set<std::string> names;
+            char buf[160];
+            snprintf(buf, sizeof buf, "conv_tc_kernel:k%ds%d:%d->%d@%dx%dx%d:%s%s%s%s:nt%d:st%d:h%d%s", ksize, stride, Cin, Cout, H, W, N,
+                     light ? "light" : "heavy", p.halo ? "+halo" : "", p.ws ? "+ws" : "", p.pair ? "+pair" : "", p.ntile, p.stages,
+                     p.halo_stages, p.has_res ? (p.res_mode == 2 ? ":res2" : ":res") : "");
+            std::lock_guard<std::mutex> lk(mu);
+            prof_name = names.insert(buf).first->c_str();
+        }
+        eitb_prof_begin(prof_name, s);
         kernel<<<grid, threads, smem, s>>>(mx, mw, my, mr, bias, p);
         EITB_CHECK_LAUNCH();
         return EITB_OK;
