@@ -61,6 +61,7 @@ SIGNATURES = {
     "eitb_conv2d_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "eitb_conv2d_tuning": (_i, [_i, _i, _i]),
     "eitb_conv2d_debug": (_i, [_i]),
+    "eitb_stem_debug": (_i, [_i]),
     "eitb_stem_conv3x3s2_nhwc": (_i, [_p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _p]),
     "eitb_dwconv3x3_nhwc": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p]),
     "eitb_tri_label_workspace_bytes": (_sz, [_i, _i]),

@@ -225,6 +225,140 @@ stem_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
+// The same stem with the 9 x 32 contraction on the tensor cores (mma.sync m16n8k16, fp32 accumulate): the CUDA-core kernel
+// above spends 9 FMAs per output and runs at ~45 % of the issue rate (0.64 ms per 320 slices for 1.4 GB of traffic).  The
+// tile is staged as fp16 (the u8 -> fp16 / 255 table), an M tile is 16 consecutive output pixels of a row, K = the 9 taps
+// padded to 16, N = 4 x 8 output channels.  The channel <-> column assignment is chosen so that a thread ends up with 8
+// CONSECUTIVE channels of its two pixels (column c of N tile j <-> channel 8 (c / 2) + 2 j + (c & 1)): one 16-byte store
+// per pixel, a warp writes 1 KB contiguous.  Weights (sums over the three equal input channels) enter as fp16 hi + lo, so
+// nothing is lost against the fp32 sums of the scalar kernel.  Epilogue: bias, SiLU as h + h tanh(h) with one
+// tanh.approx.f16x2 per two outputs (as in K11).
+constexpr int ST16_PITCH = 136;                                    // halfs per staged row (129 used)
+
+__device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
+    return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+}
+__device__ __forceinline__ void stem_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 3)
+stem_u8_mma_kernel(const uint8_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int N, int H, int W,
+                   int Ho, int Wo, int act, __half* __restrict__ y, int y_ctot, int y_coff, int tiles_x, int tiles_y) {
+    __shared__ __half lut[256];
+    __shared__ __align__(16) __half tile[ST_IN_H][ST16_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    lut[threadIdx.x] = unit_from_u8<__half>((int)threadIdx.x);
+    // B fragments: this lane's column is gid, its taps 2 tig, 2 tig + 1 (and 8 for tig 0)
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = 8 * (gid >> 1) + 2 * j + (gid & 1);
+        float wt[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int t = q < 2 ? 2 * tig + q : 8;
+            wt[q] = (q < 2 || tig == 0) ? w[(t * 3 + 0) * 32 + ch] + w[(t * 3 + 1) * 32 + ch] + w[(t * 3 + 2) * 32 + ch] : 0.f;
+        }
+        __half hi[3], lo[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { hi[q] = __float2half_rn(wt[q]); lo[q] = __float2half_rn(wt[q] - __half2float(hi[q])); }
+        const __half z = __float2half_rn(0.f);
+        bh[j][0] = pack_h2(hi[0], hi[1]); bl[j][0] = pack_h2(lo[0], lo[1]);
+        bh[j][1] = pack_h2(hi[2], z);     bl[j][1] = pack_h2(lo[2], z);
+    }
+    float hb[8];                                                   // bias / 2 of this lane's channels 8 tig .. 8 tig + 7
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hb[e] = bias ? (act ? 0.5f : 1.f) * bias[8 * tig + e] : 0.f;
+    // A fragments: taps 2 tig / 2 tig + 1 of pixel (row 2 r, column 2 ox): offsets in halfs from the pixel's top-left input
+    const int k0 = 2 * tig, k1 = 2 * tig + 1;
+    const int off0 = (k0 / 3) * ST16_PITCH + k0 % 3, off1 = (k1 / 3) * ST16_PITCH + k1 % 3, off8 = 2 * ST16_PITCH + 2;
+    const int total = N * tiles_y * tiles_x;
+    const int crow = threadIdx.x / 10, cchunk = threadIdx.x - crow * 10;
+    const bool fetcher = threadIdx.x < ST_IN_H * 10;
+    const bool vec_ok = (W & 15) == 0 && !(reinterpret_cast<uintptr_t>(x) & 15);
+    auto fetch = [&](int tix, uint4& v, bool& ok) {
+        ok = false;
+        v = make_uint4(0u, 0u, 0u, 0u);
+        if (!fetcher || tix >= total || !vec_ok) return;
+        const int tx = tix % tiles_x, ty = (tix / tiles_x) % tiles_y, n = tix / (tiles_x * tiles_y);
+        const int iy = 2 * ty * ST_TO_H - 1 + crow, xs = 2 * tx * ST_TO_W - 16 + cchunk * 16;
+        if (iy < 0 || iy >= H || xs < 0 || xs + 16 > W) return;
+        v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)n * H + iy) * W + xs));
+        ok = true;
+    };
+    uint4 pre;
+    bool pre_ok;
+    fetch(blockIdx.x, pre, pre_ok);
+    const __half hz = __float2half_rn(0.f);
+    for (int tix = blockIdx.x; tix < total; tix += gridDim.x) {
+        const int tx = tix % tiles_x, ty = (tix / tiles_x) % tiles_y, n = tix / (tiles_x * tiles_y);
+        const int ox0 = tx * ST_TO_W, oy0 = ty * ST_TO_H;
+        const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+        __syncthreads();                                           // the previous tile is consumed (and the table is written)
+        if (vec_ok) {
+            if (fetcher) {
+                const uint32_t wv[4] = {pre.x, pre.y, pre.z, pre.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int c = cchunk * 16 + k - 15;
+                    if (c >= 0 && c < ST_IN_W) tile[crow][c] = pre_ok ? lut[(wv[k >> 2] >> (8 * (k & 3))) & 0xffu] : hz;
+                }
+            }
+        } else {
+            const uint8_t* img = x + (size_t)n * H * W;
+            for (int i = threadIdx.x; i < ST_IN_H * ST_IN_W; i += 256) {
+                const int r = i / ST_IN_W, c = i - r * ST_IN_W;
+                const int iy = iy0 + r, ix = ix0 + c;
+                tile[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? lut[__ldg(img + (size_t)iy * W + ix)] : hz;
+            }
+        }
+        __syncthreads();
+        fetch(tix + gridDim.x, pre, pre_ok);                       // in flight during the arithmetic below
+        const int oy = oy0 + warp;                                 // one output row per warp, four M tiles along it
+        if (oy >= Ho) continue;
+        const __half* trow = &tile[2 * warp][0];
+#pragma unroll
+        for (int mt = 0; mt < ST_TO_W / 16; ++mt) {
+            const __half* pa = trow + 2 * (mt * 16 + gid);         // pixel gid of the M tile; pixel gid + 8 is 16 halfs on
+            const uint32_t a0 = pack_h2(pa[off0], pa[off1]);
+            const uint32_t a1 = pack_h2(pa[16 + off0], pa[16 + off1]);
+            const uint32_t a2 = tig == 0 ? (uint32_t)__half_as_ushort(pa[off8]) : 0u;
+            const uint32_t a3 = tig == 0 ? (uint32_t)__half_as_ushort(pa[16 + off8]) : 0u;
+            float c[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+                stem_mma(c[j], a0, a1, a2, a3, bl[j][0], bl[j][1]);
+                stem_mma(c[j], a0, a1, a2, a3, bh[j][0], bh[j][1]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {                       // pixel gid, then pixel gid + 8
+                const int ox = ox0 + mt * 16 + gid + 8 * rr;
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (act) {
+                        const __half2 h2 = __floats2half2_rn(fmaf(c[j][2 * rr], 0.5f, hb[2 * j]), fmaf(c[j][2 * rr + 1], 0.5f, hb[2 * j + 1]));
+                        uint32_t t;
+                        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&h2)));
+                        const __half2 r2 = __hfma2(h2, *reinterpret_cast<const __half2*>(&t), h2);
+                        o[j] = *reinterpret_cast<const uint32_t*>(&r2);
+                    } else {
+                        const __half2 r2 = __floats2half2_rn(c[j][2 * rr] + hb[2 * j], c[j][2 * rr + 1] + hb[2 * j + 1]);
+                        o[j] = *reinterpret_cast<const uint32_t*>(&r2);
+                    }
+                }
+                if (ox < Wo)
+                    *reinterpret_cast<int4*>(y + ((size_t)(n * Ho + oy) * Wo + ox) * y_ctot + y_coff + tig * 8) =
+                        make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+            }
+        }
+    }
+}
+
 // depthwise 3x3, stride 1, pad 1; w [9][C] fp16.  One thread = 8 channels (one 16-byte vector) x DW_PX consecutive
 // output pixels of one row: its 3 x (DW_PX + 2) input vectors are 18 independent 16-byte loads issued back to back (288 B
 // in flight per thread -- the round-1 kernel had 24 B and sat at 19 % of the DRAM peak), the 72 weights live in
@@ -425,7 +559,11 @@ DwEncodeFn dw_encoder() {
     return fn;
 }
 
+int g_stem_scalar = 0;                                              // eitb_stem_debug(1): the CUDA-core u8 stem (A/B runs, tests)
+
 }  // namespace
+
+extern "C" int eitb_stem_debug(int scalar) { g_stem_scalar = scalar != 0; return EITB_OK; }
 
 extern "C" int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, const float* w27, const float* bias, int Cout, int act,
                                         int gray, void* y, int y_ctot, int y_coff, eitb_stream_t stream) {
@@ -440,8 +578,13 @@ extern "C" int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, cons
         const int tiles_x = eitb_div_up(Wo, ST_TO_W), tiles_y = eitb_div_up(Ho, ST_TO_H);
         const long long tiles = (long long)N * tiles_x * tiles_y;
         if (tiles > 0x7fffffffLL) return EITB_ERR_UNSUPPORTED;
-        const int grid = tiles < 2 * EITB_NUM_SMS ? (int)tiles : 2 * EITB_NUM_SMS;
-        stem_u8_kernel<<<grid, 256, 0, s>>>((const uint8_t*)x, w27, bias, N, H, W, Ho, Wo, act, (__half*)y, y_ctot, y_coff, tiles_x, tiles_y);
+        if (g_stem_scalar) {
+            const int grid = tiles < 2 * EITB_NUM_SMS ? (int)tiles : 2 * EITB_NUM_SMS;
+            stem_u8_kernel<<<grid, 256, 0, s>>>((const uint8_t*)x, w27, bias, N, H, W, Ho, Wo, act, (__half*)y, y_ctot, y_coff, tiles_x, tiles_y);
+        } else {
+            const int grid = tiles < 3 * EITB_NUM_SMS ? (int)tiles : 3 * EITB_NUM_SMS;
+            stem_u8_mma_kernel<<<grid, 256, 0, s>>>((const uint8_t*)x, w27, bias, N, H, W, Ho, Wo, act, (__half*)y, y_ctot, y_coff, tiles_x, tiles_y);
+        }
     } else if (gray)
         stem_gray_kernel<<<eitb_grid(total * 4, 256, 8), 256, 0, s>>>((const __half*)x, w27, bias, N, H, W, Ho, Wo, act, (__half*)y, y_ctot,
                                                                       y_coff);

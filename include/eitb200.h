@@ -275,6 +275,9 @@ int eitb_conv2d_debug(int flags);
  * never written to HBM. */
 int eitb_stem_conv3x3s2_nhwc(const void* x, int N, int H, int W, const float* w27, const float* bias, int Cout, int act,
                              int gray, void* y, int y_ctot, int y_coff, eitb_stream_t stream);
+/* gray 2 runs its 9 x 32 contraction as warp-level mma.sync (fp16 inputs, weight sums as fp16 hi + lo, fp32 accumulate);
+ * eitb_stem_debug(1) selects the CUDA-core kernel instead (host, process-wide; A/B runs and tests). */
+int eitb_stem_debug(int scalar);
 /* Depthwise Conv(C -> C, k3, s1, pad 1, groups C): w9 [9][C] fp16, C % 8 == 0. */
 int eitb_dwconv3x3_nhwc(const void* x, int N, int H, int W, int x_ctot, int x_coff, int C, const void* w9, const float* bias,
                         int act, void* y, int y_ctot, int y_coff, eitb_stream_t stream);

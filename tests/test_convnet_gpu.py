@@ -131,6 +131,18 @@ def test_depthwise_and_stem():
         refu = F.silu(F.conv2d(xin, ws.float(), bs, 2, 1)).permute(0, 2, 3, 1)
         assert yu.buf.shape == refu.shape
         assert float((yu.buf.float() - refu).abs().max()) <= 2e-3 * float(refu.abs().max()) + 2e-3
+        # the CUDA-core form of the same kernel (the default runs the contraction as warp-level MMAs), and no activation
+        from eitsynthai_b200 import cabi
+        cabi.load().eitb_stem_debug(1)
+        try:
+            ysc = stem_u8(u8, PackedConv.from_weight(ws, bs, 2, 1, True))
+        finally:
+            cabi.load().eitb_stem_debug(0)
+        assert float((ysc.buf.float() - refu).abs().max()) <= 2e-3 * float(refu.abs().max()) + 2e-3
+        assert float((ysc.buf.float() - yu.buf.float()).abs().max()) <= 2e-3 * float(refu.abs().max()) + 2e-3
+        yl = stem_u8(u8, PackedConv.from_weight(ws, bs, 2, 1, False))
+        refl = F.conv2d(xin, ws.float(), bs, 2, 1).permute(0, 2, 3, 1)
+        assert float((yl.buf.float() - refl).abs().max()) <= 1e-3 * float(refl.abs().max()) + 1e-3
 
 
 @pytest.mark.parametrize("C,H,W,B", [(128, 64, 64, 3), (256, 16, 16, 5), (64, 33, 17, 2), (512, 13, 20, 2), (24, 9, 31, 2)])
