@@ -280,6 +280,27 @@ def _events_ms(torch, fn, n=10, warm=3):
     return a.elapsed_time(b) / n
 
 
+_ALL_CPUS = None
+
+
+def _bind_near_gpu(index: int):
+    """Pin this process to the CPUs NVML names as closest to its GPU, so that the pinned host buffers it allocates afterwards
+    (series in, label maps out) live on the GPU's NUMA node: with 8 ranks the host-side copies otherwise cross the
+    socket interconnect and share one memory controller.  Returns the CPU list, or None when NVML cannot tell."""
+    global _ALL_CPUS
+    try:
+        _ALL_CPUS = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        cpus = sorted(os.sched_getaffinity(0))
+        return [cpus[0], cpus[-1], len(cpus)] if cpus else None
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -293,6 +314,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_affinity = _bind_near_gpu(local)                           # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         # the exchange is 0.3 MB of coronal rows per step: one NCCL CTA moves it, and more would take SMs away from the
         # persistent one-CTA-per-SM convolution kernels that run concurrently on the main stream
@@ -694,6 +716,8 @@ def run_b200(args):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
+            if _ALL_CPUS:
+                os.sched_setaffinity(0, _ALL_CPUS)                  # the CPU baseline may use every host core again
             threads = os.cpu_count() or 1
             rate, kind, sample, _ = cpu_path_rate(25.0, threads, 1, 0, nslices)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
@@ -703,7 +727,8 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f16 (CNN, fp32 accumulate) / int16,u8,f32,f64 (kernels)", "data": "synthetic",
                 "config": dict(config(world, S, nslices), chunk=args.chunk, engine=args.engine, class_bias_shift=pipe.bias_shift,
                                mean_detections_per_slice=ndet_mean, cuda_graphs=not args.no_graphs,
-                               overlap=runner_overlap, label_fan=args.label_fan),
+                               overlap=runner_overlap, label_fan=args.label_fan,
+                               cpu_affinity_first_last_count=cpu_affinity),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roof, "cpu_baseline": cpu,
                 "roofline_kernels": kroof, "conv_work_per_step": {k: v for k, v in conv_stats.items() if k != "by_kind"},
                 "eager_profiled_ms_per_step": ms_eager,

@@ -102,6 +102,44 @@ small_first_kernel(const uint8_t* __restrict__ code, const int* __restrict__ any
     }
 }
 
+// The same test on 16 pixels per thread (rows that are multiples of 16 pixels): "not background" of a row chunk and of the
+// chunk above it as 16-bit masks from two 16-byte loads; a pixel can only be the raster-first pixel of its component when
+// neither its left nor its upper neighbour is set, so dense label images leave (almost) no survivor for the bounded flood.
+__device__ __forceinline__ uint32_t nb_mask16(const uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)                                     // byte > 1 <=> neither black (0) nor muscle (1)
+        m |= ((((__vcmpgtu4(w[i], 0x01010101u) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * i);
+    return m;
+}
+static_assert(EITB_CODE_BLACK == 0 && EITB_CODE_MUSCLE == 1, "nb_mask16 tests code > 1");
+
+__global__ void __launch_bounds__(256)
+small_first16_kernel(const uint8_t* __restrict__ code, const int* __restrict__ anybody, int B, int H, int W,
+                     unsigned* __restrict__ bitmap, int words_per_img) {
+    const long long per_img = (long long)H * W / 16, total = per_img * B;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_img);
+        if (!anybody[b]) continue;
+        const int p0 = (int)(i - (long long)b * per_img) * 16;
+        const uint8_t* img = code + (long long)b * H * W;
+        const uint32_t m = nb_mask16(*reinterpret_cast<const uint4*>(img + p0));
+        if (!m) continue;
+        const int y = p0 / W, x0 = p0 - y * W;
+        const uint32_t left = (m << 1) | ((x0 > 0 && not_bg(img[p0 - 1])) ? 1u : 0u);
+        const uint32_t up = y > 0 ? nb_mask16(*reinterpret_cast<const uint4*>(img + p0 - W)) : 0u;
+        uint32_t cand = m & ~left & ~up & 0xffffu;
+        while (cand) {
+            const int p = p0 + __ffs(cand) - 1;
+            cand &= cand - 1;
+            int px[5];
+            if (small_component(img, H, W, p, px) < 5 && px[0] == p)
+                atomicOr(bitmap + (long long)b * words_per_img + (p >> 5), 1u << (p & 31));
+        }
+    }
+}
+
 // Order-dependent repaints, parallel where the order cannot matter: a candidate reads and writes only the bounding box
 // of its pixels grown by one pixel.  Every candidate registers that box in a coarse grid of cells (shared memory, one
 // counter per cell); a candidate whose cells all count exactly one is isolated -- no other candidate's reads or writes
@@ -643,7 +681,10 @@ extern "C" int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int
         EITB_CHECK_LAUNCH();
         eitb_prof_begin("small_first_kernel", s);
         if (H > 65535 || B > 65535) return EITB_ERR_UNSUPPORTED;
-        small_first_kernel<<<dim3(eitb_div_up(W, 256), H, B), 256, 0, s>>>(code, anybody, B, H, W, bitmap, words);
+        if (W % 16 == 0 && !(reinterpret_cast<uintptr_t>(code) & 15))
+            small_first16_kernel<<<eitb_grid((long long)n / 16, 256, 8), 256, 0, s>>>(code, anybody, B, H, W, bitmap, words);
+        else
+            small_first_kernel<<<dim3(eitb_div_up(W, 256), H, B), 256, 0, s>>>(code, anybody, B, H, W, bitmap, words);
         EITB_CHECK_LAUNCH();
         eitb_prof_begin("small_repaint_kernel", s);
         small_repaint_kernel<<<B, kRepaintWarps * 32, 0, s>>>(code, anybody, H, W, bitmap, words);
