@@ -532,7 +532,7 @@ def run_b200(args):
             t = _events_ms(torch, lambda: ops.nms(hd, 4, want_idx=False))
             iso["K5_nms"] = {"ms": t, "bytes_per_slice": 430080 + 45600}
             dets, _, nd = ops.nms(hd, 4, want_idx=False)
-            for nm_, var in (("K6_mask_decode_tensor_core", 0x20), ("K6_mask_decode_cuda_core", 0x10)):
+            for nm_, var in (("K6_mask_decode_tcgen05", 0x20), ("K6_mask_decode_scalar", 0x10), ("K6_mask_decode_warp_mma_default", 0)):
                 t = _events_ms(torch, lambda: ops.mask_decode(dets, nd, pr, var))
                 iso[nm_] = {"ms": t, "bytes_per_slice": 1048576 + 45600 + 262144, "flops_per_slice": 1048576 * float(nd.float().mean())}
             if code0 is not None:

@@ -53,6 +53,9 @@ SIGNATURES = {
     "eitb_label_cleanup_workspace_bytes": (_sz, [_i, _i, _i]),
     "eitb_label_cleanup": (_i, [_p, _p, _i, _i, _i, _p, _sz, _p]),
     "eitb_codes_to_bgr": (_i, [_p, _p, _i64, _p]),
+    "eitb_apply_mask_u8": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "eitb_class_images": (_i, [_p, _p, _i, _i64, _p, _p]),
+    "eitb_bgr_or_code": (_i, [_p, _i64, _i, _p, _p]),
     "eitb_bias_act_nhwc": (_i, [_p, _i, C.c_longlong, _i, _p, _i, _p]),
     "eitb_conv_epilogue_nhwc": (_i, [_p, _i, C.c_longlong, _i, _p, _i, _p, _p, _p, _i, _i, _p]),
     "eitb_upsample2x_concat_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

@@ -123,6 +123,73 @@ extern "C" int eitb_codes_to_bgr(const uint8_t* code, uint8_t* bgr, int64_t n, e
 }
 
 // ---------------------------------------------------------------------------------------------
+// The per-function entry points of the mirror (callers that use the reference's helpers one by one, with numpy images
+// in between): the same pixel rules as the fused kernels, as library calls instead of host-framework arithmetic.
+
+// cv2.bitwise_and(img, img, mask=m) of ai_tools.py:212: out = mask != 0 ? img : 0   (K1 fuses this on the batched path)
+__global__ void apply_mask_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, int64_t n, int ch,
+                                  uint8_t* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * ch; i += stride) out[i] = mask[i / ch] ? img[i] : 0;
+}
+
+extern "C" int eitb_apply_mask_u8(const uint8_t* img, const uint8_t* mask, int64_t n_px, int channels, uint8_t* out,
+                                  eitb_stream_t stream) {
+    if (!img || !mask || !out || n_px < 0 || channels < 1 || channels > 4) return EITB_ERR_BAD_ARG;
+    if (n_px == 0) return EITB_OK;
+    eitb_prof_begin("apply_mask_kernel", (cudaStream_t)stream);
+    apply_mask_kernel<<<eitb_grid(n_px * channels, 256, 8), 256, 0, (cudaStream_t)stream>>>(img, mask, n_px, channels, out);
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
+}
+
+// create_segmentations_masks (utils.py:437-523): per class the union of its instances' masks (> 0) painted in the class
+// colour.  masks [n, S*S] fp32, cls [n] int32 (0 bone, 1 muscles, 2 lung, 3 adipose; others ignored) -> bgr4 [4, S*S, 3] u8.
+__global__ void class_images_kernel(const float* __restrict__ masks, const int32_t* __restrict__ cls, int n, int64_t px,
+                                    uint8_t* __restrict__ bgr4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < px; p += stride) {
+        unsigned hit = 0;
+        for (int i = 0; i < n; ++i) {
+            const int c = cls[i];
+            if (c >= 0 && c < 4 && masks[(int64_t)i * px + p] > 0.f) hit |= 1u << c;
+        }
+        // colours of utils.py:468-473 (BGR): bone white, muscles red, lung cyan-ish (255,255,0), adipose yellow (0,255,255)
+        const uint8_t col[4][3] = {{255, 255, 255}, {0, 0, 255}, {255, 255, 0}, {0, 255, 255}};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) bgr4[((int64_t)c * px + p) * 3 + k] = (hit >> c) & 1u ? col[c][k] : 0;
+    }
+}
+
+extern "C" int eitb_class_images(const float* masks, const int32_t* cls, int n, int64_t n_px, uint8_t* bgr4, eitb_stream_t stream) {
+    if (!bgr4 || n < 0 || n_px < 0 || (n > 0 && (!masks || !cls))) return EITB_ERR_BAD_ARG;
+    if (n_px == 0) return EITB_OK;
+    eitb_prof_begin("class_images_kernel", (cudaStream_t)stream);
+    class_images_kernel<<<eitb_grid(n_px, 256, 8), 256, 0, (cudaStream_t)stream>>>(masks, cls, n, n_px, bgr4);
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
+}
+
+// overlay_segmentation_masks (utils.py:395-434) of one class image: code |= value wherever any BGR channel is non-zero
+// (the saturating colour adds of the four class images are the OR of their 3-bit colour codes).
+__global__ void bgr_or_code_kernel(const uint8_t* __restrict__ bgr, int64_t px, int value, uint8_t* __restrict__ code) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < px; p += stride)
+        if (bgr[p * 3] | bgr[p * 3 + 1] | bgr[p * 3 + 2]) code[p] |= (uint8_t)value;
+}
+
+extern "C" int eitb_bgr_or_code(const uint8_t* bgr, int64_t n_px, int value, uint8_t* code, eitb_stream_t stream) {
+    if (!bgr || !code || n_px < 0 || value < 0 || value > 7) return EITB_ERR_BAD_ARG;
+    if (n_px == 0) return EITB_OK;
+    eitb_prof_begin("bgr_or_code_kernel", (cudaStream_t)stream);
+    bgr_or_code_kernel<<<eitb_grid(n_px, 256, 8), 256, 0, (cudaStream_t)stream>>>(bgr, n_px, value, code);
+    EITB_CHECK_LAUNCH();
+    return EITB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host path of K3: the coronal image needs one row of every slice.  Ship exactly those rows
 // from the pinned host series with one strided DMA (no CPU gather, no staging copy): row `row` of each of
 // n_slices [H,W] int16 slices -> dev_rows [n_slices, W].

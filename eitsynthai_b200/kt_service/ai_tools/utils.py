@@ -126,7 +126,7 @@ def apply_body_mask(norm_u8, body_mask):
 
 
 def _masked(img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    return torch.where(mask != 0, img, torch.zeros_like(img))
+    return ops.apply_mask_u8(img.contiguous(), mask.contiguous())
 
 
 # ---------------------------------------------------------------------------- a2 / a3
@@ -192,18 +192,14 @@ def search_number_axial_slice(detections, custom_number_slise=0, image_width=512
 def create_segmentations_masks(results, img_size=512):
     """utils.py:437-523: ``results.masks.data`` (n,S,S), ``results.boxes.cls`` -> dict of 4 BGR images."""
     try:
-        masks = torch.as_tensor(results.masks.data).to(_dev())
-        cls = torch.as_tensor(results.boxes.cls).to(_dev()).long()
+        masks = torch.as_tensor(results.masks.data).to(_dev()).float().contiguous()
+        cls = torch.as_tensor(results.boxes.cls).to(_dev()).to(torch.int32).contiguous()
         size = int(results.orig_shape[0])
-        colors = {"bone": (255, 255, 255), "muscles": (0, 0, 255), "lung": (255, 255, 0), "adipose": (0, 255, 255)}
-        out = {}
-        for c, name in enumerate(CLASS_NAMES):
-            sel = masks[cls == c]
-            union = (sel > 0).any(0) if sel.shape[0] else torch.zeros((size, size), dtype=torch.bool, device=_dev())
-            img = torch.zeros((size, size, 3), dtype=torch.uint8, device=_dev())
-            img[union] = torch.tensor(colors[name], dtype=torch.uint8, device=_dev())
-            out[name] = img.cpu().numpy()
-        return out
+        if masks.ndim != 3 or masks.shape[0] == 0:
+            masks = torch.zeros((0, size, size), dtype=torch.float32, device=_dev())
+            cls = torch.zeros((0,), dtype=torch.int32, device=_dev())
+        imgs = ops.class_images(masks, cls).cpu().numpy()           # one library call: union per class, painted
+        return {name: imgs[c] for c, name in enumerate(CLASS_NAMES)}
     except Exception as e:
         logger.error(f"create_segmentations_masks failed: {e}")
         return {}
@@ -215,9 +211,10 @@ def _codes_from_class_images(d, device) -> torch.Tensor:
     code = None
     for name, val in (("bone", 7), ("muscles", 1), ("lung", 6), ("adipose", 3)):
         if name in d:
-            img = torch.from_numpy(np.ascontiguousarray(d[name])).to(device)
-            hit = (img > 0).any(dim=2).to(torch.uint8) * val
-            code = hit if code is None else torch.bitwise_or(code, hit)
+            img = torch.from_numpy(np.ascontiguousarray(d[name], dtype=np.uint8)).to(device)
+            if code is None:
+                code = torch.zeros(img.shape[:2], dtype=torch.uint8, device=device)
+            ops.bgr_or_code(img, val, code)
     return code
 
 

@@ -265,6 +265,39 @@ def label_cleanup(code: torch.Tensor, body: torch.Tensor | None) -> torch.Tensor
     return code
 
 
+def apply_mask_u8(img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """img [..., H, W] or [H, W, C] u8, mask [H, W] u8 -> img where mask != 0 else 0 (cv2.bitwise_and(x, x, mask=m))."""
+    _chk(img, torch.uint8, "img")
+    _chk(mask, torch.uint8, "mask")
+    n_px = mask.numel()
+    assert img.numel() % n_px == 0 and img.numel() // n_px <= 4
+    out = torch.empty_like(img)
+    with torch.cuda.device(img.device):
+        cabi.call("eitb_apply_mask_u8", img.data_ptr(), mask.data_ptr(), n_px, img.numel() // n_px, out.data_ptr(), _stream(img))
+    return out
+
+
+def class_images(masks: torch.Tensor, cls: torch.Tensor) -> torch.Tensor:
+    """masks [n, S, S] fp32, cls [n] int32 -> [4, S, S, 3] u8: create_segmentations_masks' four BGR class images."""
+    _chk(masks, torch.float32, "masks")
+    _chk(cls, torch.int32, "cls")
+    n, H, W = masks.shape
+    out = torch.empty((4, H, W, 3), dtype=torch.uint8, device=masks.device)
+    with torch.cuda.device(masks.device):
+        cabi.call("eitb_class_images", masks.data_ptr(), cls.data_ptr(), n, H * W, out.data_ptr(), _stream(masks))
+    return out
+
+
+def bgr_or_code(bgr: torch.Tensor, value: int, code: torch.Tensor) -> torch.Tensor:
+    """code |= value wherever the [H, W, 3] u8 image is non-zero (overlay_segmentation_masks on colour codes)."""
+    _chk(bgr, torch.uint8, "bgr")
+    _chk(code, torch.uint8, "code")
+    assert bgr.numel() == code.numel() * 3
+    with torch.cuda.device(code.device):
+        cabi.call("eitb_bgr_or_code", bgr.data_ptr(), code.numel(), int(value), code.data_ptr(), _stream(code))
+    return code
+
+
 def codes_to_bgr(code: torch.Tensor) -> torch.Tensor:
     _chk(code, torch.uint8, "code")
     out = torch.empty(code.shape + (3,), dtype=torch.uint8, device=code.device)

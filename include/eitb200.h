@@ -205,6 +205,16 @@ int eitb_label_cleanup(uint8_t* code, const uint8_t* body, int B, int H, int W, 
 /* code image -> the reference's BGR colour image, [n] -> [n,3]. */
 int eitb_codes_to_bgr(const uint8_t* code, uint8_t* bgr, int64_t n, eitb_stream_t stream);
 
+/* Per-function entry points of the mirror (the fused kernels cover these rules on the batched path):
+ *   eitb_apply_mask_u8  cv2.bitwise_and(img, img, mask=m), ai_tools.py:212: out[p, c] = mask[p] ? img[p, c] : 0
+ *   eitb_class_images   create_segmentations_masks, utils.py:437-523: masks [n, n_px] fp32 (> 0 = set), cls [n] int32
+ *                       -> bgr4 [4, n_px, 3]: per class (bone, muscles, lung, adipose) the union painted in its colour
+ *   eitb_bgr_or_code    overlay_segmentation_masks, utils.py:395-434, one class image at a time: code[p] |= value where
+ *                       any channel of bgr[p] is non-zero (code must be initialised by the caller) */
+int eitb_apply_mask_u8(const uint8_t* img, const uint8_t* mask, int64_t n_px, int channels, uint8_t* out, eitb_stream_t stream);
+int eitb_class_images(const float* masks, const int32_t* cls, int n, int64_t n_px, uint8_t* bgr4, eitb_stream_t stream);
+int eitb_bgr_or_code(const uint8_t* bgr, int64_t n_px, int value, uint8_t* code, eitb_stream_t stream);
+
 /* ---- K9: conv epilogue of the CNN ------------------------------------------------------------------
  * In-place per-channel bias (BatchNorm folded into the convolution, as ultralytics' fuse() does for
  * the models loaded at ai_tools.py:69-71) + SiLU on a channels-last activation tensor.

@@ -16,7 +16,7 @@ rh, rp = synth.random_heads(64, 300, seed=1)
 dets300, _, n300 = ops.nms(torch.from_numpy(rh).cuda().half(), 4, want_idx=False)
 p300 = torch.from_numpy(rp).cuda().half().contiguous(memory_format=torch.channels_last)
 for name, d, nn, pr in (("bench-like", dets, n, protos), ("300 dets", dets300, n300, p300)):
-    for label, var in (("tcgen05", 0x20), ("cuda-core", 0x10)):
+    for label, var in (("tcgen05", 0x20), ("scalar", 0x10), ("warp-mma", 0)):
         for _ in range(3):
             ops.mask_decode(d, nn, pr, var)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

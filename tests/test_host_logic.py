@@ -85,20 +85,6 @@ def test_config_surface_keeps_the_reference_names():
     assert config.device() == "cuda:0"
 
 
-def test_mirror_overlay_and_mask_helpers_on_cpu_tensors(golden):
-    """Device-agnostic torch helpers of the kt_service mirror (they run on the GPU in the product)."""
-    import torch
-    from eitsynthai_b200 import synth
-    from eitsynthai_b200.kt_service.ai_tools import utils as U
-    from oracle.gen_golden import segmentation_case
-    masks, cls = segmentation_case(1, 512, 60)
-    d = O.create_segmentations_masks(masks, cls, 512)
-    code = U._codes_from_class_images(d, torch.device("cpu")).numpy()
-    assert np.array_equal(O.code_to_bgr(code), golden["seg1_overlay"])
-    img, m = torch.from_numpy(golden["p0_norm"]), torch.from_numpy(golden["p0_body"])
-    assert np.array_equal(U._masked(img, m).numpy(), golden["p0_normbody"])
-
-
 def test_tri_label_oracle_against_exact_rational_arithmetic_on_the_most_delicate_triangles():
     """oracle/tri_label.c (fp64, with its 1e-9 * area noise floor) against process_triangle evaluated in exact rational
     arithmetic (no rounding, no noise-floor rule), on the triangles of two real polygon sets whose decisions are closest

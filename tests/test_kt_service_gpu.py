@@ -178,6 +178,24 @@ def test_conv_epilogue_and_upsample_concat_kernels():
     assert torch.equal(got, torch.cat((torch.nn.functional.interpolate(a, scale_factor=2.0, mode="nearest"), b), 1))
 
 
+def test_mirror_overlay_and_mask_helpers_are_library_calls(golden):
+    """The per-function helpers of the kt_service mirror (overlay of the class images, mask apply, class images from the
+    instance masks) run as libeitb200 kernels and reproduce the real reference's outputs."""
+    from eitsynthai_b200 import ops
+    from eitsynthai_b200.kt_service.ai_tools import utils as U
+    masks, cls = segmentation_case(1, 512, 60)
+    d = O.create_segmentations_masks(masks, cls, 512)
+    code = U._codes_from_class_images(d, torch.device("cuda:0")).cpu().numpy()
+    assert np.array_equal(O.code_to_bgr(code), golden["seg1_overlay"])
+    img, m = torch.from_numpy(golden["p0_norm"]).cuda(), torch.from_numpy(golden["p0_body"]).cuda()
+    assert np.array_equal(U._masked(img, m).cpu().numpy(), golden["p0_normbody"])
+    got = ops.class_images(torch.from_numpy(masks.astype(np.float32)).cuda(), torch.from_numpy(cls.astype(np.int32)).cuda()).cpu().numpy()
+    for c, name in enumerate(U.CLASS_NAMES):
+        assert np.array_equal(got[c], d[name]), name
+    with pytest.raises(Exception):
+        U._masked(torch.from_numpy(golden["p0_norm"]), torch.from_numpy(golden["p0_body"]))   # host tensors: no CPU fallback
+
+
 def test_series_batch_runner_graphs_match_eager(pipe):
     """Public throughput engine: CUDA-graph replay and the host path give the same label maps as the
     plain per-chunk calls, and the same coronal decision as ImagingPipeline.rib_select."""
