@@ -725,7 +725,10 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
         } else {
             p.stages = avail / p.stage_bytes;
             if (p.stages > g_stage_cap) p.stages = g_stage_cap;
-            if (p.stages < (want_light ? 3 : 2)) return false;
+            // two CTAs per SM: a ring that also streams the weights needs three stages; with resident weights two are enough
+            // (128 -> 128 1x1 at 64 x 64: 191 -> 138 us against the one-CTA configuration it fell back to; experiment 1<<21
+            // restores the old rule)
+            if (p.stages < ((want_light && (!p.ws || (g_dbg & (1 << 21)))) ? 3 : 2)) return false;
         }
         smem = (size_t)fixed + p.ws_bytes + (size_t)p.stages * p.stage_bytes + (size_t)p.halo_stages * p.halo_bytes;
         light = want_light;
