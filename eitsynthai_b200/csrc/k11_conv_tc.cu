@@ -707,7 +707,7 @@ extern "C" int eitb_conv2d_nhwc(const void* x, int N, int H, int W, int x_ctot, 
         // they fit beside the minimum ring -- measured SLOWER on every 3x3 layer of the network, e.g. proto.cv2 757 -> 1017 us:
         // the ring gets too shallow to cover the TMA latency.)
         if (g_dbg & 512) p.ws = (g_ws && (p.n_tiles == 1 || p.n_tiles == 2) && ws_pad + min_ring <= avail) ? 1 : 0;
-        else p.ws = (g_ws && p.n_tiles == 1 && all_w <= (total * 2) / 5) ? 1 : 0;
+        else p.ws = (g_ws && p.n_tiles == 1 && all_w <= ((g_dbg & (1 << 22)) && ksize == 1 ? (total * 3) / 5 : (total * 2) / 5)) ? 1 : 0;   // experiment 1<<22: 1x1 weights up to 60 %
         if (need_ws && !p.ws) return false;
         p.ws_bytes = p.ws ? ws_pad : 0;
         avail -= p.ws_bytes;

@@ -364,6 +364,11 @@ class SeriesBatchRunner:
         # across steps.  Buffers are guarded by events (previous reader -> next writer), never by stream joins.
         self.overlap = bool(overlap and use_graphs)
         self.pre_s, self.post_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        # The network's graphs are captured on and replayed in a HIGH-priority stream: when one of its persistent
+        # convolution kernels starts, its CTAs are placed before pending CTAs of the label kernels and of the rib network
+        # (which then fill the tails), instead of waiting behind them with a static tile split
+        self.cnn_prio = os.environ.get("EITB_CNN_PRIORITY", "1") == "1" and self.overlap
+        self.cnn_s = torch.cuda.Stream(dev, priority=-1) if self.cnn_prio else None
         # K2 and K7 are chains of latency-bound kernels (one CTA per image, a few busy warps): inside their graphs a chunk is
         # cut into ``label_fan`` groups of images whose chains run on parallel branches, so that several stages are
         # resident at once (and the instruction-bound K6 of one group runs beside the K7 of another)
@@ -549,7 +554,7 @@ class SeriesBatchRunner:
                     assert x.data_ptr() == h["x"].data_ptr()
                     self.pre_graphs[st].append(g)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, pool=pools[1]):
+                    with torch.cuda.graph(g, pool=pools[1], **({"stream": self.cnn_s} if self.cnn_prio else {})):
                         head, protos = self.cnn_stage(h["x"], out=(h["head"], h["protos"]))
                     assert head.data_ptr() == h["head"].data_ptr() and protos.data_ptr() == h["protos"].data_ptr()
                     self.cnn_graphs[st].append(g)
@@ -608,9 +613,11 @@ class SeriesBatchRunner:
             self.pre_graphs[st][ci].replay()
             ev_pre = self._event(self.pre_s)
         self.ev_px[ci] = ev_pre
-        main.wait_event(ev_pre)
-        self.cnn_graphs[st][ci].replay()
-        ev_cnn = self._event(main)
+        cnn_s = self.cnn_s if self.cnn_prio else main
+        with torch.cuda.stream(cnn_s):
+            cnn_s.wait_event(ev_pre)
+            self.cnn_graphs[st][ci].replay()
+            ev_cnn = self._event(cnn_s)
         with torch.cuda.stream(self.post_s):
             self.post_s.wait_event(ev_cnn)
             if self.ev_d2h[st][ci] is not None:
@@ -622,7 +629,7 @@ class SeriesBatchRunner:
     def join(self):
         """Make the caller's stream wait for everything the runner has in flight on its own streams."""
         main = torch.cuda.current_stream(self.dev)
-        for st in (self.pre_s, self.post_s, self.copy_out, self.side):
+        for st in (self.pre_s, self.post_s, self.copy_out, self.side) + ((self.cnn_s,) if self.cnn_prio else ()):
             main.wait_stream(st)
 
     def _rib_on_side(self, px, row0=False, after=None, free_running=False):
@@ -645,7 +652,10 @@ class SeriesBatchRunner:
         before reading ``outs`` or the returned table."""
         main = torch.cuda.current_stream(self.dev)
         free = self.overlap and not join
-        sel = self._rib_on_side(self.px, free_running=free)
+        if os.environ.get("EITB_EXPERIMENT_NO_RIB") == "1":        # measurement only: what the per-series decision costs the pass
+            sel = torch.zeros((self.S, 4), dtype=torch.int32, device=self.dev)
+        else:
+            sel = self._rib_on_side(self.px, free_running=free)
         st = self._begin_pass()
         for ci in range(len(self.chunks)):
             if self.overlap:
