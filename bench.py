@@ -365,6 +365,8 @@ def run_b200(args):
         runner.capture()
         return runner, px_host, labels_host
 
+    by_rank = {}
+
     def timed(fn, steps, warmup, finish=None):
         """``finish`` closes what ``fn`` leaves in flight (side streams, the last host pass); it runs inside the timed region."""
         for _ in range(warmup):
@@ -395,6 +397,9 @@ def run_b200(args):
         timer.on = False
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            by_rank["last"] = [float(t) / steps for t in every]   # the reported time is the max; this shows the spread
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, out, timer.totals()
 
@@ -432,6 +437,7 @@ def run_b200(args):
 
     fn_d, fin_d = dev_pass(runner)
     ms_dev, sel, _ = timed(fn_d, args.steps, max(args.warmup, 3), fin_d)
+    ms_dev_by_rank = by_rank.get("last")
     clocks = sampler.stop() if rank == 0 else None
     # eager pass with per-stage and per-kernel CUDA events (same work, no graphs)
     profiling["on"] = True
@@ -735,6 +741,8 @@ def run_b200(args):
                 "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stages.items())},
                 "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1][1])},
                 "selected_slices": sel.cpu().tolist(), "mesh_labelling": mesh}
+        if ms_dev_by_rank:
+            line["ms_per_step_by_rank"] = ms_dev_by_rank
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
