@@ -151,7 +151,14 @@ class DICOMabc(abc.ABC):
             self._dev_last = (code[0], body[0])                      # stay on the device for K13 / K8
             body = body[0].cpu().numpy()
         else:
-            code, body, n = self.pipeline.segment_u8(torch.from_numpy(np.ascontiguousarray(px_or_u8, np.uint8)[None]).to(self.device))
+            img = np.asarray(px_or_u8)
+            if img.ndim == 3 and img.shape[2] >= 3 and not (np.array_equal(img[..., 0], img[..., 1]) and np.array_equal(img[..., 0], img[..., 2])):
+                # a coloured upload: all three channels, BGR -> RGB like ai_tools.py:134
+                code, body, n = self.pipeline.segment_bgr_u8(torch.from_numpy(np.ascontiguousarray(img[..., :3], np.uint8)[None]).to(self.device))
+            else:
+                if img.ndim == 3:
+                    img = img[..., 0]
+                code, body, n = self.pipeline.segment_u8(torch.from_numpy(np.ascontiguousarray(img, np.uint8)[None]).to(self.device))
             self._dev_last = (code[0], None)
         out = code[0].cpu().numpy()
         return out, body, int(n[0]), round(time.time() - t1, 3)
@@ -268,9 +275,7 @@ class ImageToMask(DICOMSequencesToMask):
         """ai_tools.py:365-400: a normalised u8 image; no windowing, no body mask, fixed spacing."""
         answer = []
         try:
-            img = np.asarray(axial_slice_norm_body)
-            if img.ndim == 3:
-                img = img[..., 0]
+            img = np.asarray(axial_slice_norm_body)               # gray, three equal channels, or a coloured BGR image
             code, body, n, t = self._axial_slice_predict(img)
             answer = self._finish(code, None, [0.753906, 0.753906], n, t, mesh)
         except Exception as e:

@@ -188,6 +188,20 @@ class ImagingPipeline:
         return self._segment_nchw(gray.contiguous() if self.fused_input else ops.u8_to_nchw(gray, self.dtype), None)
 
     @torch.no_grad()
+    def segment_bgr_u8(self, bgr: torch.Tensor):
+        """jpg_png route with a genuinely coloured upload: [B,S,S,3] u8 in OpenCV's BGR order.  The reference converts
+        BGR -> RGB and hands all three channels to the model (ai_tools.py:134,153); the three-channel network input
+        takes the generic 27-tap stem instead of the gray one."""
+        x = (bgr.flip(-1).to(torch.float32) / 255).to(self.dtype).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+        S = x.shape[-1]
+        model = self.axial_model_256 if S == 256 else self.axial_model_512
+        head, protos = model(x, gray=False) if self.engine == "eitb" and self.dtype == torch.float16 else model(x)
+        dets, _, n = ops.nms(head.contiguous(), 4, CONF, IOU, MAX_DET, want_idx=False)
+        code, _, _ = ops.mask_decode(dets, n, protos, self.mask_variant)
+        ops.label_cleanup(code, None)
+        return code, None, n
+
+    @torch.no_grad()
     def predict_instances(self, x: torch.Tensor, drop_empty: bool = True):
         """What ``model(img, conf=0.3, imgsz=S)[0]`` holds in the reference (ai_tools.py:153), per image: the kept boxes
         (xyxy, conf, cls) and the per-instance binary masks [n, S, S] u8 -- K5 -> K6 with the per-instance bit masks

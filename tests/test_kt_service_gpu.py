@@ -120,6 +120,16 @@ def test_entry_points(pipe):
     assert ans["status"] == "success" and ans["mesh_data"] == []
     c2, _, _ = pipe.segment_u8(torch.from_numpy(img[None]).cuda())
     assert np.array_equal(ans["label_codes"], c2[0].cpu().numpy())
+    # three equal channels are the same request; a coloured upload goes BGR -> RGB through the three-channel stem
+    # (ai_tools.py:134): on a gray image both stems must agree up to the summation order of the 27 taps
+    ans3 = A.ImageToMask().get_coordinate_slice_from_image(np.repeat(img[..., None], 3, axis=2))
+    assert np.array_equal(ans3["label_codes"], ans["label_codes"])
+    c3, _, _ = pipe.segment_bgr_u8(torch.from_numpy(np.repeat(img[None, ..., None], 3, axis=3)).cuda())
+    assert (c3[0].cpu().numpy() != ans["label_codes"]).mean() <= 2e-3
+    tinted = np.stack([img, img // 2, 255 - img], axis=2)
+    ansc = A.ImageToMask().get_coordinate_slice_from_image(tinted)
+    cc, _, _ = pipe.segment_bgr_u8(torch.from_numpy(tinted[None]).cuda())
+    assert ansc["status"] == "success" and np.array_equal(ansc["label_codes"], cc[0].cpu().numpy())
     nii = A.NIIToMask().get_coordinate_slice_from_nii({"hu": synth.phantom_hu(4).astype(np.int16), "pixel_spacing": [0.7, 0.7]}, mesh=(nodes, tri))
     assert nii["status"] == "success" and nii["polygons"][0] == "0.7"
     assert A.DICOMToMask().get_coordinate_slice_from_dicom_frame(b"not a zip") == []
