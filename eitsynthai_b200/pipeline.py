@@ -273,9 +273,14 @@ class ImagingPipeline:
         res.front_u8, res.rib_boxes, res.n_det = front, boxes[0], ndet
         sel_host = sel.cpu()[0].tolist()                # the one host sync of the series
         res.selected = sel_host[:3] if sel_host[3] else []
+        if not all_slices and res.selected and not all(-N <= i < N for i in res.selected):
+            # the reference indexes the sorted slice list with these numbers (ai_tools.py:177-178): a number past the end
+            # raises there and the request ends with the failure sentinel; a negative one wraps like a Python index
+            logger.error(f"selected slice numbers {res.selected} outside a series of {N} slices")
+            res.selected = []
         if not all_slices and res.selected:
             order = host.instance_order(meta.instance_numbers)
-            idx = [int(order[min(max(i, 0), N - 1)]) for i in res.selected]
+            idx = [int(order[i % N]) for i in res.selected]
             code, body, n = self.segment(px[idx].contiguous(), meta.rescale_slope, meta.rescale_intercept)
             labels, res.body = code, body
             if labels_host is not None:
