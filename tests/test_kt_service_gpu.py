@@ -284,6 +284,14 @@ def test_series_batch_runner_overlapped_passes(pipe):
     assert torch.equal(fast.wait_host(handles[5]), want_sel[2]) and torch.equal(outs[5], want[2])
     fast.join()
     torch.cuda.synchronize()
+    # the label chains cut into parallel graph branches (label_fan), two chunk sizes in one pass
+    fan = SeriesBatchRunner(pipe, [SeriesMeta(inst)], 48, 512, chunk=32, overlap=True, label_fan=3)
+    input_sensitive(fan)
+    fan.load(hosts[1])
+    fan.capture(warm=1)
+    out = torch.zeros((1, 48, 512, 512), dtype=torch.uint8).pin_memory()
+    for k in (1, 2):
+        assert torch.equal(fan.step_host(hosts[k], out), want_sel[k]) and torch.equal(out, want[k])
 
 
 def test_zip_of_dicom_files_end_to_end(pipe):
