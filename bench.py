@@ -471,8 +471,9 @@ def run_b200(args):
     # algorithmic bytes per 512x512 slice and launch; CC passes count source + label traffic
     per_slice_bytes = {
         "hu_window_kernel": px * (2 + 1 + (1 if pipe.fused_input else 6)), "thr_bits_kernel": px * 2 + px // 8, "morph5_bits_kernel": px // 4,
-        "frame_flood_kernel": px // 4, "cc_local_kernel": px // 8 + px * 4, "cc_merge_kernel": 15 * SIZE * 8, "cc_flatten_kernel": px * 8,
-        "area_kernel": px * 4, "best_kernel": px * 8, "write_mask_kernel": px * 5,
+        "frame_flood_kernel": px // 4,
+        # cc_local / cc_merge / cc_flatten / area / best / write_mask: the general body-mask path; its kernels return at once for
+        # the images the dominant-component fast path has answered (all of them here), so bytes per slice would be fiction
         "nms_kernel": 40 * 5376 * 2 + MAX_DET * 38 * 4,
         "mask_decode_kernel": 32 * 128 * 128 * 2 + MAX_DET * 38 * 4 + px,
         "fill_body_kernel": px * 3, "small_first_kernel": px, "small_repaint_kernel": px // 8,
@@ -493,7 +494,10 @@ def run_b200(args):
             ent["frac"] = ent["achieved"] / tf_sustained
         elif per_slice_bytes.get(name):
             # per launch a kernel sees one chunk; K2/K7 sub-kernels run several times per chunk: bytes x launches
-            launches_per_chunk = max(1, round(cnt / args.steps / n_chunks))
+            # (the rib network launches the stem / SPPF / head decode / NMS kernels once more per owned series, on one
+            # image: those launches are not another chunk's worth of bytes)
+            rib_launches = len(runner.mine) if name in ("stem_conv_kernel", "sppf_kernel", "head_decode_kernel", "nms_kernel") else 0
+            launches_per_chunk = max(1, round((cnt / args.steps - rib_launches) / n_chunks))
             ach = per_slice_bytes[name] * local_slices * launches_per_chunk / (per_step / 1e3) / 1e9
             ent.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                         "algorithmic_bytes_per_slice": per_slice_bytes[name]})
