@@ -110,7 +110,7 @@ __device__ __forceinline__ uint16_t unit16_bits(int u, int bf16) {
 
 template <bool NHWC, bool WANT_U8>
 __global__ void __launch_bounds__(kThreads)
-hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int lo, int hi, int rot180,
+hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, long long total_units, int lo, int hi, int rot180,
                    const uint8_t* __restrict__ mask_all, uint8_t* __restrict__ out_u8_all,
                    uint16_t* __restrict__ out_all, int bf16) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -125,28 +125,34 @@ hu_window16_kernel(const int16_t* __restrict__ px_all, int units_per_slice, int 
     }
     __syncthreads();
     const int hw = units_per_slice * 8;
-    const long long b = blockIdx.y;
-    const int16_t* px = px_all + b * hw;
-    const uint8_t* mask = mask_all ? mask_all + b * hw : nullptr;
     const unsigned lo2 = ((unsigned)lo & 0xffffu) | ((unsigned)lo << 16), hi2 = ((unsigned)hi & 0xffffu) | ((unsigned)hi << 16);
-    // two 8-pixel units per trip: both loads (and both mask loads) are issued before any arithmetic
-    const int step = gridDim.x * kThreads;
-    for (int o0 = blockIdx.x * kThreads + threadIdx.x; o0 < units_per_slice; o0 += 2 * step) {
-        int4 raws[2];
-        uint2 mks[2];
-        const int nu = o0 + step < units_per_slice ? 2 : 1;
+    // One flat grid over the 8-pixel units of ALL slices (exactly one resident wave: a (CTAs per slice, slice) grid left
+    // 960 CTAs on 1,184 slots, 7 on some SMs and 6 on others), four units per trip: all four loads (and mask loads) are
+    // issued before any arithmetic -- 96 bytes in flight per thread.
+    constexpr int kUnr = 4;
+    const long long step = (long long)gridDim.x * kThreads;
+    for (long long g0 = (long long)blockIdx.x * kThreads + threadIdx.x; g0 < total_units; g0 += kUnr * step) {
+        int4 raws[kUnr];
+        uint2 mks[kUnr];
+        long long bs[kUnr];
+        int os[kUnr];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u < nu) {
-                const int o = o0 + u * step;
-                raws[u] = ld_stream_int4(reinterpret_cast<const int4*>(px + (rot180 ? hw - 8 - o * 8 : o * 8)));
-                if (mask) mks[u] = ld_stream_uint2(reinterpret_cast<const uint2*>(mask + o * 8));
+        for (int u = 0; u < kUnr; ++u) {
+            const long long g = g0 + u * step;
+            if (g < total_units) {
+                const long long bb = g / units_per_slice;
+                const int oo = (int)(g - bb * units_per_slice);
+                bs[u] = bb; os[u] = oo;
+                raws[u] = ld_stream_int4(reinterpret_cast<const int4*>(px_all + bb * hw + (rot180 ? hw - 8 - oo * 8 : oo * 8)));
+                if (mask_all) mks[u] = ld_stream_uint2(reinterpret_cast<const uint2*>(mask_all + bb * hw + oo * 8));
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u >= nu) break;
-            const int o = o0 + u * step;
+        for (int u = 0; u < kUnr; ++u) {
+            if (g0 + u * step >= total_units) break;
+            const long long b = bs[u];
+            const int o = os[u];
+            const bool mask = mask_all != nullptr;
             const int4 raw = raws[u];
         unsigned w[4];
         if (rot180) {
@@ -215,16 +221,24 @@ int launch_hu16(const int16_t* px, int B, int H, int W, int lo, int hi, int rot1
                 void* out, int bf16, int nhwc, cudaStream_t s) {
     const int ups = H * W / 8;
     const int d = hi - lo;
-    if (B > 65535) return EITB_ERR_UNSUPPORTED;
-    const dim3 grid(eitb_grid_per_image(ups, kThreads, B), B);
     const size_t smem = (size_t)(d + 1) * 3 + 16 + (kThreads / 32) * 96 * sizeof(int4);
+    const long long total = (long long)B * ups;
     eitb_prof_begin("hu_window_kernel", s);
+    auto go = [&](auto kernel) {
+        // one resident wave, and every CTA the same number of four-unit trips (a grid of exactly `cap` CTAs leaves a ragged
+        // last trip: 17.3 units per thread = 4.3 trips on 160 slices)
+        const long long need = (total + kThreads - 1) / kThreads;
+        const long long cap = eitb_resident_ctas(kernel, kThreads, smem);
+        const long long trips = (need + cap * 4 - 1) / (cap * 4);
+        const long long grid = (need + trips * 4 - 1) / (trips * 4);
+        kernel<<<(int)grid, kThreads, smem, s>>>(px, ups, total, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
+    };
     if (nhwc) {
-        if (out_u8) hu_window16_kernel<true, true><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
-        else hu_window16_kernel<true, false><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
+        if (out_u8) go(hu_window16_kernel<true, true>);
+        else go(hu_window16_kernel<true, false>);
     } else {
-        if (out_u8) hu_window16_kernel<false, true><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
-        else hu_window16_kernel<false, false><<<grid, kThreads, smem, s>>>(px, ups, lo, hi, rot180, mask, out_u8, (uint16_t*)out, bf16);
+        if (out_u8) go(hu_window16_kernel<false, true>);
+        else go(hu_window16_kernel<false, false>);
     }
     EITB_CHECK_LAUNCH();
     return EITB_OK;
