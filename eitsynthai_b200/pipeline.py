@@ -403,6 +403,7 @@ class SeriesBatchRunner:
         self.ev_post = [[None] * nch for _ in range(2)]           # per set: the label kernels have read body / head / prototypes
         self.ev_d2h = [[None] * nch for _ in range(2)]            # per set: the copy-out has read the label image
         self._passes, self._last_set = 0, 0
+        self._sel_ring, self._submitted = [], 0
 
     # ---------------------------------------------------------------- stages
     def _fan(self, n: int, fn, enabled: bool):
@@ -689,8 +690,9 @@ class SeriesBatchRunner:
         """Enqueue one pass from pinned host memory and return a handle for ``wait_host``; nothing blocks the host, so
         a caller that keeps two passes in flight (two ``labels_host`` buffers) overlaps the copies of one pass with
         the kernels of the other.  px_host [S, n_local, H, W] int16 pinned, labels_host [S, n_local, H, W] u8 pinned
-        (file order).  ``wait_host`` (or ``join()`` + a device synchronise) before switching to ``step_device``: the
-        resident-pixel path does not wait for copies that are still in flight."""
+        (file order).  At most eight passes may be between ``submit_host`` and ``wait_host`` (the selected-slice tables
+        are eight pinned buffers used in turn).  ``wait_host`` (or ``join()`` + a device synchronise) before switching to
+        ``step_device``: the resident-pixel path does not wait for copies that are still in flight."""
         main = torch.cuda.current_stream(self.dev)
         flat_host = px_host.view(self.S * self.nl, self.size, self.size)
         flat_out = labels_host.view(self.S * self.nl, self.size, self.size)
@@ -731,7 +733,11 @@ class SeriesBatchRunner:
                 self.ev_d2h[st][ci] = self._event(self.copy_out)
             code.record_stream(self.copy_out)
         # the selected-slice table travels last on the copy-out stream: its event closes the pass
-        sel_host = torch.empty((self.S, 4), dtype=torch.int32, pin_memory=True)   # cached pinned allocation, one per pass
+        # one of eight pinned tables in turn: a caller may have up to eight passes between submit_host and wait_host
+        if not self._sel_ring:
+            self._sel_ring = [torch.empty((self.S, 4), dtype=torch.int32, pin_memory=True) for _ in range(8)]
+        sel_host = self._sel_ring[self._submitted % len(self._sel_ring)]
+        self._submitted += 1
         self.copy_out.wait_stream(self.side)
         with torch.cuda.stream(self.copy_out):
             sel_host.copy_(sel, non_blocking=True)
