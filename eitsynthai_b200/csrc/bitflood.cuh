@@ -18,7 +18,7 @@
 
 namespace eitb_flood {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 8;
 
 enum Src { SRC_U8_NE = 0, SRC_BITS_ZERO = 1, SRC_U8_EQ = 2 };
 
