@@ -226,8 +226,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     budget = float(os.environ.get("EITB_REF_BUDGET_S", "120"))    # whole run, all steps; bounded so the arm ends in minutes
     rate, kind, sample, ms = cpu_path_rate(budget, threads, max(args.steps, 1), min(args.warmup, 1), args.slices)
-    cfg = config(args.gpus, args.series, args.slices)
-    cfg["sample"] = sample
+    cfg = config(args.gpus, args.series, args.slices)             # the same object as the b200 arm's; the sample is in cpu_baseline
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -735,10 +734,12 @@ def run_b200(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "strong" if (args.series and args.series < world) else "weak",
                 "vs_baseline": None, "dtype": "f16 (CNN, fp32 accumulate) / int16,u8,f32,f64 (kernels)", "data": "synthetic",
-                "config": dict(config(world, S, nslices), chunk=args.chunk, engine=args.engine, class_bias_shift=pipe.bias_shift,
-                               mean_detections_per_slice=ndet_mean, cuda_graphs=not args.no_graphs,
-                               overlap=runner_overlap, label_fan=args.label_fan,
-                               cpu_affinity_first_last_count=cpu_affinity),
+                # `config` names the workload and is the same object in both arms (--impl reference); how THIS arm ran it
+                # is under `run`
+                "config": config(world, S, nslices),
+                "run": dict(chunk=args.chunk, engine=args.engine, class_bias_shift=pipe.bias_shift,
+                            mean_detections_per_slice=ndet_mean, cuda_graphs=not args.no_graphs,
+                            overlap=runner_overlap, label_fan=args.label_fan, cpu_affinity_first_last_count=cpu_affinity),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roof, "cpu_baseline": cpu,
                 "roofline_kernels": kroof, "conv_work_per_step": {k: v for k, v in conv_stats.items() if k != "by_kind"},
                 "eager_profiled_ms_per_step": ms_eager,
